@@ -1,0 +1,111 @@
+"""Parity of the CUDA explore path (through the C ABI) with the CPU oracle."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+GENOME = b"AACCTAACCTAACATATCGTAACCTAACCTAACCTAACCTAACATATCGTAACCTAACCT"
+GENOME_2 = b"AACCTAACCTTAAATTAAATAACCTAACCTAACCTAACCTTAAATTAAATAACCTAACCT"
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import telomeric_identifier_b200 as T
+    c = T.Context(0)
+    yield c
+    c.close()
+
+
+def _runs_equal(ctx, seq, off, d, kmin, kmax, thr):
+    from telomeric_identifier_b200.explore import run_labels
+    got = ctx.explore_runs(seq, off, d, kmin, kmax, thr)
+    want, wlabels = O.explore_runs(seq, off, d, kmin, kmax, thr, period_filter=False)
+    assert got.size == want.size, (got.size, want.size)
+    for f in ("record", "slice", "k", "first", "start", "end"):
+        assert (got[f] == want[f]).all(), f
+    assert run_labels(seq, off, d, got) == wlabels
+
+
+def test_reference_golden_index_left(ctx):  # explore.rs:592-612
+    seq = np.frombuffer(GENOME, dtype=np.uint8)
+    runs = ctx.explore_runs(seq, np.array([0, seq.size], dtype=np.uint64), 0.5, 5, 5, 0)
+    left = runs[runs["slice"] == 0]
+    assert [(int(a), int(b)) for a, b in zip(left["start"], left["end"])] == [(0, 10), (20, 30)]
+    right = runs[runs["slice"] == 1]
+    assert [(int(a), int(b)) for a, b in zip(right["start"], right["end"])] == [(0, 10), (20, 30)]
+
+
+def test_reference_golden_estimates(ctx):  # explore.rs:622-626 (left half of GENOME_2 alone)
+    import telomeric_identifier_b200 as T
+    seq = np.frombuffer(GENOME_2[:30], dtype=np.uint8)
+    off = np.array([0, seq.size], dtype=np.uint64)
+    runs = ctx.explore_runs(seq, off, 0.5, 5, 5, 0)
+    # d = 0.5 on a 30-mer gives two 15-base slices; use the explicit one-slice form instead
+    from telomeric_identifier_b200.hostlogic import estimates
+    seq60 = np.frombuffer(GENOME_2, dtype=np.uint8)
+    runs = ctx.explore_runs(seq60, np.array([0, 60], dtype=np.uint64), 0.5, 5, 5, 0)
+    left = runs[runs["slice"] == 0]
+    labels = [GENOME_2[int(p):int(p) + 5] for p in left["label_pos"]]
+    counts = [(int(e) - int(s)) // 5 for s, e in zip(left["start"], left["end"])]
+    assert labels == [b"AACCT", b"TAAAT", b"AACCT"]
+    assert estimates(labels, counts) == [(b"AACCT", 4)]
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_runs(ctx, seed):
+    from telomeric_identifier_b200 import synth
+    rng = np.random.default_rng(seed)
+    alphabet = [b"ACGT", b"ACGTacgt", b"AC", b"ACGTN", b"Aa", b"ACGTNRYacgtn"][seed % 6]
+    unit = bytes(rng.choice(list(b"ACGT"), size=int(rng.integers(2, 9))).tolist())
+    ids, seq, off = synth.random_records(100 + seed, int(rng.integers(1, 6)), 200000 if seed % 4 == 0 else 5000,
+                                         alphabet, plant=unit, p_empty=0.15)
+    d = [0.5, 0.1, 0.01, 0.33][seed % 4]
+    thr = [0, 0, 1, 3, 100][seed % 5]
+    kmin = int(rng.integers(1, 7))
+    _runs_equal(ctx, seq, off, d, kmin, kmin + int(rng.integers(0, 6)), thr)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_explore_table_vs_oracle(ctx, seed):
+    import telomeric_identifier_b200 as T
+    from telomeric_identifier_b200 import synth
+    ids, seq, off = synth.random_records(300 + seed, 4, 20000, b"ACGTacgt" if seed % 2 else b"ACGT",
+                                         plant=[b"TTAGGG", b"AACCT", b"TTTAGGG", b"AACCCTG"][seed % 4])
+    thr = [0, 2, 10, 50][seed % 4]
+    rows = T.explore_table(ctx, seq, off, 0, 4, 9, thr, 0.5)
+    seqs = [seq[int(off[i]):int(off[i + 1])].tobytes() for i in range(len(ids))]
+    want = O.explore_text(seqs, 0.5, 4, 9, thr, literal=(thr >= 2)).splitlines()[1:]
+    assert [f"{k.decode()}\t{c}" for k, c in rows] == want
+
+
+def test_config3_scaled(ctx):
+    import telomeric_identifier_b200 as T
+    from telomeric_identifier_b200 import synth
+    ids, seq, off = synth.config2(scale=0.02)
+    _runs_equal(ctx, seq, off, 0.01, 5, 12, 100)
+    _runs_equal(ctx, seq, off, 0.05, 5, 12, 20)
+    rows = T.explore_table(ctx, seq, off, 0, 5, 12, 20, 0.05)
+    seqs = [seq[int(off[i]):int(off[i + 1])].tobytes() for i in range(len(ids))]
+    want = O.explore_text(seqs, 0.05, 5, 12, 20, literal=True).splitlines()[1:]
+    assert [f"{k.decode()}\t{c}" for k, c in rows] == want
+    assert any(k == b"AACCT" for k, _ in rows)
+
+
+def test_config5_scaled(ctx):
+    from telomeric_identifier_b200 import synth
+    ids, seq, off = synth.config5(n_reads=3000)
+    _runs_equal(ctx, seq, off, 0.5, 5, 12, 100)
+
+
+def test_explore_errors(ctx):
+    import telomeric_identifier_b200 as T
+    seq = np.frombuffer(b"ACGT" * 50, dtype=np.uint8)
+    off = np.array([0, seq.size], dtype=np.uint64)
+    with pytest.raises(T.TidkCudaError) as e:
+        ctx.explore_runs(seq, off, 0.6, 5, 12, 100)
+    assert e.value.code == -1
+    with pytest.raises(T.TidkCudaError):
+        ctx.explore_runs(seq, off, 0.1, 0, 3, 100)
+    assert ctx.explore_runs(np.zeros(0, np.uint8), np.array([0], dtype=np.uint64), 0.1, 5, 12, 100).size == 0

@@ -1,0 +1,199 @@
+"""Parity of the CUDA window counter (through the C ABI) with the CPU oracle.
+Bit-exact: every output is an integer count."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import telomeric_identifier_b200 as T
+    c = T.Context(0)
+    yield c
+    c.close()
+
+
+def _cmp(ctx, seq, off, W, queries, upper=False):
+    qs = [q.upper() for q in queries] if upper else list(queries)
+    f, r = ctx.window_counts(seq, off, W, qs)
+    of, orr = O.window_counts(seq, off, W, qs, False)
+    assert f.shape == of.shape
+    bad = np.flatnonzero((f != of) | (r != orr))
+    assert bad.size == 0, f"W={W} q={qs}: first mismatch at {bad[:5]} got {f[bad[:5]]},{r[bad[:5]]} want {of[bad[:5]]},{orr[bad[:5]]}"
+
+
+def test_reference_golden_search(ctx):  # search.rs:183-199
+    import telomeric_identifier_b200 as T
+    seq = np.frombuffer(b"TTAGGTTAGGTTAGGCAGCATCACACTGATCATCTGATTAGGTTAGGTTAGG", dtype=np.uint8)
+    off = np.array([0, seq.size], dtype=np.uint64)
+    rows = T.search_rows(ctx, ["test1"], seq, off, "TTAGG", 20).splitlines()
+    assert rows == ["test1\t20\t3\t0\tTTAGG", "test1\t40\t0\t0\tTTAGG", "test1\t52\t2\t0\tTTAGG"]
+    bed = T.search_rows(ctx, ["test1"], seq, off, "ttagg", 20, "bedgraph").splitlines()
+    assert bed == ["test1\t0\t20\t3", "test1\t20\t40\t0", "test1\t40\t52\t2"]
+
+
+def test_reference_golden_finder(ctx):  # finder.rs:213-235
+    import telomeric_identifier_b200 as T
+    seq = np.frombuffer(b"AAACCCTAAACCCTAAACCCTTGAGAGAGGGGGTGTGGGGAGGGGTTGAGAAACCCT", dtype=np.uint8)
+    off = np.array([0, seq.size], dtype=np.uint64)
+    rows = T.finder_rows(ctx, ["test1"], seq, off, ["AAACCCT"], 20).splitlines()
+    assert rows == ["test1\t20\t2\t0\tAAACCCT", "test1\t40\t0\t0\tAAACCCT", "test1\t57\t1\t0\tAAACCCT"]
+
+
+def test_reference_golden_motifs1(ctx):  # utils.rs:231-238, as a one-window count
+    hay = np.frombuffer(b"AACCTAACCTAACCTAACCTAACCTAACCTAACTAACCT", dtype=np.uint8)
+    f, r = ctx.window_counts(hay, np.array([0, hay.size], dtype=np.uint64), 1000, [b"AACCT"])
+    assert (int(f[0]), int(r[0])) == (7, 0)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_batches(ctx, seed):
+    from telomeric_identifier_b200 import synth
+    rng = np.random.default_rng(seed)
+    alphabet = [b"ACGT", b"ACGTacgt", b"ACGTNacgtn", b"ACGTNRYKMSWBDHVacgtn-*.", b"AT", b"A"][seed % 6]
+    L = int(rng.integers(1, 13))
+    q = bytes(rng.choice(list(b"ACGT"), size=L).tolist())
+    if seed % 5 == 0:
+        q = q[:1] * L  # self-overlapping
+    ids, seq, off = synth.random_records(seed, int(rng.integers(1, 6)), 30000, alphabet, plant=q, p_empty=0.2)
+    for W in [int(rng.integers(1, 40)), int(rng.integers(40, 2000)), 10000, int(rng.integers(33000, 80000))]:
+        if W < 8 and seq.size > 20000:
+            continue
+        _cmp(ctx, seq, off, W, [q])
+
+
+@pytest.mark.parametrize("W", [1, 2, 31, 32, 33, 1000, 1024, 1056, 10000, 32768, 32769, 65537, 200000])
+def test_window_alignments(ctx, W):
+    from telomeric_identifier_b200 import synth
+    ids, seq, off = synth.random_records(7, 4, 150000, b"ACGTacgtN", plant=b"TTAGGG")
+    if W < 4:
+        seq, off = seq[:4000].copy(), np.array([0, 1500, 1500, 4000], dtype=np.uint64)
+    _cmp(ctx, seq, off, W, [b"TTAGGG"])
+    _cmp(ctx, seq, off, W, [b"CCCTAA", b"TTAGG"])
+
+
+def test_multi_query_mixed_paths(ctx):
+    """Hymenoptera-like table (lengths 5..14), a lower-case repeat (never matches, finder.rs:129),
+    a query with N (literal compare), a 40-mer (beyond the plane kernel) and a 70-mer (BOM branch)."""
+    from telomeric_identifier_b200 import synth
+    ids, seq, off = synth.random_records(11, 3, 60000, b"ACGTNacgt", plant=b"TTAGGTTGGG")
+    long40 = bytes(seq[100:140]).upper()
+    long70 = bytes(seq[500:570]).upper()
+    qs = [b"AACCT", b"AACCC", b"AACCCT", b"AACCCAGACGC", b"AACCCAGACCC", b"AACCCCAACCT", b"AACCCAGACCT",
+          b"AACCCTAACCTAAC", b"TTAGGTTGGG", b"aacct", b"TTANG", b"NN", long40, long70]
+    _cmp(ctx, seq, off, 10000, qs)
+    _cmp(ctx, seq, off, 777, qs[:9])
+    _cmp(ctx, seq, off, 50000, qs)
+
+
+def test_search_uppercases_query_find_does_not(ctx):
+    import telomeric_identifier_b200 as T
+    seq = np.frombuffer(b"ttaggTTAGGttagg" * 10, dtype=np.uint8)
+    off = np.array([0, seq.size], dtype=np.uint64)
+    assert T.search_rows(ctx, ["a"], seq, off, "ttagg", 1000) == O.search_text(["a"], [seq.tobytes()], b"ttagg", 1000)[len(O.SEARCH_HEADER):]
+    assert T.finder_rows(ctx, ["a"], seq, off, ["ttagg", "TTAGG"], 1000) == O.find_text(["a"], [seq.tobytes()], [b"ttagg", b"TTAGG"], 1000)[len(O.SEARCH_HEADER):]
+
+
+def test_long_pattern_up_to_32(ctx):
+    from telomeric_identifier_b200 import synth
+    ids, seq, off = synth.random_records(3, 2, 50000, b"ACGT")
+    for L in [13, 16, 17, 31, 32]:
+        q = bytes(seq[1000:1000 + L])
+        seq[5000:5000 + L] = seq[1000:1000 + L]
+        _cmp(ctx, seq, off, 10000, [q])
+        _cmp(ctx, seq, off, 4999, [q])
+
+
+def test_errors(ctx):
+    import telomeric_identifier_b200 as T
+    seq = np.frombuffer(b"ACGT" * 100, dtype=np.uint8).copy()
+    off = np.array([0, seq.size], dtype=np.uint64)
+    with pytest.raises(T.TidkCudaError) as e:
+        ctx.window_counts(seq, off, 0, [b"ACG"])
+    assert e.value.code == -1
+    with pytest.raises(T.TidkCudaError) as e:
+        ctx.window_counts(seq, off, 10, [b""])
+    assert e.value.code == -1
+    seq[57] = 0xC3
+    with pytest.raises(T.TidkCudaError) as e:
+        ctx.window_counts(seq, off, 64, [b"ACG"])
+    assert e.value.code == -4
+    with pytest.raises(O.OracleError):
+        O.window_counts(seq, off, 64, [b"ACG"], False)
+    # the ctx stays usable after an error
+    seq[57] = ord("A")
+    _cmp(ctx, seq, off, 64, [b"ACG"])
+
+
+def test_empty_inputs(ctx):
+    f, r = ctx.window_counts(np.zeros(0, np.uint8), np.array([0], dtype=np.uint64), 100, [b"ACG"])
+    assert f.size == 0 and r.size == 0
+    f, r = ctx.window_counts(np.zeros(0, np.uint8), np.array([0, 0, 0], dtype=np.uint64), 100, [b"ACG"])
+    assert f.size == 0
+
+
+def test_resident_matches_host_path(ctx):
+    from telomeric_identifier_b200 import synth
+    ids, seq, off = synth.config2(scale=0.004)
+    b = ctx.upload(seq, off)
+    f1, r1 = ctx.window_counts_resident(b, 10000, [b"AACCT"])
+    assert ctx.last_kernel_launches == 1 and ctx.last_kernel_ms > 0
+    f2, r2 = ctx.window_counts(seq, off, 10000, [b"AACCT"])
+    of, orr = O.window_counts(seq, off, 10000, [b"AACCT"], False)
+    assert (f1 == of).all() and (r1 == orr).all() and (f2 == of).all() and (r2 == orr).all()
+    assert int(of.sum()) > 0 and int(orr.sum()) > 0
+    b.free()
+
+
+@pytest.mark.parametrize("cfg", ["config1", "config2", "config4"])
+def test_configs_scaled_text_identical(ctx, cfg):
+    """BASELINE configs at reduced scale: full output text byte-identical to the oracle's."""
+    import telomeric_identifier_b200 as T
+    from telomeric_identifier_b200 import synth
+    ids, seq, off = getattr(synth, cfg)(scale=0.01)
+    seqs = [seq[int(off[i]):int(off[i + 1])].tobytes() for i in range(len(ids))]
+    if cfg == "config1":
+        for ext in ("tsv", "bedgraph"):
+            got = T.search_rows(ctx, ids, seq, off, "TTAGG", 10000, ext)
+            want = O.search_text(ids, seqs, b"TTAGG", 10000, ext)
+            assert got == (want[len(O.SEARCH_HEADER):] if ext == "tsv" else want)
+    elif cfg == "config2":
+        hymenoptera = ["AACCT", "AACCC", "AACCCT", "AACCCAGACGC", "AACCCAGACCC", "AACCCCAACCT"]
+        for reps in (["AACCT"], hymenoptera):
+            got = T.finder_rows(ctx, ids, seq, off, reps, 10000)
+            assert got == O.find_text(ids, seqs, [r.encode() for r in reps], 10000)[len(O.SEARCH_HEADER):]
+    else:
+        got = T.search_rows(ctx, ids, seq, off, "TTAGGG", 10000)
+        assert got == O.search_text(ids, seqs, b"TTAGGG", 10000)[len(O.SEARCH_HEADER):]
+
+
+def test_full_size_properties(ctx):
+    """BASELINE config 2 at full size (500 Mb): size-independent properties instead of the oracle.
+    (a) swapping the query for its reverse complement swaps fwd and rev;
+    (b) counts with W are >= 0 and the sum over windows with W = 2W' never exceeds ... (monotone):
+        every occurrence counted at W' = 5000 is also inside a W = 10000 window, so
+        sum(W=10000) >= sum(W=5000), and the difference is the number of occurrences that
+        straddle the extra boundaries;
+    (c) a window-aligned sub-range recomputed alone gives the same counts (oracle-checked)."""
+    from telomeric_identifier_b200 import synth
+    ids, seq, off = synth.config2(scale=1.0)
+    b = ctx.upload(seq, off)
+    f, r = ctx.window_counts_resident(b, 10000, [b"AACCT"])
+    f2, r2 = ctx.window_counts_resident(b, 10000, [b"AGGTT"])
+    assert (f == r2).all() and (r == f2).all()
+    f5, r5 = ctx.window_counts_resident(b, 5000, [b"AACCT"])
+    assert int(f.sum()) >= int(f5.sum()) and int(r.sum()) >= int(r5.sum())
+    assert int(f.sum()) - int(f5.sum()) < f5.size
+    # chromosome 7, windows 100..140 against the oracle
+    o7 = int(off[7])
+    sub = seq[o7 + 100 * 10000: o7 + 140 * 10000]
+    of, orr = O.window_counts(sub, np.array([0, sub.size], dtype=np.uint64), 10000, [b"AACCT"], False)
+    nw = ((off[1:] - off[:-1] + np.uint64(9999)) // np.uint64(10000)).astype(np.int64)
+    base = int(nw[:7].sum())
+    assert (f[base + 100: base + 140] == of).all() and (r[base + 100: base + 140] == orr).all()
+    # the planted telomere arrays are seen at both ends of chromosome 1
+    assert int(f[0]) > 100 and int(r[int(nw[0]) - 1]) > 100
+    b.free()
