@@ -4,9 +4,13 @@
 // into 32-bit planes, bit b <-> base b (LSB = lowest address):
 //   lo = ASCII bit 1, hi = ASCII bit 2   (A=00 C=01 G=11 T=10 as (hi,lo); case-blind;
 //                                         complement == flip hi)
-//   va = byte is one of A C G T a c g t  (everything else never matches an A/C/G/T query,
-//                                         which is the reference's rule: the window is
-//                                         upper-cased and compared bytewise, search.rs:107-110)
+//   b0 = ASCII bit 0                      (1 for A/C/G, 0 for T)
+//   ok = all ones on the fast path; on the exact path the positions whose other
+//        ASCII bits are consistent with a letter of {A,C,G,T,a,c,g,t}
+// A base is one of A C G T a c g t  <=>  ok & (b0 ^ (hi & ~lo)).  Everything else
+// (N, IUPAC codes, gaps, ...) never matches an A/C/G/T query, which is the
+// reference's rule: the window is upper-cased and compared bytewise
+// (search.rs:107-110, finder.rs:146-149).
 //
 // How a plane is formed.  Two words wa (bases 0-3) and wb (bases 4-7) are merged
 // into nibble words  X = low nibbles, Y = high nibbles  (one shift + one LOP3
@@ -16,11 +20,11 @@
 // carries).  Four such bytes are combined with three PRMT.  IMAD runs on the fma
 // pipe, LOP3/SHF/PRMT on the alu pipe, so the two halves of the work overlap.
 //
-// Validity costs five more ASCII bits (0,3,4,6,7).  Three of them are constant
-// over the valid set and b4 == !b0 on it, so they are checked in aggregate on
-// the nibble words (AND/OR accumulators, no extraction); only b0 is extracted,
-// and  va = b0 ^ (hi & ~lo).  If the aggregate test fails for any lane of the
-// warp (N runs, IUPAC codes, anything else) the exact planes are built instead.
+// Validity needs five more ASCII bits (0,3,4,6,7).  b7=0, b6=1, b3=0 are constant
+// over the valid set and b4 == !b0 on it, so those four are checked in aggregate
+// on the nibble words (AND/OR accumulators, no extraction); only b0 is
+// extracted.  If the aggregate test fails for any lane of the warp (N runs,
+// IUPAC codes, anything else) the exact `ok` plane is built from four more planes.
 #pragma once
 #include <cstdint>
 
@@ -33,11 +37,18 @@ __device__ __forceinline__ void ld256_stream(const void *p, uint32_t (&w)[8]) {
                  : "l"(p));
 }
 
+// (a & m) | (b & ~m) in one LOP3
+__device__ __forceinline__ uint32_t bitsel(uint32_t m, uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(r) : "r"(m), "r"(a), "r"(b));
+    return r;
+}
+
 __host__ __device__ constexpr uint32_t gather_mul(int o) {
     return (1u << (24 - o)) | (1u << (17 - o)) | (1u << (10 - o)) | (1u << (3 - o));
 }
 
-// bit `o` of each of the 32 nibbles held in N[0..3] (8 nibbles per word) -> 32-bit plane
+// bit `O` of each of the 32 nibbles held in N[0..3] (8 nibbles per word) -> 32-bit plane
 template <int O>
 __device__ __forceinline__ uint32_t nibble_plane(const uint32_t (&N)[4]) {
     constexpr uint32_t M = 0x11111111u << O;
@@ -49,47 +60,67 @@ __device__ __forceinline__ uint32_t nibble_plane(const uint32_t (&N)[4]) {
     return __byte_perm(__byte_perm(p0, p1, 0x7373), __byte_perm(p2, p3, 0x7373), 0x5410);
 }
 
-struct Planes {
-    uint32_t lo, hi, va;
+struct Nibbles {
+    uint32_t X[4], Y[4]; // low / high nibbles of 32 bases, 8 per word
 };
 
-// w: 32 sequence bytes.  nonascii is OR-ed with a non-zero value if any byte >= 0x80.
-__device__ __forceinline__ Planes extract_planes(const uint32_t (&w)[8], uint32_t &nonascii) {
-    uint32_t X[4], Y[4];
-    uint32_t accA = 0xFFFFFFFFu, accO = 0u, accB = 0xFFFFFFFFu;
+__device__ __forceinline__ Nibbles to_nibbles(const uint32_t (&w)[8]) {
+    Nibbles n;
 #pragma unroll
     for (int g = 0; g < 4; g++) {
         uint32_t wa = w[2 * g], wb = w[2 * g + 1];
-        X[g] = (wa & 0x0F0F0F0Fu) | ((wb << 4) & 0xF0F0F0F0u);
-        Y[g] = ((wa >> 4) & 0x0F0F0F0Fu) | (wb & 0xF0F0F0F0u);
-        accA &= X[g] ^ Y[g]; // nibble bit 0: b0 ^ b4 must be 1
-        accO |= X[g] | Y[g]; // nibble bit 3: b3 | b7 must be 0
-        accB &= Y[g];        // nibble bit 2: b6 must be 1
+        n.X[g] = bitsel(0x0F0F0F0Fu, wa, wb << 4);
+        n.Y[g] = bitsel(0x0F0F0F0Fu, wa >> 4, wb);
     }
-    uint32_t bad = (~accA & 0x11111111u) | (accO & 0x88888888u) | (~accB & 0x44444444u);
+    return n;
+}
+
+struct Planes {
+    uint32_t lo, hi, b0, ok;
+    bool exact; // warp-uniform: ok is not all ones
+};
+
+// nonascii is OR-ed with a non-zero value if any byte >= 0x80 (exact path only:
+// such a byte always fails the aggregate test).
+__device__ __forceinline__ Planes extract_planes(const Nibbles &n, uint32_t &nonascii) {
+    uint32_t accA = 0xFFFFFFFFu, accO = 0u, accB = 0xFFFFFFFFu;
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        accA &= n.X[g] ^ n.Y[g]; // nibble bit 0: b0 ^ b4 must be 1
+        accO |= n.X[g] | n.Y[g]; // nibble bit 3: b3 | b7 must be 0
+        accB &= n.Y[g];          // nibble bit 2: b6 must be 1
+    }
+    const uint32_t bad = (~accA & 0x11111111u) | (accO & 0x88888888u) | (~accB & 0x44444444u);
     Planes P;
-    P.lo = nibble_plane<1>(X);
-    P.hi = nibble_plane<2>(X);
-    uint32_t b0 = nibble_plane<0>(X);
-    uint32_t t = P.hi & ~P.lo; // looks like T in (b2,b1)
-    if (__any_sync(0xFFFFFFFFu, bad != 0)) {
-        // exact validity: b7=0, b6=1, b3=0, b4=!b0, b0=!(b2&!b1)
-        uint32_t b3 = nibble_plane<3>(X);
-        uint32_t b4 = nibble_plane<0>(Y);
-        uint32_t b6 = nibble_plane<2>(Y);
-        uint32_t b7 = nibble_plane<3>(Y);
+    P.lo = nibble_plane<1>(n.X);
+    P.hi = nibble_plane<2>(n.X);
+    P.b0 = nibble_plane<0>(n.X);
+    P.ok = 0xFFFFFFFFu;
+    P.exact = __any_sync(0xFFFFFFFFu, bad != 0);
+    if (P.exact) {
+        uint32_t b3 = nibble_plane<3>(n.X);
+        uint32_t b4 = nibble_plane<0>(n.Y);
+        uint32_t b6 = nibble_plane<2>(n.Y);
+        uint32_t b7 = nibble_plane<3>(n.Y);
         nonascii |= b7;
-        P.va = ~b7 & b6 & ~b3 & (b4 ^ b0) & (b0 ^ t);
-    } else {
-        P.va = b0 ^ t;
+        P.ok = ~b7 & b6 & ~b3 & (b4 ^ P.b0);
     }
     return P;
 }
 
-// prev[lane] = lane > 0 ? cur[lane-1] : carry_from_previous_block[31]
+// prev[lane] = lane > 0 ? cur[lane-1] : (this lane 31's value from the previous block)
 __device__ __forceinline__ uint32_t lane_lookbehind(uint32_t cur, uint32_t old, int lane) {
     uint32_t x = (lane == 31) ? old : cur;
     return __shfl_sync(0xFFFFFFFFu, x, (lane + 31) & 31);
+}
+
+// bits b in [0,32) with lo_rel <= b < hi_rel
+__device__ __forceinline__ uint32_t range_mask32(int lo_rel, int hi_rel) {
+    if (hi_rel <= 0 || lo_rel >= 32 || hi_rel <= lo_rel) return 0u;
+    uint32_t m = 0xFFFFFFFFu;
+    if (lo_rel > 0) m <<= lo_rel;
+    if (hi_rel < 32) m &= 0xFFFFFFFFu >> (32 - hi_rel);
+    return m;
 }
 
 } // namespace tidk

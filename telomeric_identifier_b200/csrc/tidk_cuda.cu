@@ -36,6 +36,7 @@ struct tidk_seqbuf {
     std::vector<uint64_t> h_off;
     uint32_t n_records = 0;
     uint64_t total = 0;
+    uint64_t id = 0; // changes whenever the contents change (invalidates ctx-side caches)
 };
 
 struct tidk_ctx {
@@ -45,8 +46,13 @@ struct tidk_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
     tidk_seqbuf scratch; // staging for the host-pointer entry points
-    DevBuf win_base, out_fwd, out_rev, misc, qbytes, runs;
+    DevBuf win_base, out_fwd, out_rev, misc, qbytes, runs, items;
     ExploreScratch ex;
+    uint64_t next_buf_id = 1;
+    // work items cached for (sequence batch, window, query count): several clades or output
+    // formats over one uploaded genome reuse them
+    uint64_t items_buf_id = 0, items_window = 0, items_n = 0, items_nwin = 0;
+    uint32_t items_nq = 0;
 };
 
 namespace {
@@ -113,6 +119,7 @@ int seqbuf_fill(tidk_ctx *ctx, tidk_seqbuf *b, const uint8_t *seq, const uint64_
     if (n_records) b->h_off.assign(offsets, offsets + n_records + 1);
     b->n_records = n_records;
     b->total = total;
+    b->id = ctx->next_buf_id++;
     if (total) CU(ctx, cudaMemcpyAsync(b->d_seq, seq, total, cudaMemcpyHostToDevice, ctx->stream));
     CU(ctx, cudaMemsetAsync(b->d_seq + total, 0, kSeqPad, ctx->stream));
     CU(ctx, cudaMemcpyAsync(b->d_off, b->h_off.data(), off_need, cudaMemcpyHostToDevice, ctx->stream));
@@ -149,20 +156,65 @@ StrandPattern encode_strand(const uint8_t *pat, uint32_t L) {
     return sp;
 }
 
-template <int L>
-void launch_fixed(const WindowJob &job, const FastQueries &fq, int grid, cudaStream_t st) {
-    window_counts_planes_kernel<L><<<grid, kWarpsPerBlock * 32, 0, st>>>(job, fq);
+// ---- kernels specialised at compile time for known motifs ---------------------
+// Every repeat of the curated clade table (clades/curated.csv, 23 motifs) plus the
+// forms people type at `tidk search` (TTAGG, TTAGGG, ...).  A query whose reverse
+// complement is listed uses that kernel with the two outputs swapped.  Anything
+// else runs the run-time-pattern kernel.
+#define TIDK_STATIC_MOTIFS(X)                                                                   \
+    X("AAGGAC") X("AACCCT") X("AAACCCT") X("AACCC") X("AACCT") X("AACAGACCCG") X("ACCTG")       \
+    X("AAACCACCCT") X("AACCATCCCT") X("AACCCAGACCT") X("AACCCCAACCT") X("AACCCGAACCT")          \
+    X("ACCCAG") X("ACGGCAGCG") X("AAATGTGGAGG") X("AAAGAACCT") X("AAAATTGTCCGTCC") X("AAACCC")  \
+    X("AACCCAGACCC") X("AACCCAGACGC") X("AACCCTGACGC") X("AAACCCC") X("AACCCTG")                \
+    X("TTAGG") X("TTAGGG") X("TTTAGGG") X("CCCTAA") X("CCTAA") X("TTGGGG") X("TTAGGC")
+
+constexpr int cx_len(const char *s) { int n = 0; while (s[n]) n++; return n; }
+constexpr uint64_t cx_code(char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : 3; }
+constexpr uint64_t cx_enc(const char *s) {
+    uint64_t f = 0;
+    for (int j = 0; s[j]; j++) f |= cx_code(s[j]) << (2 * j);
+    return f;
 }
 
-void launch_planes(int L, const WindowJob &job, const FastQueries &fq, int grid, cudaStream_t st) {
+using LaunchFn = void (*)(const WindowJob &, int, cudaStream_t);
+template <int L, uint64_t F>
+void launch_static(const WindowJob &job, int grid, cudaStream_t st) {
+    using M = StaticMatcher<L, F>;
+    typename M::Params mp{0};
+    window_counts_kernel<M, 4><<<grid, kWarpsPerBlock * 32, 0, st>>>(job, mp);
+}
+struct StaticEntry { int L; uint64_t F; LaunchFn fn; };
+#define X_(s) {cx_len(s), cx_enc(s), &launch_static<cx_len(s), cx_enc(s)>},
+const StaticEntry kStatic[] = {TIDK_STATIC_MOTIFS(X_)};
+#undef X_
+
+LaunchFn find_static(const uint8_t *pat, uint32_t L) {
+    if (L > 32) return nullptr;
+    uint64_t f = 0;
+    for (uint32_t j = 0; j < L; j++) f |= cx_code((char)pat[j]) << (2 * j);
+    for (const StaticEntry &e : kStatic)
+        if (e.L == (int)L && e.F == f) return e.fn;
+    return nullptr;
+}
+
+template <int L>
+void launch_runtime(const WindowJob &job, const RuntimeQueries &rq, int grid, cudaStream_t st) {
+    window_counts_kernel<RuntimeMatcher<L>, 3><<<grid, kWarpsPerBlock * 32, 0, st>>>(job, rq);
+}
+
+void launch_planes(int L, const WindowJob &job, const RuntimeQueries &rq, int grid, cudaStream_t st) {
     switch (L) {
-#define C_(n) case n: launch_fixed<n>(job, fq, grid, st); break;
+#define C_(n) case n: launch_runtime<n>(job, rq, grid, st); break;
         C_(1) C_(2) C_(3) C_(4) C_(5) C_(6) C_(7) C_(8) C_(9) C_(10) C_(11) C_(12) C_(13) C_(14)
         C_(15) C_(16) C_(17) C_(18) C_(19) C_(20) C_(21) C_(22) C_(23) C_(24) C_(25) C_(26) C_(27)
         C_(28) C_(29) C_(30) C_(31) C_(32)
 #undef C_
-    default: launch_fixed<0>(job, fq, grid, st); break;
+    default: launch_runtime<0>(job, rq, grid, st); break;
     }
+}
+
+void revcomp_host(const uint8_t *f, uint32_t L, uint8_t *out) {
+    for (uint32_t j = 0; j < L; j++) out[j] = comp_base(f[L - 1 - j]);
 }
 
 } // namespace
@@ -202,7 +254,7 @@ void tidk_cuda_destroy(tidk_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     seqbuf_release(&ctx->scratch);
-    for (DevBuf *b : {&ctx->win_base, &ctx->out_fwd, &ctx->out_rev, &ctx->misc, &ctx->qbytes, &ctx->runs})
+    for (DevBuf *b : {&ctx->win_base, &ctx->out_fwd, &ctx->out_rev, &ctx->misc, &ctx->qbytes, &ctx->runs, &ctx->items})
         if (b->p) cudaFree(b->p);
     explore_scratch_release(ctx->ex);
     cudaEventDestroy(ctx->ev0);
@@ -273,41 +325,60 @@ int tidk_cuda_window_counts_resident(tidk_ctx *ctx, const tidk_seqbuf *buf, uint
     CU(ctx, cudaSetDevice(ctx->device));
 
     const uint32_t nrec = buf->n_records;
-    std::vector<uint64_t> wb((size_t)nrec + 1, 0);
-    for (uint32_t r = 0; r < nrec; r++) {
-        uint64_t len = buf->h_off[r + 1] - buf->h_off[r];
-        wb[r + 1] = wb[r] + (len / window + (len % window != 0));
+    const bool cached = ctx->items_buf_id == buf->id && ctx->items_window == window && ctx->items_nq == nq;
+    uint64_t n_windows = ctx->items_nwin;
+    std::vector<uint64_t> wb;
+    if (!cached) {
+        wb.assign((size_t)nrec + 1, 0);
+        for (uint32_t r = 0; r < nrec; r++) {
+            uint64_t len = buf->h_off[r + 1] - buf->h_off[r];
+            uint64_t nw = len / window + (len % window != 0);
+            if (nw > 0xFFFFFFFFull) return fail(ctx, TIDK_EARG, "record %u has more than 2^32 windows", r);
+            wb[r + 1] = wb[r] + nw;
+        }
+        n_windows = wb[nrec];
     }
-    const uint64_t n_windows = wb[nrec];
     const uint64_t n_out = n_windows * nq;
     if (n_out == 0) return TIDK_OK;
     if (!out_fwd || !out_rev) return fail(ctx, TIDK_EARG, "out_fwd/out_rev is NULL");
 
+    uint64_t spw64 = (window + kSegBytes - 1) / kSegBytes;
+    if (spw64 > 0xFFFFFFFFull) spw64 = 0xFFFFFFFFull; // records are < 2^64 bytes: never reached in practice
+    const uint32_t spw = (uint32_t)spw64;
+    const uint64_t n_items = n_windows * spw;
+
     int rc;
-    if ((rc = ensure(ctx, ctx->win_base, wb.size() * 8))) return rc;
     if ((rc = ensure(ctx, ctx->out_fwd, n_out * 8))) return rc;
     if ((rc = ensure(ctx, ctx->out_rev, n_out * 8))) return rc;
     if ((rc = ensure(ctx, ctx->misc, 256))) return rc;
-    CU(ctx, cudaMemcpyAsync(ctx->win_base.p, wb.data(), wb.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemsetAsync(ctx->misc.p, 0, 256, ctx->stream));
+    uint64_t *d_fwd = (uint64_t *)ctx->out_fwd.p, *d_rev = (uint64_t *)ctx->out_rev.p;
+    if (spw > 1) {
+        CU(ctx, cudaMemsetAsync(d_fwd, 0, n_out * 8, ctx->stream));
+        CU(ctx, cudaMemsetAsync(d_rev, 0, n_out * 8, ctx->stream));
+    }
+
+    uint32_t launches = 0;
+    CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    if (!cached) {
+        ctx->items_buf_id = 0;
+        if ((rc = ensure(ctx, ctx->win_base, wb.size() * 8))) return rc;
+        if ((rc = ensure(ctx, ctx->items, n_items * sizeof(ItemDesc)))) return rc;
+        CU(ctx, cudaMemcpyAsync(ctx->win_base.p, wb.data(), wb.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        PrepJob pj{buf->d_off, (const uint64_t *)ctx->win_base.p, (ItemDesc *)ctx->items.p, window, n_items, nrec, spw, nq};
+        window_items_kernel<<<(unsigned)((n_items + 255) / 256), 256, 0, ctx->stream>>>(pj);
+        launches++;
+        ctx->items_buf_id = buf->id; ctx->items_window = window; ctx->items_nq = nq;
+        ctx->items_n = n_items; ctx->items_nwin = n_windows;
+    }
 
     WindowJob job{};
     job.seq = buf->d_seq;
-    job.rec_off = buf->d_off;
-    job.win_base = (const uint64_t *)ctx->win_base.p;
-    job.out_fwd = (uint64_t *)ctx->out_fwd.p;
-    job.out_rev = (uint64_t *)ctx->out_rev.p;
+    job.items = (const ItemDesc *)ctx->items.p;
+    job.out_fwd = d_fwd;
+    job.out_rev = d_rev;
     job.err_flags = (uint32_t *)((char *)ctx->misc.p + 128);
-    job.window = window;
-    job.n_windows = n_windows;
-    job.n_records = nrec;
-    job.segs_per_window = (uint32_t)((window + kSegBytes - 1) / kSegBytes);
-    if (window > (uint64_t)kSegBytes * 0xFFFFFFFFull) job.segs_per_window = 0xFFFFFFFFu;
-    job.nq_total = nq;
-    CU(ctx, cudaMemsetAsync(ctx->misc.p, 0, 256, ctx->stream));
-    if (job.segs_per_window > 1) {
-        CU(ctx, cudaMemsetAsync(job.out_fwd, 0, n_out * 8, ctx->stream));
-        CU(ctx, cudaMemsetAsync(job.out_rev, 0, n_out * 8, ctx->stream));
-    }
+    job.n_items = n_items;
 
     // split queries: plane kernels take A/C/G/T-only patterns up to 32 bases
     std::vector<uint32_t> fast, slow;
@@ -316,28 +387,26 @@ int tidk_cuda_window_counts_resident(tidk_ctx *ctx, const tidk_seqbuf *buf, uint
         for (uint32_t j = 0; ok && j < qlens[q]; j++) ok = is_acgt((uint8_t)queries[q][j]);
         (ok ? fast : slow).push_back(q);
     }
-    // slow-query bytes (fwd then rev per query)
-    std::vector<uint8_t> qb;
+    std::vector<uint8_t> qb; // slow-query bytes (fwd then revcomp per query)
     std::vector<size_t> qoff;
     for (uint32_t q : slow) {
         qoff.push_back(qb.size());
         const uint8_t *f = (const uint8_t *)queries[q];
         qb.insert(qb.end(), f, f + qlens[q]);
-        for (uint32_t j = 0; j < qlens[q]; j++) qb.push_back(comp_base(f[qlens[q] - 1 - j]));
+        qb.resize(qb.size() + qlens[q]);
+        revcomp_host(f, qlens[q], qb.data() + qb.size() - qlens[q]);
     }
     if (!qb.empty()) {
         if ((rc = ensure(ctx, ctx->qbytes, qb.size()))) return rc;
         CU(ctx, cudaMemcpyAsync(ctx->qbytes.p, qb.data(), qb.size(), cudaMemcpyHostToDevice, ctx->stream));
     }
 
-    const uint64_t n_items = n_windows * job.segs_per_window;
-    uint64_t want_blocks = (n_items + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    uint64_t max_blocks = (uint64_t)ctx->sm_count * 8;
+    const uint64_t want_blocks = (n_items + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const uint64_t max_blocks = (uint64_t)ctx->sm_count * 8;
     int grid = (int)(want_blocks < max_blocks ? want_blocks : max_blocks);
     if (grid < 1) grid = 1;
 
-    uint32_t launches = 0;
-    unsigned long long *counters = (unsigned long long *)ctx->misc.p; // 16 counters available
+    unsigned long long *counters = (unsigned long long *)ctx->misc.p; // 16 queue counters
     uint32_t counter_i = 0;
     auto next_counter = [&]() -> unsigned long long * {
         if (counter_i == 16) { // recycle (stream-ordered)
@@ -346,59 +415,68 @@ int tidk_cuda_window_counts_resident(tidk_ctx *ctx, const tidk_seqbuf *buf, uint
         }
         return counters + counter_i++;
     };
-    CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    if (fast.size() == 1) {
-        uint32_t q = fast[0];
-        FastQueries fq{};
-        std::vector<uint8_t> rc_pat(qlens[q]);
+
+    // queries that have a compile-time specialised kernel (directly or through their reverse
+    // complement) run alone; the rest of the fast ones are fused, up to 16 per launch
+    std::vector<uint32_t> fused;
+    uint8_t rcbuf[kMaxFastLen];
+    for (uint32_t q : fast) {
         const uint8_t *f = (const uint8_t *)queries[q];
-        for (uint32_t j = 0; j < qlens[q]; j++) rc_pat[j] = comp_base(f[qlens[q] - 1 - j]);
-        fq.fwd[0] = encode_strand(f, qlens[q]);
-        fq.rev[0] = encode_strand(rc_pat.data(), qlens[q]);
-        fq.len[0] = (uint8_t)qlens[q];
-        job.nq = 1; job.q0 = q;
-        job.work_counter = next_counter();
-        launch_planes((int)qlens[q], job, fq, grid, ctx->stream);
+        revcomp_host(f, qlens[q], rcbuf);
+        LaunchFn fn = find_static(f, qlens[q]);
+        bool swap = false;
+        if (!fn && (fn = find_static(rcbuf, qlens[q]))) swap = true;
+        if (!fn) { fused.push_back(q); continue; }
+        WindowJob j2 = job;
+        j2.q0 = q; j2.nq = 1;
+        if (swap) { j2.out_fwd = d_rev; j2.out_rev = d_fwd; }
+        j2.work_counter = next_counter();
+        fn(j2, grid, ctx->stream);
         launches++;
-    } else {
-        for (size_t g0 = 0; g0 < fast.size();) {
-            // consecutive query indices only (output addressing uses q0 + i)
-            size_t g1 = g0 + 1;
-            while (g1 < fast.size() && g1 - g0 < (size_t)kMaxFastQueries && fast[g1] == fast[g1 - 1] + 1) g1++;
-            FastQueries fq{};
-            for (size_t i = g0; i < g1; i++) {
-                uint32_t q = fast[i];
-                std::vector<uint8_t> rc_pat(qlens[q]);
-                const uint8_t *f = (const uint8_t *)queries[q];
-                for (uint32_t j = 0; j < qlens[q]; j++) rc_pat[j] = comp_base(f[qlens[q] - 1 - j]);
-                fq.fwd[i - g0] = encode_strand(f, qlens[q]);
-                fq.rev[i - g0] = encode_strand(rc_pat.data(), qlens[q]);
-                fq.len[i - g0] = (uint8_t)qlens[q];
-            }
-            job.nq = (uint32_t)(g1 - g0); job.q0 = fast[g0];
-            job.work_counter = next_counter();
-            launch_planes(0, job, fq, grid, ctx->stream);
-            launches++;
-            g0 = g1;
+    }
+    for (size_t g0 = 0; g0 < fused.size();) {
+        size_t g1 = g0 + 1; // consecutive query indices only (output addressing is q0 + i)
+        while (g1 < fused.size() && g1 - g0 < (size_t)kMaxFastQueries && fused[g1] == fused[g1 - 1] + 1) g1++;
+        RuntimeQueries rq{};
+        for (size_t i = g0; i < g1; i++) {
+            const uint32_t q = fused[i];
+            const uint8_t *f = (const uint8_t *)queries[q];
+            revcomp_host(f, qlens[q], rcbuf);
+            rq.fwd[i - g0] = encode_strand(f, qlens[q]);
+            rq.rev[i - g0] = encode_strand(rcbuf, qlens[q]);
+            rq.len[i - g0] = (uint8_t)qlens[q];
         }
+        rq.nq = (uint32_t)(g1 - g0);
+        WindowJob j2 = job;
+        j2.q0 = fused[g0]; j2.nq = rq.nq;
+        j2.work_counter = next_counter();
+        launch_planes(rq.nq == 1 ? (int)rq.len[0] : 0, j2, rq, grid, ctx->stream);
+        launches++;
+        g0 = g1;
     }
     for (size_t i = 0; i < slow.size(); i++) {
-        uint32_t q = slow[i];
-        SlowQuery sq{(const uint8_t *)ctx->qbytes.p + qoff[i], (const uint8_t *)ctx->qbytes.p + qoff[i] + qlens[q], qlens[q]};
-        WindowJob j2 = job;
-        j2.nq = 1; j2.q0 = q;
-        j2.work_counter = next_counter();
-        uint64_t wbk = (n_windows + kWarpsPerBlock - 1) / kWarpsPerBlock;
-        int g2 = (int)(wbk < max_blocks ? wbk : max_blocks);
-        window_counts_bytes_kernel<<<g2 < 1 ? 1 : g2, kWarpsPerBlock * 32, 0, ctx->stream>>>(j2, sq);
+        const uint32_t q = slow[i];
+        if (cached && !ctx->win_base.p) return fail(ctx, TIDK_ECUDA, "internal: window table missing");
+        SlowJob sj{};
+        sj.seq = buf->d_seq; sj.rec_off = buf->d_off; sj.win_base = (const uint64_t *)ctx->win_base.p;
+        sj.out_fwd = d_fwd; sj.out_rev = d_rev;
+        sj.work_counter = next_counter();
+        sj.err_flags = job.err_flags;
+        sj.window = window; sj.n_windows = n_windows; sj.n_records = nrec; sj.q = q; sj.nq_total = nq;
+        sj.fwd = (const uint8_t *)ctx->qbytes.p + qoff[i];
+        sj.rev = sj.fwd + qlens[q];
+        sj.len = qlens[q];
+        const uint64_t wbk = (n_windows + kWarpsPerBlock - 1) / kWarpsPerBlock;
+        const int g2 = (int)(wbk < max_blocks ? wbk : max_blocks);
+        window_counts_bytes_kernel<<<g2 < 1 ? 1 : g2, kWarpsPerBlock * 32, 0, ctx->stream>>>(sj);
         launches++;
     }
     CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     CU(ctx, cudaGetLastError());
 
     uint32_t h_err = 0;
-    CU(ctx, cudaMemcpyAsync(out_fwd, job.out_fwd, n_out * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaMemcpyAsync(out_rev, job.out_rev, n_out * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(out_fwd, d_fwd, n_out * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(out_rev, d_rev, n_out * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaMemcpyAsync(&h_err, job.err_flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     if (kernel_ms) CU(ctx, cudaEventElapsedTime(kernel_ms, ctx->ev0, ctx->ev1));

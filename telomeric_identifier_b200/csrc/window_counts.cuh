@@ -6,207 +6,312 @@
 // equals the query, resp. its reverse complement, with matching confined to the
 // window (an occurrence that straddles a window boundary is lost).
 //
-// Mapping: one warp per work item = (window, 32 KiB segment of it); windows up
-// to 32 KiB are one item, so with the default W = 10000 a warp owns a window,
-// needs no halo from anywhere else, and writes its two counts with plain stores.
-// The warp walks its span in 1 KiB blocks (32 lanes x one 256-bit load), keeps
-// the previous block's planes for the (L-1)-base look-behind, and counts matches
-// by their END position:  match ending at e  <=>  text[e-L+1 .. e] == query.
+// Work item = (window, 32 KiB segment of it); windows up to 32 KiB are one item,
+// so with the default W = 10000 a warp owns a whole window, needs no halo from
+// anywhere, and writes its two counts with plain stores.  A small prep kernel
+// turns (record offsets, W) into one 32-byte descriptor per item; the counting
+// kernel pulls items from an atomic queue.  A warp walks its item in 1 KiB
+// blocks (32 lanes x one 256-bit load), keeps the previous block's planes for
+// the (L-1)-base look-behind, and counts matches by their END position:
+//     match ending at e  <=>  text[e-L+1 .. e] == query.
 // Window confinement is applied to the data, not the result: bases outside
 // [beg, end) are marked invalid, so no match can reach across the boundary.
+// The load of the next block -- or of the next item's first block -- is issued
+// before the current block is matched, the next item's descriptor one item
+// ahead, and the queue ticket two items ahead, so the memory pipe never drains
+// at a window boundary.
 #pragma once
 #include "planes.cuh"
 
 namespace tidk {
 
-constexpr int kMaxFastLen = 32;         // plane kernels: one look-behind word
-constexpr int kMaxFastQueries = 16;     // queries per fused plane-kernel launch
-constexpr uint32_t kSegBytes = 32768;   // work-item span for windows larger than this
+constexpr int kMaxFastLen = 32;        // plane kernels: one look-behind word
+constexpr int kMaxFastQueries = 16;    // queries per fused multi-query launch
+constexpr uint32_t kSegBytes = 32768;  // work-item span for windows larger than this
 constexpr int kWarpsPerBlock = 8;
 
-// One strand pattern for the plane kernels: for look-behind distance s (s = 0 is
-// the LAST base of the pattern) bit s of plo / phi is the expected lo / hi plane bit.
+struct __align__(32) ItemDesc {
+    uint64_t scan0;       // absolute offset of block 0 (multiple of 32)
+    uint64_t out;         // output element index for query 0 of the launch's table
+    uint32_t nwin_r;      // windows in this record = output stride between queries
+    uint16_t vbeg, vend;  // bases inside the window: [vbeg, vend) relative to scan0
+    uint16_t cbeg, cend;  // counted END positions:   [cbeg, cend) relative to scan0
+    uint16_t nblk;        // 1 KiB blocks to scan (0: nothing to do)
+    uint16_t flags;       // bit 0: window has several items -> accumulate with atomics
+};
+static_assert(sizeof(ItemDesc) == 32, "ItemDesc is one 256-bit load");
+
+struct PrepJob {
+    const uint64_t *rec_off;  // [n_records + 1]
+    const uint64_t *win_base; // [n_records + 1] windows before record r
+    ItemDesc *items;
+    uint64_t window, n_items;
+    uint32_t n_records, segs_per_window, nq_total;
+};
+
+__global__ void __launch_bounds__(256) window_items_kernel(const PrepJob job) {
+    const uint64_t item = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= job.n_items) return;
+    const uint64_t win = item / job.segs_per_window;
+    const uint32_t seg = (uint32_t)(item - win * job.segs_per_window);
+    uint32_t r_lo = 0, r_hi = job.n_records;
+    while (r_hi - r_lo > 1) { // last record with win_base[r] <= win
+        uint32_t mid = (r_lo + r_hi) >> 1;
+        if (job.win_base[mid] <= win) r_lo = mid; else r_hi = mid;
+    }
+    const uint64_t rec_beg = job.rec_off[r_lo], rec_end = job.rec_off[r_lo + 1];
+    const uint64_t wi = win - job.win_base[r_lo];
+    const uint64_t beg = rec_beg + wi * job.window;
+    const uint64_t end = (beg + job.window < rec_end) ? beg + job.window : rec_end;
+    const uint64_t sbeg = beg + (uint64_t)seg * kSegBytes;
+    ItemDesc d;
+    d.scan0 = 0; d.nblk = 0; d.vbeg = d.vend = d.cbeg = d.cend = 0;
+    d.out = job.win_base[r_lo] * job.nq_total + wi;
+    d.nwin_r = (uint32_t)(job.win_base[r_lo + 1] - job.win_base[r_lo]);
+    d.flags = job.segs_per_window > 1 ? 1 : 0;
+    if (sbeg < end) {
+        const uint64_t send = (sbeg + kSegBytes < end) ? sbeg + kSegBytes : end;
+        // later segments start one block early so that the look-behind planes are real
+        uint64_t scan0 = sbeg & ~31ull;
+        if (seg > 0) scan0 -= 1024;
+        d.scan0 = scan0;
+        d.nblk = (uint16_t)((send - scan0 + 1023) >> 10);
+        d.vbeg = (uint16_t)(beg > scan0 ? beg - scan0 : 0);
+        d.vend = (uint16_t)(end - scan0 < 65535 ? end - scan0 : 65535);
+        d.cbeg = (uint16_t)(sbeg - scan0);
+        d.cend = (uint16_t)(send - scan0);
+    }
+    job.items[item] = d;
+}
+
+struct WindowJob {
+    const uint8_t *seq;      // device, 256-B aligned, zero padding behind the data
+    const ItemDesc *items;
+    uint64_t *out_fwd;       // [record][query][window]
+    uint64_t *out_rev;
+    unsigned long long *work_counter; // zeroed before launch
+    uint32_t *err_flags;     // bit 0: non-ASCII byte seen
+    uint64_t n_items;
+    uint32_t q0;             // first query index of this launch
+    uint32_t nq;             // queries in this launch
+};
+
+// ------------------------------------------------------------------ matchers
+// A matcher turns the planes of one block (+ the look-behind carry) into per-lane
+// match counts.  Base codes in static patterns: A=0 C=1 G=2 T=3, complement = 3 - c.
+
+// Pattern known at compile time: equality planes, one funnel shift + one AND per
+// pattern position and strand, LOP3 truth tables folded into immediates.
+template <int L, uint64_t F>
+struct StaticMatcher {
+    static constexpr int NQ = 1;
+    struct Params { uint32_t unused; };
+    struct Carry { uint32_t e[4]; };
+    __host__ __device__ static constexpr int fwd_at(int j) { return (int)((F >> (2 * j)) & 3); }
+    __device__ __forceinline__ static void reset(Carry &c) { c.e[0] = c.e[1] = c.e[2] = c.e[3] = 0; }
+
+    template <int S>
+    __device__ __forceinline__ static void steps(const uint32_t (&e)[4], const uint32_t (&p)[4],
+                                                 uint32_t &mf, uint32_t &mr) {
+        if constexpr (S < L) {
+            constexpr int fb = fwd_at(L - 1 - S); // forward letter S bases behind the end
+            constexpr int rb = 3 - fwd_at(S);     // revcomp letter S bases behind the end
+            mf &= S == 0 ? e[fb] : __funnelshift_l(p[fb], e[fb], S);
+            mr &= S == 0 ? e[rb] : __funnelshift_l(p[rb], e[rb], S);
+            steps<S + 1>(e, p, mf, mr);
+        }
+    }
+
+    __device__ __forceinline__ static void step(const Params &, const Planes &P, bool special,
+                                                uint32_t cmask, int lane, Carry &carry,
+                                                uint32_t *cf, uint32_t *cr) {
+        uint32_t e[4], p[4];
+        e[0] = ~P.lo & ~P.hi & P.b0; // A
+        e[1] = P.lo & ~P.hi & P.b0;  // C
+        e[2] = P.lo & P.hi & P.b0;   // G
+        e[3] = ~P.lo & P.hi & ~P.b0; // T
+        if (special) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) e[i] &= P.ok;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) p[i] = lane_lookbehind(e[i], carry.e[i], lane);
+        uint32_t mf = 0xFFFFFFFFu, mr = 0xFFFFFFFFu;
+        steps<0>(e, p, mf, mr);
+#pragma unroll
+        for (int i = 0; i < 4; i++) carry.e[i] = e[i];
+        cf[0] += __popc(mf & cmask);
+        cr[0] += __popc(mr & cmask);
+    }
+};
+
+// One strand pattern for the runtime matchers: bit s of plo / phi is the expected
+// lo / hi plane bit s bases behind the match end (s = 0 is the LAST base).
 struct StrandPattern {
     uint32_t plo, phi;
 };
 
-struct WindowJob {
-    const uint8_t *seq;        // device, 256-B aligned, >= 2 KiB of zero padding behind the data
-    const uint64_t *rec_off;   // [n_records + 1] byte offsets
-    const uint64_t *win_base;  // [n_records + 1] windows before record r (per query)
-    uint64_t *out_fwd;         // [record][query][window]
-    uint64_t *out_rev;
-    unsigned long long *work_counter; // zeroed before launch
-    uint32_t *err_flags;       // bit 0: non-ASCII byte seen
-    uint64_t window;
-    uint64_t n_windows;        // sum over records
-    uint32_t n_records;
-    uint32_t segs_per_window;  // ceil(window / kSegBytes)
-    uint32_t nq;
-    uint32_t q0;               // first query index of this launch (output addressing)
-    uint32_t nq_total;
-};
-
-struct FastQueries {
+struct RuntimeQueries {
     StrandPattern fwd[kMaxFastQueries];
     StrandPattern rev[kMaxFastQueries];
     uint8_t len[kMaxFastQueries];
+    uint32_t nq;
 };
 
-__device__ __forceinline__ uint32_t range_mask(int64_t lo_rel, int64_t hi_rel) {
-    // bits b with lo_rel <= b < hi_rel, b in [0, 32)
-    if (hi_rel <= 0 || lo_rel >= 32 || hi_rel <= lo_rel) return 0u;
-    uint32_t m = 0xFFFFFFFFu;
-    if (lo_rel > 0) m &= 0xFFFFFFFFu << (int)lo_rel;
-    if (hi_rel < 32) m &= 0xFFFFFFFFu >> (32 - (int)hi_rel);
-    return m;
-}
-
-// mismatch accumulation for one strand over L look-behind steps.
-// mism bit e stays 0 iff text[e-s] == pattern[L-1-s] for all s < L.
-template <int L, int S>
-struct MatchStep {
-    __device__ __forceinline__ static void run(const Planes &c, const Planes &p, uint32_t flo,
-                                               uint32_t fhi, uint32_t rlo, uint32_t rhi,
-                                               uint32_t &mf, uint32_t &mr, uint32_t &inv) {
-        uint32_t lo_s = S == 0 ? c.lo : __funnelshift_l(p.lo, c.lo, S);
-        uint32_t hi_s = S == 0 ? c.hi : __funnelshift_l(p.hi, c.hi, S);
-        uint32_t va_s = S == 0 ? c.va : __funnelshift_l(p.va, c.va, S);
-        // expected bit for step S broadcast to all 32 positions
-        uint32_t eflo = 0u - ((flo >> S) & 1u), efhi = 0u - ((fhi >> S) & 1u);
-        uint32_t erlo = 0u - ((rlo >> S) & 1u), erhi = 0u - ((rhi >> S) & 1u);
-        inv |= ~va_s;
-        mf |= (lo_s ^ eflo) | (hi_s ^ efhi);
-        mr |= (lo_s ^ erlo) | (hi_s ^ erhi);
-        MatchStep<L, S + 1>::run(c, p, flo, fhi, rlo, rhi, mf, mr, inv);
-    }
-};
-template <int L>
-struct MatchStep<L, L> {
-    __device__ __forceinline__ static void run(const Planes &, const Planes &, uint32_t, uint32_t,
-                                               uint32_t, uint32_t, uint32_t &, uint32_t &,
-                                               uint32_t &) {}
-};
-
-// Runtime-length version (multi-query launches with mixed lengths).
-__device__ __forceinline__ void match_runtime(const Planes &c, const Planes &p, int L, uint32_t flo,
-                                              uint32_t fhi, uint32_t rlo, uint32_t rhi,
-                                              uint32_t &mf, uint32_t &mr, uint32_t &inv) {
-    for (int s = 0; s < L; s++) {
-        uint32_t lo_s = __funnelshift_l(p.lo, c.lo, s);
-        uint32_t hi_s = __funnelshift_l(p.hi, c.hi, s);
-        uint32_t va_s = __funnelshift_l(p.va, c.va, s);
-        uint32_t eflo = 0u - ((flo >> s) & 1u), efhi = 0u - ((fhi >> s) & 1u);
-        uint32_t erlo = 0u - ((rlo >> s) & 1u), erhi = 0u - ((rhi >> s) & 1u);
-        inv |= ~va_s;
-        mf |= (lo_s ^ eflo) | (hi_s ^ efhi);
-        mr |= (lo_s ^ erlo) | (hi_s ^ erhi);
-    }
-}
-
-// LT > 0: single query of compile-time length LT.  LT == 0: nq queries, runtime lengths.
+// Pattern known only at run time: mismatch accumulation against broadcast pattern bits.
+// LT > 0: one query of length LT (unrolled).  LT == 0: nq queries, run-time lengths.
 template <int LT>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-window_counts_planes_kernel(const WindowJob job, const FastQueries fq) {
+struct RuntimeMatcher {
+    static constexpr int NQ = LT > 0 ? 1 : kMaxFastQueries;
+    using Params = RuntimeQueries;
+    struct Carry { uint32_t lo, hi, va; };
+    __device__ __forceinline__ static void reset(Carry &c) { c.lo = c.hi = c.va = 0; }
+
+    __device__ __forceinline__ static void one(const StrandPattern &f, const StrandPattern &r, int s,
+                                               uint32_t lo_s, uint32_t hi_s, uint32_t &mf, uint32_t &mr) {
+        uint32_t eflo = 0u - ((f.plo >> s) & 1u), efhi = 0u - ((f.phi >> s) & 1u);
+        uint32_t erlo = 0u - ((r.plo >> s) & 1u), erhi = 0u - ((r.phi >> s) & 1u);
+        mf |= (lo_s ^ eflo) | (hi_s ^ efhi);
+        mr |= (lo_s ^ erlo) | (hi_s ^ erhi);
+    }
+
+    __device__ __forceinline__ static void step(const Params &q, const Planes &P, bool special,
+                                                uint32_t cmask, int lane, Carry &carry,
+                                                uint32_t *cf, uint32_t *cr) {
+        uint32_t va = P.b0 ^ (P.hi & ~P.lo);
+        if (special) va &= P.ok;
+        const uint32_t plo = lane_lookbehind(P.lo, carry.lo, lane);
+        const uint32_t phi = lane_lookbehind(P.hi, carry.hi, lane);
+        const uint32_t pva = lane_lookbehind(va, carry.va, lane);
+        carry.lo = P.lo; carry.hi = P.hi; carry.va = va;
+        if constexpr (LT > 0) {
+            uint32_t mf = 0, mr = 0, inv = 0;
+#pragma unroll
+            for (int s = 0; s < LT; s++) {
+                uint32_t lo_s = s == 0 ? P.lo : __funnelshift_l(plo, P.lo, s);
+                uint32_t hi_s = s == 0 ? P.hi : __funnelshift_l(phi, P.hi, s);
+                uint32_t va_s = s == 0 ? va : __funnelshift_l(pva, va, s);
+                inv |= ~va_s;
+                one(q.fwd[0], q.rev[0], s, lo_s, hi_s, mf, mr);
+            }
+            cf[0] += __popc(~(mf | inv) & cmask);
+            cr[0] += __popc(~(mr | inv) & cmask);
+        } else {
+#pragma unroll 1
+            for (uint32_t i = 0; i < q.nq; i++) {
+                uint32_t mf = 0, mr = 0, inv = 0;
+                const int Lq = q.len[i];
+                for (int s = 0; s < Lq; s++) {
+                    uint32_t lo_s = __funnelshift_l(plo, P.lo, s);
+                    uint32_t hi_s = __funnelshift_l(phi, P.hi, s);
+                    uint32_t va_s = __funnelshift_l(pva, va, s);
+                    inv |= ~va_s;
+                    one(q.fwd[i], q.rev[i], s, lo_s, hi_s, mf, mr);
+                }
+                const uint32_t a = __popc(~(mf | inv) & cmask), b = __popc(~(mr | inv) & cmask);
+#pragma unroll
+                for (int t = 0; t < kMaxFastQueries; t++) // keep the counters in registers
+                    if (t == (int)i) { cf[t] += a; cr[t] += b; }
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------ the kernel
+template <class M, int MINB>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
+window_counts_kernel(const WindowJob job, const typename M::Params mp) {
     const int lane = threadIdx.x & 31;
-    const uint64_t n_items = job.n_windows * job.segs_per_window;
     uint32_t nonascii = 0;
 
+    // queue tickets: current item, next item, and the raw ticket for the one after
+    unsigned long long t0 = 0, t1 = 0;
+    if (lane == 0) { t0 = atomicAdd(job.work_counter, 2ull); t1 = t0 + 1; }
+    unsigned long long item = __shfl_sync(0xFFFFFFFFu, t0, 0);
+    unsigned long long item_next = __shfl_sync(0xFFFFFFFFu, t1, 0);
+    if (item >= job.n_items) return;
+
+    const uint4 *ip = reinterpret_cast<const uint4 *>(job.items);
+    uint4 da = __ldg(ip + 2 * item), db = __ldg(ip + 2 * item + 1);
+    uint32_t w[8];
+    {
+        const uint64_t scan0 = ((uint64_t)da.y << 32) | da.x;
+        ld256_stream(job.seq + scan0 + (uint32_t)lane * 32u, w);
+    }
+
     for (;;) {
-        unsigned long long item = 0;
-        if (lane == 0) item = atomicAdd(job.work_counter, 1ull);
-        item = __shfl_sync(0xFFFFFFFFu, item, 0);
-        if (item >= n_items) break;
-        const uint64_t win = item / job.segs_per_window;
-        const uint32_t seg = (uint32_t)(item - win * job.segs_per_window);
+        // decode the current descriptor
+        const uint64_t scan0 = ((uint64_t)da.y << 32) | da.x;
+        const uint64_t out0 = ((uint64_t)da.w << 32) | da.z;
+        const uint32_t nwin_r = db.x;
+        const int vbeg = (int)(db.y & 0xFFFFu), vend = (int)(db.y >> 16);
+        const int cbeg = (int)(db.z & 0xFFFFu), cend = (int)(db.z >> 16);
+        const uint32_t nblk = db.w & 0xFFFFu;
+        const bool multi = (db.w >> 16) & 1u;
+        const uint32_t nlead = multi ? 2u : 1u; // leading blocks that can hold a window / segment start
 
-        // record of this window: last r with win_base[r] <= win
-        uint32_t r_lo = 0, r_hi = job.n_records;
-        while (r_hi - r_lo > 1) {
-            uint32_t mid = (r_lo + r_hi) >> 1;
-            if (job.win_base[mid] <= win) r_lo = mid; else r_hi = mid;
-        }
-        const uint32_t rec = r_lo;
-        const uint64_t rec_beg = job.rec_off[rec], rec_end = job.rec_off[rec + 1];
-        const uint64_t wi = win - job.win_base[rec];
-        const uint64_t nwin_r = job.win_base[rec + 1] - job.win_base[rec];
-        const uint64_t beg = rec_beg + wi * job.window;
-        const uint64_t end = (beg + job.window < rec_end) ? beg + job.window : rec_end;
-        // segment span: END positions counted by this item
-        const uint64_t sbeg = beg + (uint64_t)seg * kSegBytes;
-        if (sbeg >= end) continue; // last window of a record can be short
-        const uint64_t send = (sbeg + kSegBytes < end) ? sbeg + kSegBytes : end;
-        // scan from one block (1 KiB) before the segment when it is not the window start,
-        // so that the look-behind planes are real
-        uint64_t scan0 = sbeg & ~31ull;
-        if (seg > 0) scan0 -= 1024;
-        const uint32_t nblk = (uint32_t)((send - scan0 + 1023) >> 10);
+        // look ahead: descriptor of the next item, ticket of the one after
+        const bool have_next = item_next < job.n_items;
+        uint4 na = make_uint4(0, 0, 0, 0), nb = na;
+        if (have_next) { na = __ldg(ip + 2 * item_next); nb = __ldg(ip + 2 * item_next + 1); }
+        unsigned long long t2 = 0;
+        if (lane == 0) t2 = atomicAdd(job.work_counter, 1ull);
 
-        uint32_t cf[LT > 0 ? 1 : kMaxFastQueries], cr[LT > 0 ? 1 : kMaxFastQueries];
+        uint32_t cf[M::NQ], cr[M::NQ];
 #pragma unroll
-        for (int q = 0; q < (LT > 0 ? 1 : kMaxFastQueries); q++) { cf[q] = 0; cr[q] = 0; }
+        for (int q = 0; q < M::NQ; q++) { cf[q] = 0; cr[q] = 0; }
+        typename M::Carry carry;
+        M::reset(carry);
 
-        Planes prev_own = {0u, 0u, 0u}; // this lane's planes of the previous block
-        uint32_t w[8], wn[8];
-        const uint8_t *ptr = job.seq + scan0 + (uint64_t)lane * 32;
-        ld256_stream(ptr, w);
+        const uint8_t *ptr = job.seq + scan0 + (uint32_t)lane * 32u;
         for (uint32_t blk = 0; blk < nblk; blk++) {
-            if (blk + 1 < nblk) ld256_stream(ptr + 1024, wn); // prefetch next block
-            Planes cur = extract_planes(w, nonascii);
-            const uint64_t P = scan0 + ((uint64_t)blk << 10) + (uint64_t)lane * 32;
+            const Nibbles nib = to_nibbles(w); // w is dead from here: refill it
+            if (blk + 1 < nblk) {
+                ptr += 1024;
+                ld256_stream(ptr, w);
+            } else if (have_next) {
+                const uint64_t nscan0 = ((uint64_t)na.y << 32) | na.x;
+                ld256_stream(job.seq + nscan0 + (uint32_t)lane * 32u, w);
+            }
+            Planes P = extract_planes(nib, nonascii);
             uint32_t cmask = 0xFFFFFFFFu;
-            if (blk <= 1 || blk + 1 == nblk) { // warp-uniform: only edge blocks pay for masks
-                cur.va &= range_mask((int64_t)beg - (int64_t)P, (int64_t)end - (int64_t)P);
-                cmask = range_mask((int64_t)sbeg - (int64_t)P, (int64_t)send - (int64_t)P);
+            bool special = P.exact;
+            if (blk < nlead || blk + 1 == nblk) { // warp-uniform: only edge blocks pay for masks
+                const int prel = (int)(blk << 10) + lane * 32;
+                P.ok &= range_mask32(vbeg - prel, vend - prel);
+                special = true;
+                if (multi) cmask = range_mask32(cbeg - prel, cend - prel);
             }
-            Planes prv;
-            prv.lo = lane_lookbehind(cur.lo, prev_own.lo, lane);
-            prv.hi = lane_lookbehind(cur.hi, prev_own.hi, lane);
-            prv.va = lane_lookbehind(cur.va, prev_own.va, lane);
-            if (LT > 0) {
-                uint32_t mf = 0, mr = 0, inv = 0;
-                MatchStep<LT, 0>::run(cur, prv, fq.fwd[0].plo, fq.fwd[0].phi, fq.rev[0].plo,
-                                      fq.rev[0].phi, mf, mr, inv);
-                cf[0] += __popc(~(mf | inv) & cmask);
-                cr[0] += __popc(~(mr | inv) & cmask);
-            } else {
-#pragma unroll 1
-                for (uint32_t q = 0; q < job.nq; q++) {
-                    uint32_t mf = 0, mr = 0, inv = 0;
-                    match_runtime(cur, prv, fq.len[q], fq.fwd[q].plo, fq.fwd[q].phi,
-                                  fq.rev[q].plo, fq.rev[q].phi, mf, mr, inv);
-                    uint32_t a = __popc(~(mf | inv) & cmask), b = __popc(~(mr | inv) & cmask);
-#pragma unroll
-                    for (int t = 0; t < kMaxFastQueries; t++) // keep cf/cr in registers
-                        if (t == (int)q) { cf[t] += a; cr[t] += b; }
-                }
-            }
-            prev_own = cur;
-            ptr += 1024;
-#pragma unroll
-            for (int i = 0; i < 8; i++) w[i] = wn[i];
+            M::step(mp, P, special, cmask, lane, carry, cf, cr);
         }
 
-        // reduce over the warp and write
-        const uint32_t nq_here = LT > 0 ? 1u : job.nq;
+        if (nblk == 0 && have_next) { // empty item (window shorter than its segment grid):
+            const uint64_t nscan0 = ((uint64_t)na.y << 32) | na.x; // nobody prefetched for the next one
+            ld256_stream(job.seq + nscan0 + (uint32_t)lane * 32u, w);
+        }
+        if (nblk > 0) {
 #pragma unroll
-        for (int q = 0; q < (LT > 0 ? 1 : kMaxFastQueries); q++) {
-            if ((uint32_t)q < nq_here) {
-                uint32_t f = __reduce_add_sync(0xFFFFFFFFu, cf[q]);
-                uint32_t r = __reduce_add_sync(0xFFFFFFFFu, cr[q]);
-                if (lane == 0) {
-                    const uint64_t o = job.win_base[rec] * job.nq_total +
-                                       (uint64_t)(job.q0 + q) * nwin_r + wi;
-                    if (job.segs_per_window == 1) {
-                        job.out_fwd[o] = f;
-                        job.out_rev[o] = r;
-                    } else {
-                        atomicAdd((unsigned long long *)&job.out_fwd[o], (unsigned long long)f);
-                        atomicAdd((unsigned long long *)&job.out_rev[o], (unsigned long long)r);
+            for (int q = 0; q < M::NQ; q++) {
+                if (M::NQ == 1 || (uint32_t)q < job.nq) {
+                    const uint32_t f = __reduce_add_sync(0xFFFFFFFFu, cf[q]);
+                    const uint32_t r = __reduce_add_sync(0xFFFFFFFFu, cr[q]);
+                    if (lane == 0) {
+                        const uint64_t o = out0 + (uint64_t)(job.q0 + q) * nwin_r;
+                        if (!multi) {
+                            job.out_fwd[o] = f;
+                            job.out_rev[o] = r;
+                        } else {
+                            atomicAdd((unsigned long long *)&job.out_fwd[o], (unsigned long long)f);
+                            atomicAdd((unsigned long long *)&job.out_rev[o], (unsigned long long)r);
+                        }
                     }
                 }
             }
         }
+        if (!have_next) break;
+        item = item_next;
+        da = na; db = nb;
+        item_next = __shfl_sync(0xFFFFFFFFu, t2, 0);
     }
     if (__any_sync(0xFFFFFFFFu, nonascii != 0) && lane == 0) atomicOr(job.err_flags, 1u);
 }
@@ -214,15 +319,22 @@ window_counts_planes_kernel(const WindowJob job, const FastQueries fq) {
 // Exact byte-wise kernel for queries the plane kernels do not take: letters other
 // than A/C/G/T (compared literally against the upper-cased text, e.g. 'N' or the
 // 'N's produced by utils::reverse_complement for non-ACGT letters, utils.rs:49-58)
-// or length > 32 (incl. the reference's BOM branch, utils.rs:25-28).
-struct SlowQuery {
-    const uint8_t *fwd; // device, length len
-    const uint8_t *rev;
+// or length > 32 (incl. the reference's BOM branch, utils.rs:25-28).  One warp per
+// window; correctness path, not a roofline path.
+struct SlowJob {
+    const uint8_t *seq;
+    const uint64_t *rec_off;
+    const uint64_t *win_base;
+    uint64_t *out_fwd, *out_rev;
+    unsigned long long *work_counter;
+    uint32_t *err_flags;
+    uint64_t window, n_windows;
+    uint32_t n_records, q, nq_total;
+    const uint8_t *fwd, *rev; // device, length len
     uint32_t len;
 };
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-window_counts_bytes_kernel(const WindowJob job, const SlowQuery sq) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) window_counts_bytes_kernel(const SlowJob job) {
     const int lane = threadIdx.x & 31;
     uint32_t nonascii = 0;
     for (;;) {
@@ -244,13 +356,13 @@ window_counts_bytes_kernel(const WindowJob job, const SlowQuery sq) {
         unsigned long long f = 0, r = 0;
         for (uint64_t p = beg + lane; p < end; p += 32) {
             nonascii |= job.seq[p] & 0x80u;
-            if (p + sq.len > end) continue;
+            if (p + job.len > end) continue;
             bool mf = true, mr = true;
-            for (uint32_t j = 0; j < sq.len && (mf || mr); j++) {
+            for (uint32_t j = 0; j < job.len && (mf || mr); j++) {
                 uint8_t c = job.seq[p + j];
                 c = (c >= 'a' && c <= 'z') ? c - 32 : c;
-                mf = mf && (c == sq.fwd[j]);
-                mr = mr && (c == sq.rev[j]);
+                mf = mf && (c == job.fwd[j]);
+                mr = mr && (c == job.rev[j]);
             }
             f += mf; r += mr;
         }
@@ -259,7 +371,7 @@ window_counts_bytes_kernel(const WindowJob job, const SlowQuery sq) {
             r += __shfl_down_sync(0xFFFFFFFFu, r, o);
         }
         if (lane == 0) {
-            const uint64_t o = job.win_base[rec] * job.nq_total + (uint64_t)job.q0 * nwin_r + wi;
+            const uint64_t o = job.win_base[rec] * job.nq_total + (uint64_t)job.q * nwin_r + wi;
             job.out_fwd[o] = f;
             job.out_rev[o] = r;
         }
