@@ -202,10 +202,11 @@ def main():
         of, orr = O.window_counts(seq[:nchk], np.array([0, nchk], dtype=np.uint64), WINDOW, REPEATS, False)
         assert (f[:of.size] == of).all() and (r[:orr.size] == orr).all(), "GPU counts differ from the oracle"
 
-    for _ in range(warmup):
-        ctx.window_counts_resident(batch, WINDOW, REPEATS, out=(pf, pr))
     sampler = ClockSampler(local)
     sampler.start()
+    t_s = time.perf_counter()
+    for _ in range(warmup):
+        ctx.window_counts_resident(batch, WINDOW, REPEATS, out=(pf, pr))
     kernel_ms, launches = 0.0, 0
     barrier()
     t0 = time.perf_counter()
@@ -215,7 +216,12 @@ def main():
         launches += ctx.last_kernel_launches
     barrier()
     dt = time.perf_counter() - t0
+    # nvidia-smi samples every 100 ms: keep the same step running (untimed) until the sampler has
+    # seen at least ~1.5 s of this load, so the clocks line describes the kernel that was timed
+    while time.perf_counter() - t_s < 1.5:
+        ctx.window_counts_resident(batch, WINDOW, REPEATS, out=(pf, pr))
     clocks = sampler.stop()
+    clocks["note"] = "sampled over warm-up + timed steps + identical untimed steps (>= 1.5 s of the same kernel)"
 
     # end to end through the C ABI with host buffers
     e2e_steps = args.e2e_steps or min(steps, 5)
@@ -242,12 +248,12 @@ def main():
         k_ms = kernel_ms / steps
         achieved = bases / (k_ms * 1e-3) / 1e9  # GB/s per GPU at 1 B per scanned base
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "window_counts_planes_kernel<5>", "kernel_ms": k_ms,
+                "traffic": None, "kernel": "window_counts_kernel<StaticMatcher<5,AACCT>>", "kernel_ms": k_ms,
                 "algorithmic_bytes_per_launch": bases, "peak_source": peak_src}
         tr = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tr):
             try:
-                roof["traffic"] = json.load(open(tr)).get("window_counts_planes_kernel_bytes_per_launch")
+                roof["traffic"] = json.load(open(tr)).get("window_counts_kernel_dram_bytes_per_launch")
             except Exception:
                 pass
         cb = None

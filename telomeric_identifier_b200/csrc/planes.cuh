@@ -70,7 +70,7 @@ __device__ __forceinline__ Nibbles to_nibbles(const uint32_t (&w)[8]) {
     for (int g = 0; g < 4; g++) {
         uint32_t wa = w[2 * g], wb = w[2 * g + 1];
         n.X[g] = bitsel(0x0F0F0F0Fu, wa, wb << 4);
-        n.Y[g] = bitsel(0x0F0F0F0Fu, wa >> 4, wb);
+        n.Y[g] = bitsel(0x0F0F0F0Fu, __umulhi(wa, 0x10000000u), wb); // wa >> 4 on the fma pipe
     }
     return n;
 }
