@@ -1,0 +1,299 @@
+// tidk (B200 host driver) -- plays the role of the reference's Rust host for the hot path:
+// same subcommands, flags and defaults as main.rs:18-146 for search / find / explore, same output
+// files and rows (search.rs:35-54,132-147; finder.rs:66-78,169-172; explore.rs:140-143), same
+// stderr progress lines.  All counting / run detection goes through libtidk_cuda.so (C ABI);
+// there is no CPU path.  `plot`, `build` and `--log` are out of scope.
+#include <sys/stat.h>
+
+#include <cerrno>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../../include/tidk_cuda.h"
+#include "clades.hpp"
+#include "fasta.hpp"
+#include "hostlogic.hpp"
+
+using namespace tidk_host;
+
+namespace {
+
+struct Args {
+    std::string sub, fasta, string_, clade, output, dir, extension = "tsv", database;
+    uint64_t window = 10000;
+    long long length = -1, minimum = 5, maximum = 12, threshold = 100;
+    bool have_min = false, have_max = false;
+    double distance = 0.01;
+    bool print = false, verbose = false, log = false, stats = false;
+    int device = 0;
+};
+
+[[noreturn]] void die(const std::string &msg, int code = 2) {
+    fprintf(stderr, "error: %s\n", msg.c_str());
+    exit(code);
+}
+
+void usage() {
+    fprintf(stderr,
+            "tidk (B200) -- A Telomere Identification Toolkit, hot path on NVIDIA B200\n\n"
+            "Usage: tidk search  <FASTA> -s <STRING> [-w 10000] -o <OUTPUT> -d <DIR> [-e tsv|bedgraph]\n"
+            "       tidk find    <FASTA> -c <CLADE>  [-w 10000] -o <OUTPUT> -d <DIR> [-p] [--database CSV]\n"
+            "       tidk explore <FASTA> [-l LENGTH | -m 5 -x 12] [-t 100] [--distance 0.01] [-v]\n"
+            "Extra: --device N, --gpu-stats (kernel time and Gbases/s on stderr)\n");
+}
+
+Args parse(int argc, char **argv) {
+    Args a;
+    if (argc < 2) { usage(); exit(2); }
+    a.sub = argv[1];
+    if (a.sub == "-h" || a.sub == "--help") { usage(); exit(0); }
+    if (a.sub == "plot" || a.sub == "build") die("`tidk " + a.sub + "` is outside the B200 hot path; use the reference binary");
+    if (a.sub != "search" && a.sub != "find" && a.sub != "explore") die("unrecognized subcommand '" + a.sub + "'");
+    auto need = [&](int &i) -> std::string {
+        if (i + 1 >= argc) die(std::string("a value is required for '") + argv[i] + "'");
+        return argv[++i];
+    };
+    for (int i = 2; i < argc; i++) {
+        std::string f = argv[i];
+        std::string val;
+        size_t eq = f.find('=');
+        bool has_eq = f.rfind("--", 0) == 0 && eq != std::string::npos;
+        if (has_eq) { val = f.substr(eq + 1); f = f.substr(0, eq); }
+        auto v = [&]() { return has_eq ? val : need(i); };
+        if (f == "-s" || f == "--string") a.string_ = v();
+        else if (f == "-w" || f == "--window") a.window = strtoull(v().c_str(), nullptr, 10);
+        else if (f == "-o" || f == "--output") a.output = v();
+        else if (f == "-d" || f == "--dir") a.dir = v();
+        else if (f == "-e" || f == "--extension") a.extension = v();
+        else if (f == "-c" || f == "--clade") a.clade = v();
+        else if (f == "-p" || f == "--print") a.print = true;
+        else if (f == "-l" || f == "--length") a.length = atoll(v().c_str());
+        else if (f == "-m" || f == "--minimum") { a.minimum = atoll(v().c_str()); a.have_min = true; }
+        else if (f == "-x" || f == "--maximum") { a.maximum = atoll(v().c_str()); a.have_max = true; }
+        else if (f == "-t" || f == "--threshold") a.threshold = atoll(v().c_str());
+        else if (f == "--distance") a.distance = atof(v().c_str());
+        else if (f == "-v" || f == "--verbose") a.verbose = true;
+        else if (f == "--log") a.log = true;
+        else if (f == "--database") a.database = v();
+        else if (f == "--device") a.device = atoi(v().c_str());
+        else if (f == "--gpu-stats") a.stats = true;
+        else if (!f.empty() && f[0] == '-') die("unexpected argument '" + f + "'");
+        else if (a.fasta.empty()) a.fasta = f;
+        else die("unexpected argument '" + f + "'");
+    }
+    if (a.log) fprintf(stderr, "[-]\t--log is not implemented in the B200 driver (out of scope)\n");
+    return a;
+}
+
+void mkdirs(const std::string &dir) { // create_dir_all
+    std::string cur;
+    for (size_t i = 0; i <= dir.size(); i++) {
+        if (i == dir.size() || dir[i] == '/') {
+            if (!cur.empty() && mkdir(cur.c_str(), 0777) != 0 && errno != EEXIST) die("cannot create directory " + cur, 1);
+        }
+        if (i < dir.size()) cur += dir[i];
+    }
+}
+
+struct Ctx {
+    tidk_ctx *h = nullptr;
+    explicit Ctx(int device) {
+        int ids[1] = {device};
+        if (tidk_cuda_create(ids, 1, &h) != 0) die(std::string("tidk_cuda_create: ") + tidk_cuda_last_error(nullptr), 1);
+    }
+    ~Ctx() { tidk_cuda_destroy(h); }
+    void check(int rc) const {
+        if (rc != 0) die(std::string("tidk-cuda error ") + std::to_string(rc) + ": " + tidk_cuda_last_error(h), 1);
+    }
+};
+
+const char *kHeader = "id\twindow\tforward_repeat_number\treverse_repeat_number\ttelomeric_repeat\n";
+
+// rows in the reference order record -> repeat -> window
+void write_rows(FILE *out, const Fasta &fa, uint64_t W, const std::vector<std::string> &labels,
+                const std::vector<uint64_t> &f, const std::vector<uint64_t> &r, bool bedgraph) {
+    std::string buf;
+    buf.reserve(1 << 22);
+    char line[512];
+    size_t p = 0;
+    for (size_t rec = 0; rec < fa.ids.size(); rec++) {
+        const uint64_t n = fa.offsets[rec + 1] - fa.offsets[rec];
+        const uint64_t nw = n / W + (n % W != 0);
+        for (const std::string &lab : labels) {
+            for (uint64_t i = 0; i < nw; i++, p++) {
+                const uint64_t end = (i + 1) * W < n ? (i + 1) * W : n;
+                int m;
+                if (!bedgraph)
+                    m = snprintf(line, sizeof line, "%s\t%llu\t%llu\t%llu\t%s\n", fa.ids[rec].c_str(), (unsigned long long)end,
+                                 (unsigned long long)f[p], (unsigned long long)r[p], lab.c_str());
+                else
+                    m = snprintf(line, sizeof line, "%s\t%llu\t%llu\t%llu\n", fa.ids[rec].c_str(), (unsigned long long)(i * W),
+                                 (unsigned long long)end, (unsigned long long)(f[p] + r[p]));
+                if (m >= (int)sizeof line) { // very long id: format into a string
+                    std::string s = fa.ids[rec] + "\t" + (bedgraph ? std::to_string(i * W) + "\t" : std::string()) + std::to_string(end) + "\t";
+                    s += bedgraph ? std::to_string(f[p] + r[p]) + "\n"
+                                  : std::to_string(f[p]) + "\t" + std::to_string(r[p]) + "\t" + lab + "\n";
+                    buf += s;
+                } else buf.append(line, (size_t)m);
+                if (buf.size() > (1 << 22) - 1024) { fwrite(buf.data(), 1, buf.size(), out); buf.clear(); }
+            }
+        }
+        fprintf(stderr, "[+]\tChromosome %s processed\n", fa.ids[rec].c_str()); // search.rs:71 / finder.rs:99
+    }
+    fwrite(buf.data(), 1, buf.size(), out);
+}
+
+int run_counts(const Args &a, const std::vector<std::string> &queries, const std::vector<std::string> &labels,
+               const std::string &path, bool header, bool bedgraph) {
+    if (a.window == 0) die("window must be greater than 0", 1);
+    const auto t0 = std::chrono::steady_clock::now();
+    Fasta fa = read_fasta(a.fasta);
+    const auto t1 = std::chrono::steady_clock::now();
+    mkdirs(a.dir);
+    FILE *out = fopen(path.c_str(), "wb");
+    if (!out) die("cannot create " + path, 1);
+    if (header) fputs(kHeader, out);
+    Ctx ctx(a.device);
+    uint64_t nwin = 0;
+    for (size_t r = 0; r < fa.ids.size(); r++) {
+        uint64_t n = fa.offsets[r + 1] - fa.offsets[r];
+        nwin += n / a.window + (n % a.window != 0);
+    }
+    std::vector<uint64_t> f(nwin * queries.size() + 1), r(nwin * queries.size() + 1);
+    std::vector<const char *> qp;
+    std::vector<uint32_t> ql;
+    for (auto &q : queries) { qp.push_back(q.c_str()); ql.push_back((uint32_t)q.size()); }
+    tidk_seqbuf *buf = nullptr;
+    ctx.check(tidk_cuda_seqbuf_upload(ctx.h, fa.seq.data(), fa.offsets.data(), (uint32_t)fa.ids.size(), &buf));
+    float ms = 0;
+    uint32_t nl = 0;
+    ctx.check(tidk_cuda_window_counts_resident(ctx.h, buf, a.window, qp.data(), ql.data(), (uint32_t)qp.size(), f.data(),
+                                               r.data(), &ms, &nl));
+    tidk_cuda_seqbuf_free(ctx.h, buf);
+    const auto t2 = std::chrono::steady_clock::now();
+    write_rows(out, fa, a.window, labels, f, r, bedgraph);
+    fclose(out);
+    fprintf(stderr, "[+]\tFinished searching genome.\n");
+    if (a.stats) {
+        const auto t3 = std::chrono::steady_clock::now();
+        auto s = [](auto x, auto y) { return std::chrono::duration<double>(y - x).count(); };
+        fprintf(stderr, "{\"bases\": %zu, \"kernel_ms\": %.4f, \"kernel_launches\": %u, \"kernel_gbases_s\": %.1f, "
+                        "\"parse_s\": %.3f, \"upload_and_count_s\": %.3f, \"write_s\": %.3f, \"end_to_end_gbases_s\": %.3f}\n",
+                fa.seq.size(), ms, nl, ms > 0 ? fa.seq.size() / (ms * 1e-3) / 1e9 : 0.0, s(t0, t1), s(t1, t2), s(t2, t3),
+                fa.seq.size() / s(t0, t3) / 1e9);
+    }
+    return 0;
+}
+
+int cmd_search(const Args &a) { // search::search, search.rs:10-79
+    if (a.fasta.empty() || a.string_.empty() || a.output.empty() || a.dir.empty())
+        die("search needs <FASTA> --string --output --dir");
+    if (a.extension != "tsv" && a.extension != "bedgraph") die("invalid value '" + a.extension + "' for '--extension'");
+    fprintf(stderr, "[+]\tSearching genome for telomeric repeat: %s\n", a.string_.c_str());
+    const std::string fwd = ascii_upper(a.string_); // search.rs:93
+    const std::string path = a.dir + "/" + a.output + "_telomeric_repeat_windows." + a.extension;
+    return run_counts(a, {fwd}, {fwd}, path, a.extension == "tsv", a.extension != "tsv");
+}
+
+int cmd_find(const Args &a) { // finder::finder, finder.rs:13-107
+    const std::string db = a.database.empty() ? database_path() : a.database;
+    CladeTable table = load_clades(db);
+    if (a.print) { // finder.rs:15-18 prints the table and exits 1; the pretty `tabled` layout is out of scope
+        for (const std::string &c : get_clades(table)) {
+            std::string line = c + "\t";
+            auto seqs = return_telomere_sequence(table, c);
+            for (size_t i = 0; i < seqs.size(); i++) line += (i ? ", " : "") + seqs[i];
+            fprintf(stderr, "%s\n", line.c_str());
+        }
+        return 1;
+    }
+    if (a.fasta.empty() || a.clade.empty() || a.output.empty() || a.dir.empty()) die("find needs <FASTA> --clade --output --dir");
+    bool known = false;
+    for (const std::string &c : get_clades(table)) known = known || c == a.clade;
+    if (!known) die("invalid value '" + a.clade + "' for '--clade <CLADE>'");
+    const std::vector<std::string> reps = return_telomere_sequence(table, a.clade);
+    if (reps.size() == 1) fprintf(stderr, "[+]\tSearching genome for a single telomeric repeat: %s\n", reps[0].c_str());
+    else if (reps.size() > 1) {
+        fprintf(stderr, "[+]\tSearching genome for %zu telomeric repeats:\n", reps.size());
+        for (auto &r : reps) fprintf(stderr, "[+]\t\t%s\n", r.c_str());
+    }
+    const std::string path = a.dir + "/" + a.output + "_telomeric_repeat_windows.tsv";
+    return run_counts(a, reps, reps, path, true, false); // repeats verbatim, finder.rs:129-136
+}
+
+int cmd_explore(const Args &a) { // explore::explore, explore.rs:20-149
+    if (a.fasta.empty()) die("explore needs <FASTA>");
+    // main.rs:71-88: --length is required unless --minimum and --maximum are both given, and
+    // defaults to 0 when --minimum is present
+    long long length = a.length;
+    if (length < 0) {
+        if (!(a.have_min && a.have_max)) die("the following required arguments were not provided: --length <LENGTH> (or both --minimum and --maximum)");
+        length = 0;
+    }
+    if (a.distance > 0.5) die("Distance from chromosome end as a proportion can't be more than 0.5.", 1); // explore.rs:41-43
+    uint32_t kmin, kmax;
+    if (length > 0) {
+        fprintf(stderr, "[+]\tExploring genome for potential telomeric repeats of length: %lld\n", length);
+        kmin = kmax = (uint32_t)length;
+    } else {
+        fprintf(stderr, "[+]\tExploring genome for potential telomeric repeats between lengths %lld and %lld.\n", a.minimum, a.maximum);
+        for (long long k = a.minimum; k <= a.maximum; k++) fprintf(stderr, "[+]\t\tFinding telomeric repeat length: %lld\n", k);
+        kmin = (uint32_t)a.minimum; kmax = (uint32_t)a.maximum;
+    }
+    Fasta fa = read_fasta(a.fasta);
+    std::vector<std::pair<std::string, long long>> rows;
+    float ms = 0;
+    uint32_t nl = 0;
+    uint64_t n = 0;
+    if (kmax >= kmin && kmin > 0) {
+        Ctx ctx(a.device);
+        tidk_seqbuf *buf = nullptr;
+        ctx.check(tidk_cuda_seqbuf_upload(ctx.h, fa.seq.data(), fa.offsets.data(), (uint32_t)fa.ids.size(), &buf));
+        tidk_run *runs = nullptr;
+        // `threshold as usize` (explore.rs:71,116): a negative i32 wraps to a huge usize
+        const uint64_t thr = a.threshold < 0 ? (uint64_t)(int64_t)a.threshold : (uint64_t)a.threshold;
+        ctx.check(tidk_cuda_explore_runs_resident(ctx.h, buf, a.distance, kmin, kmax, thr, &runs, &n, &ms, &nl));
+        tidk_cuda_seqbuf_free(ctx.h, buf);
+        std::vector<std::string> labels;
+        std::vector<long long> counts;
+        for (uint64_t i = 0; i < n; i++) {
+            const tidk_run &r = runs[i];
+            const uint64_t o = fa.offsets[r.record], e = fa.offsets[r.record + 1], len = e - o;
+            double v = std::ceil((double)len * a.distance); // explore.rs:156
+            const uint64_t dist = v > 0 ? (uint64_t)v : 0;
+            const uint64_t base = r.slice == 0 ? o : e - dist;
+            std::string lab((const char *)fa.seq.data() + base + r.label_pos, r.k);
+            lab = ascii_upper(lab);
+            if (period(lab) < 3) continue; // filter_by_frequency's simple-repeat half, explore.rs:265-274,351-354
+            labels.push_back(lab);
+            counts.push_back((long long)((r.end - r.start) / r.k));
+        }
+        tidk_cuda_free_runs(runs);
+        rows = estimates(labels, counts);
+    }
+    fprintf(stderr, "[+]\tFinished searching genome\n[+]\tGenerating output\n");
+    printf("canonical_repeat_unit\tcount_repeat_runs_gt_%lld\n", a.threshold); // explore.rs:140
+    for (auto &r : rows) printf("%s\t%lld\n", r.first.c_str(), r.second);
+    if (a.stats) fprintf(stderr, "{\"runs\": %llu, \"kernel_ms\": %.4f, \"kernel_launches\": %u}\n", (unsigned long long)n, ms, nl);
+    return 0;
+}
+
+} // namespace
+
+int main(int argc, char **argv) {
+    try {
+        Args a = parse(argc, argv);
+        if (a.sub == "search") return cmd_search(a);
+        if (a.sub == "find") return cmd_find(a);
+        return cmd_explore(a);
+    } catch (const std::exception &e) {
+        fprintf(stderr, "Error: %s\n", e.what());
+        return 1;
+    }
+}

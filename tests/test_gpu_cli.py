@@ -1,0 +1,99 @@
+"""The C++ host driver (bin/tidk) end to end: FASTA file in, the reference's output files out,
+compared byte for byte with the oracle's text."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TIDK = os.path.join(ROOT, "telomeric_identifier_b200", "bin", "tidk")
+DB = os.path.join(ROOT, "tests", "golden", "clades_min.csv")
+
+
+def write_fasta(path, ids, seq, off, width=60, gz=False):
+    import gzip
+    opener = gzip.open if gz else open
+    with opener(path, "wb") as fh:
+        for i, rid in enumerate(ids):
+            fh.write(f">{rid} synthetic record {i}\n".encode())
+            s = seq[int(off[i]):int(off[i + 1])].tobytes()
+            for j in range(0, len(s), width):
+                fh.write(s[j:j + width] + b"\n")
+
+
+def run(*args):
+    return subprocess.run([TIDK, *args], capture_output=True, text=True, timeout=300)
+
+
+@pytest.fixture(scope="module")
+def genome(tmp_path_factory):
+    from telomeric_identifier_b200 import synth
+    d = tmp_path_factory.mktemp("cli")
+    ids, seq, off = synth.config2(scale=0.01)
+    fa = str(d / "g.fa")
+    write_fasta(fa, ids, seq, off)
+    seqs = [seq[int(off[i]):int(off[i + 1])].tobytes() for i in range(len(ids))]
+    return d, fa, ids, seq, off, seqs
+
+
+@pytest.mark.gpu
+def test_cli_search_tsv_and_bedgraph(genome):
+    d, fa, ids, seq, off, seqs = genome
+    r = run("search", fa, "-s", "ttagg", "-o", "out", "-d", str(d / "s"), "--gpu-stats")
+    assert r.returncode == 0, r.stderr
+    assert "[+]\tSearching genome for telomeric repeat: ttagg" in r.stderr
+    assert f"[+]\tChromosome {ids[0]} processed" in r.stderr and "[+]\tFinished searching genome." in r.stderr
+    got = open(d / "s" / "out_telomeric_repeat_windows.tsv").read()
+    assert got == O.search_text(ids, seqs, b"ttagg", 10000)
+    r = run("search", fa, "--string", "TTAGG", "--window", "3333", "--output", "b", "--dir", str(d / "s"), "-e", "bedgraph")
+    assert r.returncode == 0, r.stderr
+    assert open(d / "s" / "b_telomeric_repeat_windows.bedgraph").read() == O.search_text(ids, seqs, b"TTAGG", 3333, "bedgraph")
+
+
+@pytest.mark.gpu
+def test_cli_find_clades(genome):
+    d, fa, ids, seq, off, seqs = genome
+    from telomeric_identifier_b200 import clades
+    for clade in ("Lepidoptera", "Hymenoptera", "Coleoptera"):
+        r = run("find", fa, "-c", clade, "-o", clade, "-d", str(d / "f"), "--database", DB)
+        assert r.returncode == 0, r.stderr
+        reps = clades.return_telomere_sequence(clade, DB)
+        want = O.find_text(ids, seqs, [x.encode() for x in reps], 10000)
+        assert open(d / "f" / f"{clade}_telomeric_repeat_windows.tsv").read() == want
+    assert "[+]\tSearching genome for 15 telomeric repeats:" in run("find", fa, "-c", "Hymenoptera", "-o", "h", "-d", str(d / "f"), "--database", DB).stderr
+
+
+@pytest.mark.gpu
+def test_cli_gzip_input(genome, tmp_path):
+    d, fa, ids, seq, off, seqs = genome
+    gz = str(tmp_path / "g.fa.gz")
+    write_fasta(gz, ids[:5], seq, off, width=80, gz=True)
+    r = run("search", gz, "-s", "AACCT", "-o", "z", "-d", str(tmp_path))
+    assert r.returncode == 0, r.stderr
+    assert open(tmp_path / "z_telomeric_repeat_windows.tsv").read() == O.search_text(ids[:5], seqs[:5], b"AACCT", 10000)
+
+
+@pytest.mark.gpu
+def test_cli_explore(genome):
+    d, fa, ids, seq, off, seqs = genome
+    r = run("explore", fa, "--minimum", "5", "--maximum", "12", "-t", "20", "--distance", "0.05")
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == O.explore_text(seqs, 0.05, 5, 12, 20, literal=True)
+    r = run("explore", fa, "--length", "5", "-t", "100", "--distance", "0.01")
+    assert r.returncode == 0 and r.stdout == O.explore_text(seqs, 0.01, 5, 5, 100, literal=True)
+    assert run("explore", fa, "-l", "5", "--distance", "0.6").returncode == 1  # explore.rs:41-43
+
+
+def test_cli_argument_errors(tmp_path):
+    """No GPU needed: argument handling fails before the device is touched."""
+    import __graft_entry__ as g
+    g.build()
+    assert run("find", "x.fa", "-c", "NotAClade", "-o", "o", "-d", str(tmp_path), "--database", DB).returncode == 2
+    assert run("search", "x.fa", "-o", "o", "-d", str(tmp_path)).returncode == 2
+    assert run("explore", "x.fa").returncode == 2  # needs --length or both --minimum and --maximum (main.rs:71-76)
+    assert run("plot", "-t", "x.tsv").returncode == 2
+    p = run("find", "--print", "--database", DB)
+    assert p.returncode == 1 and "Lepidoptera\tAACCT" in p.stderr

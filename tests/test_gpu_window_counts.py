@@ -199,3 +199,20 @@ def test_full_size_properties(ctx):
     # the planted telomere arrays are seen at both ends of chromosome 1
     assert int(f[0]) > 100 and int(r[int(nw[0]) - 1]) > 100
     b.free()
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_sharded_ranks_emulated_on_one_gpu(ctx, world):
+    """the ranks' shards computed one after another on this GPU and merged on the host
+    equal the single-GPU (and oracle) result -- no halo is needed because shards cut at window multiples."""
+    from telomeric_identifier_b200 import sharding, synth
+    ids, seq, off = synth.config4(scale=0.004)
+    qs = [b"TTAGGG"]
+    plans = sharding.plan_shards(off, 10000, world)
+    per_rank = []
+    for r in range(world):
+        ls, lo = sharding.shard_batch(seq, off, plans[r], 10000)
+        per_rank.append(ctx.window_counts(ls, lo, 10000, qs))
+    f, r = sharding.merge_counts(plans, per_rank, off, 10000, 1)
+    of, orr = O.window_counts(seq, off, 10000, qs, False)
+    assert (f == of).all() and (r == orr).all()
