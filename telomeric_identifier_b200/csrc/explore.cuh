@@ -64,12 +64,12 @@ struct ExploreJob {
 };
 
 struct ExploreScratch {
-    void *slices = nullptr, *tile_base = nullptr, *events = nullptr, *misc = nullptr;
-    size_t slices_cap = 0, tile_cap = 0, events_cap = 0;
+    void *slices = nullptr, *tile_base = nullptr, *events = nullptr, *misc = nullptr, *items = nullptr;
+    size_t slices_cap = 0, tile_cap = 0, events_cap = 0, items_cap = 0;
 };
 
 inline void explore_scratch_release(ExploreScratch &s) {
-    for (void *p : {s.slices, s.tile_base, s.events, s.misc})
+    for (void *p : {s.slices, s.tile_base, s.events, s.misc, s.items})
         if (p) cudaFree(p);
     s = ExploreScratch();
 }
@@ -196,105 +196,6 @@ inline void events_to_runs(std::vector<RunEvent> &ev, uint64_t threshold, std::v
         }
         flush();
     }
-}
-
-inline int explore_runs_device(ExploreScratch &sc, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1,
-                               int sm_count, const uint8_t *d_seq, const uint64_t *d_off,
-                               const uint64_t *h_off, uint32_t n_records, double distance,
-                               uint32_t kmin, uint32_t kmax, uint64_t threshold, tidk_run **out_runs,
-                               uint64_t *n_runs, float *kernel_ms, uint32_t *kernel_launches,
-                               std::string &err) {
-    (void)d_off;
-    auto cuerr = [&](cudaError_t e, const char *what) {
-        err = std::string(what) + " failed: " + cudaGetErrorString(e);
-        return e == cudaErrorMemoryAllocation ? TIDK_ENOMEM : TIDK_ECUDA;
-    };
-    if (n_records > 0x7FFFFFFFu) { err = "too many records"; return TIDK_EARG; }
-    const uint32_t n_slices = n_records * 2;
-    std::vector<SliceDesc> slices(n_slices);
-    std::vector<uint64_t> tile_base((size_t)n_slices + 1, 0);
-    uint64_t scanned = 0;
-    for (uint32_t r = 0; r < n_records; r++) {
-        const uint64_t len = h_off[r + 1] - h_off[r];
-        const uint64_t dist = split_dist(len, distance);
-        if (dist > len) { err = "slice longer than record"; return TIDK_EARG; }
-        slices[2 * r] = {h_off[r], dist};                 // explore.rs:157
-        slices[2 * r + 1] = {h_off[r] + (len - dist), dist}; // explore.rs:158
-        const uint64_t tiles = (dist + kExploreTile - 1) / kExploreTile;
-        tile_base[2 * r + 1] = tile_base[2 * r] + tiles;
-        tile_base[2 * r + 2] = tile_base[2 * r + 1] + tiles;
-        scanned += 2 * dist;
-    }
-    const uint64_t n_tiles = tile_base[n_slices];
-    std::vector<tidk_run> runs;
-    if (n_tiles > 0) {
-        cudaError_t e;
-        auto grow = [&](void *&p, size_t &cap, size_t need) -> cudaError_t {
-            if (p && need <= cap) return cudaSuccess;
-            if (p) cudaFree(p);
-            p = nullptr; cap = 0;
-            cudaError_t e2 = cudaMalloc(&p, need + need / 8 + 256);
-            if (e2 == cudaSuccess) cap = need + need / 8 + 256; else p = nullptr;
-            return e2;
-        };
-        if ((e = grow(sc.slices, sc.slices_cap, slices.size() * sizeof(SliceDesc))) != cudaSuccess) return cuerr(e, "cudaMalloc(slices)");
-        if ((e = grow(sc.tile_base, sc.tile_cap, tile_base.size() * 8)) != cudaSuccess) return cuerr(e, "cudaMalloc(tile_base)");
-        if (!sc.misc && (e = cudaMalloc(&sc.misc, 256)) != cudaSuccess) { sc.misc = nullptr; return cuerr(e, "cudaMalloc(misc)"); }
-        if ((e = cudaMemcpyAsync(sc.slices, slices.data(), slices.size() * sizeof(SliceDesc), cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuerr(e, "H2D slices");
-        if ((e = cudaMemcpyAsync(sc.tile_base, tile_base.data(), tile_base.size() * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuerr(e, "H2D tile_base");
-
-        uint64_t cap = std::max<uint64_t>(1u << 16, scanned / 64);
-        std::vector<RunEvent> events;
-        float ms_total = 0.f;
-        uint32_t launches = 0;
-        for (int attempt = 0; attempt < 3; attempt++) {
-            if ((e = grow(sc.events, sc.events_cap, cap * sizeof(RunEvent))) != cudaSuccess) return cuerr(e, "cudaMalloc(events)");
-            if ((e = cudaMemsetAsync(sc.misc, 0, 256, st)) != cudaSuccess) return cuerr(e, "memset");
-            ExploreJob job{};
-            job.seq = d_seq;
-            job.slices = (const SliceDesc *)sc.slices;
-            job.tile_base = (const uint64_t *)sc.tile_base;
-            job.n_tiles = n_tiles;
-            job.n_slices = n_slices;
-            job.kmin = kmin; job.kmax = kmax;
-            job.events = (RunEvent *)sc.events;
-            job.cap_events = cap;
-            job.work_counter = (unsigned long long *)sc.misc;
-            job.n_events = (unsigned long long *)sc.misc + 1;
-            job.err_flags = (uint32_t *)((char *)sc.misc + 128);
-            uint64_t want = (n_tiles + 7) / 8, maxb = (uint64_t)sm_count * 8;
-            int grid = (int)std::max<uint64_t>(1, std::min(want, maxb));
-            cudaEventRecord(ev0, st);
-            explore_events_kernel<<<grid, 256, 0, st>>>(job);
-            cudaEventRecord(ev1, st);
-            launches++;
-            if ((e = cudaGetLastError()) != cudaSuccess) return cuerr(e, "explore_events_kernel launch");
-            unsigned long long h_counts[2] = {0, 0};
-            uint32_t h_err = 0;
-            if ((e = cudaMemcpyAsync(h_counts, sc.misc, 16, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuerr(e, "D2H counters");
-            if ((e = cudaMemcpyAsync(&h_err, (char *)sc.misc + 128, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuerr(e, "D2H flags");
-            if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuerr(e, "explore_events_kernel");
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, ev0, ev1);
-            ms_total += ms;
-            if (h_err & 1u) { err = "sequence contains a byte >= 0x80 (str::from_utf8 panics, explore.rs:212)"; return TIDK_ENONASCII; }
-            const uint64_t ne = h_counts[1];
-            if (ne > cap) { cap = ne; continue; } // event buffer too small: rerun with the exact size
-            events.resize(ne);
-            if (ne && (e = cudaMemcpy(events.data(), sc.events, ne * sizeof(RunEvent), cudaMemcpyDeviceToHost)) != cudaSuccess) return cuerr(e, "D2H events");
-            break;
-        }
-        if (kernel_ms) *kernel_ms = ms_total;
-        if (kernel_launches) *kernel_launches = launches;
-        events_to_runs(events, threshold, runs);
-    }
-    *n_runs = runs.size();
-    if (!runs.empty()) {
-        *out_runs = (tidk_run *)malloc(runs.size() * sizeof(tidk_run));
-        if (!*out_runs) { err = "out of host memory"; *n_runs = 0; return TIDK_ENOMEM; }
-        memcpy(*out_runs, runs.data(), runs.size() * sizeof(tidk_run));
-    }
-    return TIDK_OK;
 }
 
 } // namespace tidk

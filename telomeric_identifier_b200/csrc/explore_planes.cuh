@@ -1,0 +1,302 @@
+// explore_planes.cuh -- tandem k-mer run detection on bit-planes (k <= 16).
+//
+// Same contract as explore_events_kernel (explore.cuh): emit one RunEvent per raw-run
+// boundary of every (slice, k).  Restated in look-behind form, with q a slice-relative
+// position and t the slice:
+//     D_k[q] = t[q] == t[q-k]                       (both inside the slice)
+//     G_k[q] = D_k[q-k+1] & ... & D_k[q]            (the k-mer ending at q equals the one before it)
+// At a chunk end q = (j+2)k - 1, G_k[q] is the reference's raw_j = (c_j == c_{j+1})
+// (explore.rs:208) and G_k[q-k] is raw_{j-1}; where they differ chunk j starts a raw run or is
+// the last entry of one.  Positions up to m + k - 1 are evaluated so that the run that touches
+// the end of the slice is closed (G is 0 beyond the slice: a partial chunk equals nothing).
+//
+// A lane owns 32 bases per 1 KiB block (one 256-bit load) as planes lo / hi / va
+// (va = base is A/C/G/T in any case AND inside the slice).  D_k costs three funnel shifts and
+// three LOP3 for the lane's word; the previous lane's D_k arrives by SHFL; G_k is built with
+// log2(k) shift-AND doubling steps on the (previous | current) word pair; the chunk-end phase
+// mask is a constant shifted by (q mod k).  Events are rare (4^-k per chunk on random
+// sequence), so the append path is off the hot path.
+//
+// Exactness.  Plane equality is byte equality only for bases in {A,C,G,T} of uniform case.  A
+// block (and the one after it) in which any in-slice base is something else, or whose letter
+// case is mixed or differs from the previous block's, is evaluated byte-wise instead
+// (warp-uniform branch) -- N runs and soft-mask edges take the slow path, everything else the
+// fast one.
+#pragma once
+#include <cstddef>
+
+#include "explore.cuh"
+#include "planes.cuh"
+
+namespace tidk {
+
+constexpr int kPlaneMaxK = 16;
+constexpr uint32_t kExTile = 16384; // chunk-end positions owned by one work item
+
+struct __align__(64) ExItem {
+    uint64_t scan0;     // absolute offset of block 0 (multiple of 32)
+    int64_t rel0;       // scan0 - slice_beg (slice-relative position of block 0, lane 0, bit 0)
+    uint64_t slice_len; // m
+    uint32_t slice;     // 2 * record + (0 left | 1 right)
+    uint16_t nblk;
+    uint16_t own_lo, own_hi; // owned chunk-end positions, relative to scan0
+    uint16_t v_lo, v_hi;     // bases inside the slice, relative to scan0
+    uint16_t pad;
+    uint8_t pad2[8];
+    uint8_t r0[kPlaneMaxK];  // r0[k-1] = rel0 mod k (non-negative); 16-byte aligned (offset 48)
+};
+static_assert(offsetof(ExItem, r0) % 16 == 0, "r0 is read as one uint4");
+static_assert(sizeof(ExItem) == 64, "ExItem is two 256-bit loads");
+
+struct ExPrepJob {
+    const SliceDesc *slices;
+    const uint64_t *tile_base; // [n_slices + 1]
+    ExItem *items;
+    uint64_t n_items;
+    uint32_t n_slices, kmax;
+};
+
+__global__ void __launch_bounds__(256) explore_items_kernel(const ExPrepJob job) {
+    const uint64_t item = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= job.n_items) return;
+    uint32_t lo = 0, hi = job.n_slices;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (job.tile_base[mid] <= item) lo = mid; else hi = mid;
+    }
+    const SliceDesc sd = job.slices[lo];
+    const uint64_t tile_off = (item - job.tile_base[lo]) * (uint64_t)kExTile;
+    const uint64_t q_end = sd.len + job.kmax; // chunk ends up to m + k - 1 close the last run
+    const uint64_t own_end = tile_off + kExTile < q_end ? tile_off + kExTile : q_end;
+    ExItem d;
+    memset(&d, 0, sizeof d);
+    uint64_t scan0 = (sd.beg + tile_off) & ~31ull;
+    if (tile_off > 0) scan0 -= 1024; // real look-behind planes for the first owned block
+    d.scan0 = scan0;
+    d.rel0 = (int64_t)scan0 - (int64_t)sd.beg;
+    d.slice_len = sd.len;
+    d.slice = lo;
+    const uint64_t end_abs = sd.beg + own_end;
+    d.nblk = (uint16_t)((end_abs - scan0 + 1023) >> 10);
+    d.own_lo = (uint16_t)(sd.beg + tile_off - scan0);
+    d.own_hi = (uint16_t)(end_abs - scan0);
+    d.v_lo = (uint16_t)(d.rel0 < 0 ? -d.rel0 : 0);
+    const int64_t vhi = (int64_t)sd.len - d.rel0;
+    d.v_hi = (uint16_t)(vhi < 0 ? 0 : (vhi > 65535 ? 65535 : vhi));
+    for (int k = 1; k <= kPlaneMaxK; k++) {
+        int64_t r = d.rel0 % k;
+        if (r < 0) r += k;
+        d.r0[k - 1] = (uint8_t)r;
+    }
+    job.items[item] = d;
+}
+
+struct ExJob {
+    const uint8_t *seq;
+    const SliceDesc *slices;
+    const ExItem *items;
+    uint64_t n_items;
+    uint32_t kmin, kmax;
+    RunEvent *events;
+    unsigned long long *n_events;
+    uint64_t cap_events;
+    unsigned long long *work_counter;
+    uint32_t *err_flags;
+};
+
+__device__ __forceinline__ void emit_event(const ExJob &job, uint32_t slice, uint32_t k, uint64_t chunk,
+                                           bool start, bool joins) {
+    RunEvent ev;
+    ev.slice = slice; ev.k = (uint8_t)k; ev.type = start ? 0 : 1; ev.joins = joins ? 1 : 0; ev.pad = 0;
+    ev.chunk = chunk;
+    unsigned long long idx = atomicAdd(job.n_events, 1ull);
+    if (idx < job.cap_events) job.events[idx] = ev;
+}
+
+// byte-wise G_k[q] (exact for any bytes)
+__device__ __forceinline__ bool g_bytes(const uint8_t *t, int64_t m, int k, int64_t q) {
+    if (q < 2 * (int64_t)k - 1 || q >= m) return false;
+    const uint8_t *a = t + (q - k + 1);
+    for (int j = 0; j < k; j++)
+        if (a[j] != a[j - k]) return false;
+    return true;
+}
+
+__device__ __forceinline__ bool chunks_equal_upper(const uint8_t *t, int k, uint64_t j) {
+    const uint8_t *a = t + (j - 1) * (uint64_t)k;
+    for (int i = 0; i < k; i++)
+        if (dev_upper(a[i]) != dev_upper(a[i + k])) return false;
+    return true;
+}
+
+template <int K>
+__host__ __device__ constexpr uint32_t periodic_mask() {
+    uint32_t m = 0;
+    for (int b = 0; b < 32; b += K) m |= 1u << b;
+    return m;
+}
+
+struct Planes3 {
+    uint32_t lo, hi, va;
+};
+
+// run-of-K detection on the (lo | hi) word pair: returns G for both words
+template <int K>
+__device__ __forceinline__ void runs_of(uint32_t d_lo, uint32_t d_hi, uint32_t &g_lo, uint32_t &g_hi) {
+    uint32_t a_lo = d_lo, a_hi = d_hi;
+    int len = 1;
+#pragma unroll
+    for (int step = 0; step < 4; step++) {
+        if (len * 2 <= K) {
+            const uint32_t n_hi = a_hi & __funnelshift_l(a_lo, a_hi, len);
+            const uint32_t n_lo = a_lo & (a_lo << len);
+            a_hi = n_hi; a_lo = n_lo;
+            len *= 2;
+        }
+    }
+    if (len < K) { // two overlapping runs of `len` cover K (K < 2 * len)
+        const int s = K - len;
+        const uint32_t n_hi = a_hi & __funnelshift_l(a_lo, a_hi, s);
+        const uint32_t n_lo = a_lo & (a_lo << s);
+        a_hi = n_hi; a_lo = n_lo;
+    }
+    g_lo = a_lo; g_hi = a_hi;
+}
+
+template <int K>
+__device__ __forceinline__ void explore_k(const ExJob &job, const Planes3 &cur, const Planes3 &prv,
+                                          uint32_t &carry_d, int lane, uint32_t x0 /* (rel0 mod K) + block/lane offset */,
+                                          uint32_t own, bool emit, uint32_t slice, const uint8_t *t,
+                                          int64_t p /* slice-relative position of bit 0 */) {
+    // D for this lane's word
+    const uint32_t lo_k = __funnelshift_l(prv.lo, cur.lo, K);
+    const uint32_t hi_k = __funnelshift_l(prv.hi, cur.hi, K);
+    const uint32_t va_k = __funnelshift_l(prv.va, cur.va, K);
+    const uint32_t d_hi = ~((cur.lo ^ lo_k) | (cur.hi ^ hi_k)) & cur.va & va_k;
+    const uint32_t d_lo = lane_lookbehind(d_hi, carry_d, lane);
+    carry_d = d_hi;
+    if (!emit) return; // special block: only the carries are kept consistent
+    uint32_t g_lo, g_hi;
+    runs_of<K>(d_lo, d_hi, g_lo, g_hi);
+    const uint32_t g_prev = __funnelshift_l(g_lo, g_hi, K); // G[q - K]
+    // chunk ends: bits b with (r + b) mod K == K - 1, r = p mod K
+    const uint32_t r = x0 % K; // K is a compile-time constant: multiply-shift
+    const uint32_t s = (K - 1 + K - r) % K;
+    uint32_t ev = (g_hi ^ g_prev) & (periodic_mask<K>() << s) & own;
+    while (ev) { // rare
+        const int b = __ffs(ev) - 1;
+        ev &= ev - 1;
+        const int64_t q = p + b;
+        const uint64_t j = (uint64_t)((q + 1) / K) - 2;
+        const bool start = (g_hi >> b) & 1u;
+        const bool joins = start && j > 0 && chunks_equal_upper(t, K, j);
+        emit_event(job, slice, K, j, start, joins);
+    }
+}
+
+// byte-wise evaluation of this lane's owned chunk ends (special blocks)
+__device__ __forceinline__ void explore_k_bytes(const ExJob &job, int k, uint32_t own, uint32_t slice,
+                                                const uint8_t *t, int64_t m, int64_t p) {
+    for (int b = 0; b < 32; b++) {
+        if (!((own >> b) & 1u)) continue;
+        const int64_t q = p + b;
+        if (q < 0 || (q + 1) % k != 0) continue;
+        const bool cur = g_bytes(t, m, k, q), prv = g_bytes(t, m, k, q - k);
+        if (cur == prv) continue;
+        const uint64_t j = (uint64_t)((q + 1) / k) - 2;
+        const bool joins = cur && j > 0 && chunks_equal_upper(t, k, j);
+        emit_event(job, slice, (uint32_t)k, j, cur, joins);
+    }
+}
+
+__device__ __forceinline__ uint32_t r0_of(const uint4 &v, int i) { // byte i of a 16-byte vector
+    const uint32_t wsel = i < 4 ? v.x : i < 8 ? v.y : i < 12 ? v.z : v.w;
+    return (wsel >> (8 * (i & 3))) & 0xFFu;
+}
+
+// KMIN > 0: the k range is a compile-time constant (default 5..12); KMIN == 0: run-time range.
+template <int KMIN, int KMAX>
+__global__ void __launch_bounds__(256, 2) explore_planes_kernel(const ExJob job) {
+    const int lane = threadIdx.x & 31;
+    uint32_t nonascii = 0;
+    for (;;) {
+        unsigned long long item = 0;
+        if (lane == 0) item = atomicAdd(job.work_counter, 1ull);
+        item = __shfl_sync(0xFFFFFFFFu, item, 0);
+        if (item >= job.n_items) break;
+        const ExItem *ip = job.items + item;
+        const uint64_t scan0 = ip->scan0;
+        const int64_t rel0 = ip->rel0;
+        const int64_t m = (int64_t)ip->slice_len;
+        const uint32_t slice = ip->slice;
+        const uint32_t nblk = ip->nblk;
+        const int own_lo = ip->own_lo, own_hi = ip->own_hi, v_lo = ip->v_lo, v_hi = ip->v_hi;
+        const uint4 rq0 = *reinterpret_cast<const uint4 *>(ip->r0);
+        const uint8_t *t = job.seq + ((int64_t)scan0 - rel0); // slice start
+
+        Planes3 own_prev = {0u, 0u, 0u};
+        uint32_t carry_d[kPlaneMaxK];
+#pragma unroll
+        for (int i = 0; i < kPlaneMaxK; i++) carry_d[i] = 0;
+        bool dirty_prev = false;
+        int case_prev = -1; // -1 unknown, 0 all upper, 1 all lower
+
+        uint32_t w[8];
+        const uint8_t *ptr = job.seq + scan0 + (uint32_t)lane * 32u;
+        ld256_stream(ptr, w);
+        for (uint32_t blk = 0; blk < nblk; blk++) {
+            const Nibbles nib = to_nibbles(w);
+            if (blk + 1 < nblk) { ptr += 1024; ld256_stream(ptr, w); }
+            uint32_t na = 0;
+            const Planes P = extract_planes(nib, na);
+            const int prel = (int)(blk << 10) + lane * 32;
+            const uint32_t inslice = range_mask32(v_lo - prel, v_hi - prel);
+            nonascii |= na & inslice;
+            uint32_t own = 0xFFFFFFFFu;
+            if (blk < 2 || blk + 1 == nblk) own = range_mask32(own_lo - prel, own_hi - prel);
+            Planes3 cur;
+            cur.lo = P.lo; cur.hi = P.hi;
+            cur.va = (P.b0 ^ (P.hi & ~P.lo)) & P.ok & inslice;
+
+            // letter case (ASCII bit 5 = bit 1 of the high nibbles).  Plane equality is byte equality
+            // only under uniform case; a lane that straddles the slice edge is judged on all its 32
+            // bytes, which can only make the block "mixed" more often (slow path, still exact).
+            const uint32_t all_l = nib.Y[0] & nib.Y[1] & nib.Y[2] & nib.Y[3];
+            const uint32_t any_l = nib.Y[0] | nib.Y[1] | nib.Y[2] | nib.Y[3];
+            const bool lane_in = inslice != 0;
+            const bool lane_any_lower = (any_l & 0x22222222u) != 0;
+            const bool lane_all_lower = (all_l & 0x22222222u) == 0x22222222u;
+            const bool blk_upper = __all_sync(0xFFFFFFFFu, !lane_in || !lane_any_lower);
+            const bool blk_lower = __all_sync(0xFFFFFFFFu, !lane_in || lane_all_lower);
+            const bool blk_any = __any_sync(0xFFFFFFFFu, lane_in);
+            const int case_now = blk_upper ? 0 : (blk_lower ? 1 : 2);
+            const bool case_bad = case_now == 2 || (case_prev >= 0 && blk_any && case_now != case_prev);
+            const bool dirty_now = __any_sync(0xFFFFFFFFu, (~cur.va & inslice) != 0) || case_bad;
+            const bool special = dirty_now || dirty_prev;
+            dirty_prev = dirty_now;
+            if (blk_any) case_prev = case_now == 2 ? -1 : case_now;
+
+            Planes3 prv;
+            prv.lo = lane_lookbehind(cur.lo, own_prev.lo, lane);
+            prv.hi = lane_lookbehind(cur.hi, own_prev.hi, lane);
+            prv.va = lane_lookbehind(cur.va, own_prev.va, lane);
+            own_prev = cur;
+            const int64_t p = rel0 + prel;
+            const uint32_t xoff = (uint32_t)prel; // < 2^15
+#define TIDK_EXK(K)                                                                              \
+    if ((KMIN > 0) ? (K >= KMIN && K <= KMAX) : (job.kmin <= K && K <= job.kmax))                \
+        explore_k<K>(job, cur, prv, carry_d[K - 1], lane, r0_of(rq0, K - 1) + xoff, own, !special, \
+                     slice, t, p);
+            TIDK_EXK(1) TIDK_EXK(2) TIDK_EXK(3) TIDK_EXK(4) TIDK_EXK(5) TIDK_EXK(6) TIDK_EXK(7) TIDK_EXK(8)
+            TIDK_EXK(9) TIDK_EXK(10) TIDK_EXK(11) TIDK_EXK(12) TIDK_EXK(13) TIDK_EXK(14) TIDK_EXK(15) TIDK_EXK(16)
+#undef TIDK_EXK
+            if (special) { // exact byte-wise evaluation of this block's owned chunk ends
+                const uint32_t k0 = KMIN > 0 ? KMIN : job.kmin, k1 = KMIN > 0 ? KMAX : job.kmax;
+                for (uint32_t k = k0; k <= k1; k++) explore_k_bytes(job, (int)k, own, slice, t, m, p);
+            }
+        }
+    }
+    if (__any_sync(0xFFFFFFFFu, nonascii != 0) && lane == 0) atomicOr(job.err_flags, 1u);
+}
+
+} // namespace tidk

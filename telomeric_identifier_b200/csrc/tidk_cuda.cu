@@ -13,7 +13,7 @@
 #include <string>
 #include <vector>
 
-#include "explore.cuh"
+#include "explore_host.cuh"
 #include "window_counts.cuh"
 
 using namespace tidk;

@@ -109,3 +109,44 @@ def test_explore_errors(ctx):
     with pytest.raises(T.TidkCudaError):
         ctx.explore_runs(seq, off, 0.1, 0, 3, 100)
     assert ctx.explore_runs(np.zeros(0, np.uint8), np.array([0], dtype=np.uint64), 0.1, 5, 12, 100).size == 0
+
+
+def test_large_k_uses_bytewise_kernel(ctx):
+    """k > 16 is outside the plane kernel: the byte-wise kernel must give the same answer."""
+    from telomeric_identifier_b200 import synth
+    ids, seq, off = synth.random_records(77, 3, 60000, b"ACGTacgtN", plant=b"TTAGGGTTAGGGTTAGGCA")
+    _runs_equal(ctx, seq, off, 0.5, 15, 20, 0)
+    _runs_equal(ctx, seq, off, 0.25, 19, 19, 2)
+
+
+def test_tile_and_block_boundaries(ctx):
+    """Arrays, N runs and soft-masked stretches placed across 1 KiB block and 16 KiB tile edges."""
+    rng = np.random.default_rng(5)
+    n = 200_000
+    s = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, n)].copy()
+    for pos in (1000, 16380, 32700, 49152 - 7, 65536 + 3, 99990):
+        unit = np.frombuffer(b"TTAGGG", dtype=np.uint8)
+        arr = np.tile(unit, 40)
+        s[pos:pos + arr.size] = arr
+    s[20000:23000] = ord("N")           # N run: equal chunks of N are runs too (and can be the first run)
+    s[40000:40100] |= 0x20              # soft-masked stretch inside random sequence
+    s[65530:65600] |= 0x20              # case change inside an array
+    s[150000:150012] = np.frombuffer(b"acgtacACGTAC", dtype=np.uint8)  # equal after upper-casing only
+    off = np.array([0, n], dtype=np.uint64)
+    for d, k0, k1, thr in ((0.5, 1, 16, 0), (0.5, 5, 12, 3), (0.3, 6, 6, 0), (0.085, 2, 9, 1)):
+        _runs_equal(ctx, s, off, d, k0, k1, thr)
+
+
+def test_many_tiny_records(ctx):
+    """Records shorter than k, than 2k, than one block; offsets at every alignment."""
+    rng = np.random.default_rng(9)
+    parts = []
+    for i in range(400):
+        ln = int(rng.integers(0, 90))
+        unit = np.frombuffer(b"ACGTT"[: int(rng.integers(1, 6))], dtype=np.uint8)
+        parts.append(np.tile(unit, ln // unit.size + 1)[:ln] if i % 3 else np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, ln)])
+    off = np.zeros(len(parts) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([p.size for p in parts])
+    seq = np.concatenate(parts).astype(np.uint8)
+    _runs_equal(ctx, seq, off, 0.5, 1, 8, 0)
+    _runs_equal(ctx, seq, off, 0.2, 3, 5, 1)
