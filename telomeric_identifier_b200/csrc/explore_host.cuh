@@ -19,8 +19,13 @@ inline int explore_runs_device(ExploreScratch &sc, cudaStream_t st, cudaEvent_t 
     };
     if (n_records > 0x7FFFFFFFu) { err = "too many records"; return TIDK_EARG; }
     const bool planes = kmax <= (uint32_t)kPlaneMaxK; // bit-plane kernel; byte-wise kernel otherwise
-    const uint64_t tile = planes ? kExTile : kExploreTile;
     const uint32_t n_slices = n_records * 2;
+    uint64_t tile = kExploreTile;
+    if (planes) { // smaller items when the big ones would leave most of the GPU idle (C3: 60 slices)
+        uint64_t total = 0;
+        for (uint32_t r = 0; r < n_records; r++) total += 2 * split_dist(h_off[r + 1] - h_off[r], distance);
+        tile = total / kExTile < (uint64_t)sm_count * 32 ? kExTileSmall : kExTile;
+    }
     std::vector<SliceDesc> slices(n_slices);
     std::vector<uint64_t> tile_base((size_t)n_slices + 1, 0);
     uint64_t scanned = 0;
@@ -69,7 +74,7 @@ inline int explore_runs_device(ExploreScratch &sc, cudaStream_t st, cudaEvent_t 
             cudaEventRecord(ev0, st);
             if (planes) {
                 if (!items_ready) {
-                    ExPrepJob pj{(const SliceDesc *)sc.slices, (const uint64_t *)sc.tile_base, (ExItem *)sc.items, n_tiles, n_slices, kmax};
+                    ExPrepJob pj{(const SliceDesc *)sc.slices, (const uint64_t *)sc.tile_base, (ExItem *)sc.items, n_tiles, n_slices, kmax, (uint32_t)tile};
                     explore_items_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, st>>>(pj);
                     launches++;
                     items_ready = true;

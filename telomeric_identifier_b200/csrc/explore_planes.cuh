@@ -31,7 +31,8 @@
 namespace tidk {
 
 constexpr int kPlaneMaxK = 16;
-constexpr uint32_t kExTile = 16384; // chunk-end positions owned by one work item
+constexpr uint32_t kExTile = 16384;      // chunk-end positions owned by one work item ...
+constexpr uint32_t kExTileSmall = 4096;  // ... or this when there are too few items to fill the GPU
 
 struct __align__(64) ExItem {
     uint64_t scan0;     // absolute offset of block 0 (multiple of 32)
@@ -53,7 +54,7 @@ struct ExPrepJob {
     const uint64_t *tile_base; // [n_slices + 1]
     ExItem *items;
     uint64_t n_items;
-    uint32_t n_slices, kmax;
+    uint32_t n_slices, kmax, tile;
 };
 
 __global__ void __launch_bounds__(256) explore_items_kernel(const ExPrepJob job) {
@@ -65,9 +66,9 @@ __global__ void __launch_bounds__(256) explore_items_kernel(const ExPrepJob job)
         if (job.tile_base[mid] <= item) lo = mid; else hi = mid;
     }
     const SliceDesc sd = job.slices[lo];
-    const uint64_t tile_off = (item - job.tile_base[lo]) * (uint64_t)kExTile;
+    const uint64_t tile_off = (item - job.tile_base[lo]) * (uint64_t)job.tile;
     const uint64_t q_end = sd.len + job.kmax; // chunk ends up to m + k - 1 close the last run
-    const uint64_t own_end = tile_off + kExTile < q_end ? tile_off + kExTile : q_end;
+    const uint64_t own_end = tile_off + job.tile < q_end ? tile_off + job.tile : q_end;
     ExItem d;
     memset(&d, 0, sizeof d);
     uint64_t scan0 = (sd.beg + tile_off) & ~31ull;
@@ -130,9 +131,9 @@ __device__ __forceinline__ bool chunks_equal_upper(const uint8_t *t, int k, uint
 }
 
 template <int K>
-__host__ __device__ constexpr uint32_t periodic_mask() {
-    uint32_t m = 0;
-    for (int b = 0; b < 32; b += K) m |= 1u << b;
+__host__ __device__ constexpr uint64_t periodic_mask64() { // bits at multiples of K below 64
+    uint64_t m = 0;
+    for (int b = 0; b < 64; b += K) m |= 1ull << b;
     return m;
 }
 
@@ -140,67 +141,58 @@ struct Planes3 {
     uint32_t lo, hi, va;
 };
 
-// run-of-K detection on the (lo | hi) word pair: returns G for both words
-template <int K>
-__device__ __forceinline__ void runs_of(uint32_t d_lo, uint32_t d_hi, uint32_t &g_lo, uint32_t &g_hi) {
-    uint32_t a_lo = d_lo, a_hi = d_hi;
-    int len = 1;
-#pragma unroll
-    for (int step = 0; step < 4; step++) {
-        if (len * 2 <= K) {
-            const uint32_t n_hi = a_hi & __funnelshift_l(a_lo, a_hi, len);
-            const uint32_t n_lo = a_lo & (a_lo << len);
-            a_hi = n_hi; a_lo = n_lo;
-            len *= 2;
-        }
-    }
-    if (len < K) { // two overlapping runs of `len` cover K (K < 2 * len)
-        const int s = K - len;
-        const uint32_t n_hi = a_hi & __funnelshift_l(a_lo, a_hi, s);
-        const uint32_t n_lo = a_lo & (a_lo << s);
-        a_hi = n_hi; a_lo = n_lo;
-    }
-    g_lo = a_lo; g_hi = a_hi;
-}
-
-template <int K>
+// One k for one 32-base word.  WITH_VA: honour the validity plane (edge blocks); interior blocks of
+// a clean stretch have va == all ones for both words and skip it.
+//
+// "All K positions of an aligned chunk match K behind" is a zero-field test on F = ~D over the
+// (previous | current) 64-bit pair, fields = chunks, H = top bit of each field (the chunk ends):
+//     Z = ~(((F & ~H) + ~H)) & ~F & H          -- exact, no carries across fields
+// which costs 2 LOP3 + one 64-bit add + 2 LOP3 regardless of K.
+template <int K, bool WITH_VA, bool EMIT>
 __device__ __forceinline__ void explore_k(const ExJob &job, const Planes3 &cur, const Planes3 &prv,
-                                          uint32_t &carry_d, int lane, uint32_t x0 /* (rel0 mod K) + block/lane offset */,
-                                          uint32_t own, bool emit, uint32_t slice, const uint8_t *t,
+                                          uint32_t &carry_d, int lane, uint32_t x0 /* (rel0 mod K) + offset of bit 0 */,
+                                          uint32_t own, uint32_t slice,
                                           int64_t p /* slice-relative position of bit 0 */) {
-    // D for this lane's word
     const uint32_t lo_k = __funnelshift_l(prv.lo, cur.lo, K);
     const uint32_t hi_k = __funnelshift_l(prv.hi, cur.hi, K);
-    const uint32_t va_k = __funnelshift_l(prv.va, cur.va, K);
-    const uint32_t d_hi = ~((cur.lo ^ lo_k) | (cur.hi ^ hi_k)) & cur.va & va_k;
+    uint32_t d_hi = ~((cur.lo ^ lo_k) | (cur.hi ^ hi_k));
+    if (WITH_VA) d_hi &= cur.va & __funnelshift_l(prv.va, cur.va, K);
     const uint32_t d_lo = lane_lookbehind(d_hi, carry_d, lane);
     carry_d = d_hi;
-    if (!emit) return; // special block: only the carries are kept consistent
-    uint32_t g_lo, g_hi;
-    runs_of<K>(d_lo, d_hi, g_lo, g_hi);
-    const uint32_t g_prev = __funnelshift_l(g_lo, g_hi, K); // G[q - K]
-    // chunk ends: bits b with (r + b) mod K == K - 1, r = p mod K
-    const uint32_t r = x0 % K; // K is a compile-time constant: multiply-shift
-    const uint32_t s = (K - 1 + K - r) % K;
-    uint32_t ev = (g_hi ^ g_prev) & (periodic_mask<K>() << s) & own;
+    if (!EMIT) return; // special block: only the carries are kept consistent
+    // chunk ends of the word pair: positions b (0..63, bit 0 = first base of the previous word)
+    // with (r_lo + b) mod K == K - 1, r_lo = phase of that base = (x0 - 32) mod K
+    const uint32_t r_lo = (x0 + 32u * (K - 1)) % K; // 32 * (K - 1) == -32 (mod K); compile-time K
+    const uint32_t s_lo = K - 1 - r_lo;
+    constexpr uint64_t PER = periodic_mask64<K>();
+    const uint32_t h_lo = (uint32_t)PER << s_lo;
+    const uint32_t h_hi = __funnelshift_l((uint32_t)PER, (uint32_t)(PER >> 32), s_lo);
+    const uint64_t a = ((uint64_t)(~(d_hi | h_hi)) << 32) | (uint32_t)(~(d_lo | h_lo));
+    const uint64_t nh = ((uint64_t)(~h_hi) << 32) | (uint32_t)(~h_lo);
+    const uint64_t sum = a + nh;
+    const uint32_t z_lo = ~(uint32_t)sum & d_lo & h_lo;
+    const uint32_t z_hi = ~(uint32_t)(sum >> 32) & d_hi & h_hi;
+    const uint32_t z_prev = __funnelshift_l(z_lo, z_hi, K); // the chunk before
+    uint32_t ev = (z_hi ^ z_prev) & own;                    // both are subsets of h_hi
     while (ev) { // rare
         const int b = __ffs(ev) - 1;
         ev &= ev - 1;
         const int64_t q = p + b;
         const uint64_t j = (uint64_t)((q + 1) / K) - 2;
-        const bool start = (g_hi >> b) & 1u;
-        const bool joins = start && j > 0 && chunks_equal_upper(t, K, j);
-        emit_event(job, slice, K, j, start, joins);
+        // a run start in a clean block never joins the previous chunk: the two chunks differ as
+        // bytes and have the same letter case, so they differ after upper-casing too
+        emit_event(job, slice, K, j, (z_hi >> b) & 1u, false);
     }
 }
 
-// byte-wise evaluation of this lane's owned chunk ends (special blocks)
-__device__ __forceinline__ void explore_k_bytes(const ExJob &job, int k, uint32_t own, uint32_t slice,
-                                                const uint8_t *t, int64_t m, int64_t p) {
-    for (int b = 0; b < 32; b++) {
+// byte-wise evaluation of this lane's owned chunk ends (special blocks).  x0 = (rel0 mod k) + offset
+// of bit 0, so the first chunk end of the word is at bit k - 1 - (x0 mod k) and the rest follow
+// every k bits.
+__device__ __forceinline__ void explore_k_bytes(const ExJob &job, int k, uint32_t x0, uint32_t own,
+                                                uint32_t slice, const uint8_t *t, int64_t m, int64_t p) {
+    for (int b = k - 1 - (int)(x0 % (uint32_t)k); b < 32; b += k) {
         if (!((own >> b) & 1u)) continue;
         const int64_t q = p + b;
-        if (q < 0 || (q + 1) % k != 0) continue;
         const bool cur = g_bytes(t, m, k, q), prv = g_bytes(t, m, k, q - k);
         if (cur == prv) continue;
         const uint64_t j = (uint64_t)((q + 1) / k) - 2;
@@ -250,10 +242,15 @@ __global__ void __launch_bounds__(256, 2) explore_planes_kernel(const ExJob job)
             uint32_t na = 0;
             const Planes P = extract_planes(nib, na);
             const int prel = (int)(blk << 10) + lane * 32;
-            const uint32_t inslice = range_mask32(v_lo - prel, v_hi - prel);
+            // slice edges (and the item's owned range) can only fall into the first two and the
+            // last two blocks of an item
+            const bool edge = blk < 2 || blk + 2 >= nblk;
+            uint32_t inslice = 0xFFFFFFFFu, own = 0xFFFFFFFFu;
+            if (edge) {
+                inslice = range_mask32(v_lo - prel, v_hi - prel);
+                own = range_mask32(own_lo - prel, own_hi - prel);
+            }
             nonascii |= na & inslice;
-            uint32_t own = 0xFFFFFFFFu;
-            if (blk < 2 || blk + 1 == nblk) own = range_mask32(own_lo - prel, own_hi - prel);
             Planes3 cur;
             cur.lo = P.lo; cur.hi = P.hi;
             cur.va = (P.b0 ^ (P.hi & ~P.lo)) & P.ok & inslice;
@@ -283,16 +280,28 @@ __global__ void __launch_bounds__(256, 2) explore_planes_kernel(const ExJob job)
             own_prev = cur;
             const int64_t p = rel0 + prel;
             const uint32_t xoff = (uint32_t)prel; // < 2^15
-#define TIDK_EXK(K)                                                                              \
+#define TIDK_EXK(K, VA, EM)                                                                       \
     if ((KMIN > 0) ? (K >= KMIN && K <= KMAX) : (job.kmin <= K && K <= job.kmax))                \
-        explore_k<K>(job, cur, prv, carry_d[K - 1], lane, r0_of(rq0, K - 1) + xoff, own, !special, \
-                     slice, t, p);
-            TIDK_EXK(1) TIDK_EXK(2) TIDK_EXK(3) TIDK_EXK(4) TIDK_EXK(5) TIDK_EXK(6) TIDK_EXK(7) TIDK_EXK(8)
-            TIDK_EXK(9) TIDK_EXK(10) TIDK_EXK(11) TIDK_EXK(12) TIDK_EXK(13) TIDK_EXK(14) TIDK_EXK(15) TIDK_EXK(16)
+        explore_k<K, VA, EM>(job, cur, prv, carry_d[K - 1], lane, r0_of(rq0, K - 1) + xoff, own, slice, p);
+#define TIDK_EXALL(VA, EM)                                                                        \
+    TIDK_EXK(1, VA, EM) TIDK_EXK(2, VA, EM) TIDK_EXK(3, VA, EM) TIDK_EXK(4, VA, EM)               \
+    TIDK_EXK(5, VA, EM) TIDK_EXK(6, VA, EM) TIDK_EXK(7, VA, EM) TIDK_EXK(8, VA, EM)               \
+    TIDK_EXK(9, VA, EM) TIDK_EXK(10, VA, EM) TIDK_EXK(11, VA, EM) TIDK_EXK(12, VA, EM)            \
+    TIDK_EXK(13, VA, EM) TIDK_EXK(14, VA, EM) TIDK_EXK(15, VA, EM) TIDK_EXK(16, VA, EM)
+            // three straight-line variants, chosen per block (warp-uniform):
+            //   interior of a clean stretch (every base of both words valid) -> no va plane
+            //   clean block at a slice edge                                  -> va plane
+            //   special block                                                -> carries only + byte-wise
+            const bool all_valid = __all_sync(0xFFFFFFFFu, (cur.va & prv.va) == 0xFFFFFFFFu);
+            if (!special && all_valid) { TIDK_EXALL(false, true) }
+            else if (!special) { TIDK_EXALL(true, true) }
+            else { TIDK_EXALL(true, false) }
+#undef TIDK_EXALL
 #undef TIDK_EXK
             if (special) { // exact byte-wise evaluation of this block's owned chunk ends
                 const uint32_t k0 = KMIN > 0 ? KMIN : job.kmin, k1 = KMIN > 0 ? KMAX : job.kmax;
-                for (uint32_t k = k0; k <= k1; k++) explore_k_bytes(job, (int)k, own, slice, t, m, p);
+                for (uint32_t k = k0; k <= k1; k++)
+                    explore_k_bytes(job, (int)k, r0_of(rq0, (int)k - 1) + xoff, own, slice, t, m, p);
             }
         }
     }
