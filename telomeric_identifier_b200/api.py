@@ -38,7 +38,8 @@ RUN_DTYPE = np.dtype([("record", "<u4"), ("slice", "u1"), ("k", "u1"), ("first",
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "libtidk_cuda.so")
+    # TIDK_CUDA_LIB: kernel-tuning experiments load an alternative build of the same library
+    return os.environ.get("TIDK_CUDA_LIB") or os.path.join(_HERE, "libtidk_cuda.so")
 
 
 def load_library():

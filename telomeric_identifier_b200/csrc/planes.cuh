@@ -14,10 +14,10 @@
 //
 // How a plane is formed.  Two words wa (bases 0-3) and wb (bases 4-7) are merged
 // into nibble words  X = low nibbles, Y = high nibbles  (one shift + one LOP3
-// each); bit o of the eight nibbles is then gathered into one byte by a single
-// multiply:  ((X & 0x11111111<<o) * C_o) >> 24, C_o = 2^(24-o)+2^(17-o)+2^(10-o)+2^(3-o)
-// (all 32 partial products land on distinct bit positions, so there are no
-// carries).  Four such bytes are combined with three PRMT.  IMAD runs on the fma
+// each); bit o of the eight nibbles of a word is then gathered into one byte by a
+// single dot product (dp4a with weights 1,2,4,8) -- or, in the alternative build,
+// by a single multiply whose 32 partial products land on distinct bits -- and the
+// four bytes are strung together with multiply-adds.  IDP/IMAD run on the fma
 // pipe, LOP3/SHF/PRMT on the alu pipe, so the two halves of the work overlap.
 //
 // Validity needs five more ASCII bits (0,3,4,6,7).  b7=0, b6=1, b3=0 are constant
@@ -48,16 +48,37 @@ __host__ __device__ constexpr uint32_t gather_mul(int o) {
     return (1u << (24 - o)) | (1u << (17 - o)) | (1u << (10 - o)) | (1u << (3 - o));
 }
 
-// bit `O` of each of the 32 nibbles held in N[0..3] (8 nibbles per word) -> 32-bit plane
+// bit `O` of each of the 32 nibbles held in N[0..3] (8 nibbles per word) -> 32-bit plane.
+//
+// TIDK_GATHER 2 (default): dp4a gather.  Byte b of (N & M) is l*2^O + h*2^(O+4) (l / h = the wanted
+// bit of the low / high nibble); dotting the four bytes with the weights (1,2,4,8) gives the eight
+// gathered bits, shifted left by O.  Three multiply-adds string the four groups together and one
+// funnel shift removes the O.  IDP.4A and IMAD issue on the fma pipe, which this kernel leaves
+// mostly idle, so only the four masks (and two shifts for O > 0) land on the busy alu pipe.
+// TIDK_GATHER 0: multiply gather ((N & M) * C_O puts the eight bits into the top byte; the 32 partial
+// products land on distinct bit positions, so there are no carries) + a three-PRMT tree.
+#ifndef TIDK_GATHER
+#define TIDK_GATHER 2
+#endif
 template <int O>
 __device__ __forceinline__ uint32_t nibble_plane(const uint32_t (&N)[4]) {
     constexpr uint32_t M = 0x11111111u << O;
+#if TIDK_GATHER == 2
+    const uint32_t d0 = __dp4a(N[0] & M, 0x08040201u, 0u);
+    const uint32_t d1 = __dp4a(N[1] & M, 0x08040201u, 0u);
+    const uint32_t d2 = __dp4a(N[2] & M, 0x08040201u, 0u);
+    const uint32_t d3 = __dp4a(N[3] & M, 0x08040201u, 0u);
+    const uint32_t r = d3 * 0x1000000u + (d2 * 0x10000u + (d1 * 0x100u + d0)); // (plane << O) mod 2^32
+    if (O == 0) return r;
+    return __funnelshift_r(r, d3 >> 8, O); // the O bits that fell off the top are d3's bits 8..8+O
+#else
     constexpr uint32_t C = gather_mul(O);
     uint32_t p0 = (N[0] & M) * C;
     uint32_t p1 = (N[1] & M) * C;
     uint32_t p2 = (N[2] & M) * C;
     uint32_t p3 = (N[3] & M) * C;
     return __byte_perm(__byte_perm(p0, p1, 0x7373), __byte_perm(p2, p3, 0x7373), 0x5410);
+#endif
 }
 
 struct Nibbles {
@@ -70,7 +91,7 @@ __device__ __forceinline__ Nibbles to_nibbles(const uint32_t (&w)[8]) {
     for (int g = 0; g < 4; g++) {
         uint32_t wa = w[2 * g], wb = w[2 * g + 1];
         n.X[g] = bitsel(0x0F0F0F0Fu, wa, wb << 4);
-        n.Y[g] = bitsel(0x0F0F0F0Fu, __umulhi(wa, 0x10000000u), wb); // wa >> 4 on the fma pipe
+        n.Y[g] = bitsel(0x0F0F0F0Fu, wa >> 4, wb);
     }
     return n;
 }

@@ -181,6 +181,12 @@ template <int L, uint64_t F>
 void launch_static(const WindowJob &job, int grid, cudaStream_t st) {
     using M = StaticMatcher<L, F>;
     typename M::Params mp{0};
+#ifdef TIDK_TUNE
+    static const int minb = getenv("TIDK_MINB") ? atoi(getenv("TIDK_MINB")) : 4;
+    if (L == 5 && minb == 3) { window_counts_kernel<M, 3><<<grid, kWarpsPerBlock * 32, 0, st>>>(job, mp); return; }
+    if (L == 5 && minb == 5) { window_counts_kernel<M, 5><<<grid, kWarpsPerBlock * 32, 0, st>>>(job, mp); return; }
+    if (L == 5 && minb == 6) { window_counts_kernel<M, 6><<<grid, kWarpsPerBlock * 32, 0, st>>>(job, mp); return; }
+#endif
     window_counts_kernel<M, 4><<<grid, kWarpsPerBlock * 32, 0, st>>>(job, mp);
 }
 struct StaticEntry { int L; uint64_t F; LaunchFn fn; };
