@@ -176,17 +176,27 @@ constexpr uint64_t cx_enc(const char *s) {
     return f;
 }
 
+// persistent launch: the grid is the number of CTAs that are resident at once (the kernels assign
+// the first items statically and rely on every CTA running from the start)
+template <class K>
+int resident_grid(K kernel, int sm_count, uint64_t n_items) {
+    static int per_sm = 0; // one static per kernel instantiation
+    if (per_sm == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWarpsPerBlock * 32, 0) != cudaSuccess || per_sm < 1)
+            per_sm = 1;
+    }
+    const uint64_t want = (n_items + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const uint64_t cap = (uint64_t)sm_count * per_sm;
+    const uint64_t g = want < cap ? want : cap;
+    return g < 1 ? 1 : (int)g;
+}
+
 using LaunchFn = void (*)(const WindowJob &, int, cudaStream_t);
 template <int L, uint64_t F>
-void launch_static(const WindowJob &job, int grid, cudaStream_t st) {
+void launch_static(const WindowJob &job, int sm_count, cudaStream_t st) {
     using M = StaticMatcher<L, F>;
     typename M::Params mp{0};
-#ifdef TIDK_TUNE
-    static const int minb = getenv("TIDK_MINB") ? atoi(getenv("TIDK_MINB")) : 4;
-    if (L == 5 && minb == 3) { window_counts_kernel<M, 3><<<grid, kWarpsPerBlock * 32, 0, st>>>(job, mp); return; }
-    if (L == 5 && minb == 5) { window_counts_kernel<M, 5><<<grid, kWarpsPerBlock * 32, 0, st>>>(job, mp); return; }
-    if (L == 5 && minb == 6) { window_counts_kernel<M, 6><<<grid, kWarpsPerBlock * 32, 0, st>>>(job, mp); return; }
-#endif
+    const int grid = resident_grid(window_counts_kernel<M, 4>, sm_count, job.n_items);
     window_counts_kernel<M, 4><<<grid, kWarpsPerBlock * 32, 0, st>>>(job, mp);
 }
 struct StaticEntry { int L; uint64_t F; LaunchFn fn; };
@@ -204,18 +214,19 @@ LaunchFn find_static(const uint8_t *pat, uint32_t L) {
 }
 
 template <int L>
-void launch_runtime(const WindowJob &job, const RuntimeQueries &rq, int grid, cudaStream_t st) {
+void launch_runtime(const WindowJob &job, const RuntimeQueries &rq, int sm_count, cudaStream_t st) {
+    const int grid = resident_grid(window_counts_kernel<RuntimeMatcher<L>, 3>, sm_count, job.n_items);
     window_counts_kernel<RuntimeMatcher<L>, 3><<<grid, kWarpsPerBlock * 32, 0, st>>>(job, rq);
 }
 
-void launch_planes(int L, const WindowJob &job, const RuntimeQueries &rq, int grid, cudaStream_t st) {
+void launch_planes(int L, const WindowJob &job, const RuntimeQueries &rq, int sm_count, cudaStream_t st) {
     switch (L) {
-#define C_(n) case n: launch_runtime<n>(job, rq, grid, st); break;
+#define C_(n) case n: launch_runtime<n>(job, rq, sm_count, st); break;
         C_(1) C_(2) C_(3) C_(4) C_(5) C_(6) C_(7) C_(8) C_(9) C_(10) C_(11) C_(12) C_(13) C_(14)
         C_(15) C_(16) C_(17) C_(18) C_(19) C_(20) C_(21) C_(22) C_(23) C_(24) C_(25) C_(26) C_(27)
         C_(28) C_(29) C_(30) C_(31) C_(32)
 #undef C_
-    default: launch_runtime<0>(job, rq, grid, st); break;
+    default: launch_runtime<0>(job, rq, sm_count, st); break;
     }
 }
 
@@ -407,10 +418,8 @@ int tidk_cuda_window_counts_resident(tidk_ctx *ctx, const tidk_seqbuf *buf, uint
         CU(ctx, cudaMemcpyAsync(ctx->qbytes.p, qb.data(), qb.size(), cudaMemcpyHostToDevice, ctx->stream));
     }
 
-    const uint64_t want_blocks = (n_items + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const uint64_t max_blocks = (uint64_t)ctx->sm_count * 8;
-    int grid = (int)(want_blocks < max_blocks ? want_blocks : max_blocks);
-    if (grid < 1) grid = 1;
+    const int grid = ctx->sm_count; // launch helpers turn the SM count into the resident grid
 
     unsigned long long *counters = (unsigned long long *)ctx->misc.p; // 16 queue counters
     uint32_t counter_i = 0;

@@ -224,11 +224,13 @@ window_counts_kernel(const WindowJob job, const typename M::Params mp) {
     const int lane = threadIdx.x & 31;
     uint32_t nonascii = 0;
 
-    // queue tickets: current item, next item, and the raw ticket for the one after
-    unsigned long long t0 = 0, t1 = 0;
-    if (lane == 0) { t0 = atomicAdd(job.work_counter, 2ull); t1 = t0 + 1; }
-    unsigned long long item = __shfl_sync(0xFFFFFFFFu, t0, 0);
-    unsigned long long item_next = __shfl_sync(0xFFFFFFFFu, t1, 0);
+    // Work queue.  The grid is exactly the resident set (persistent CTAs), so the first two items
+    // of every warp are assigned statically -- thousands of warps hitting one atomic counter in the
+    // first microsecond serialise in L2 -- and the shared counter hands out the rest.
+    const unsigned long long n_warps = (unsigned long long)gridDim.x * kWarpsPerBlock;
+    const unsigned long long gw = (unsigned long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    unsigned long long item = gw, item_next = gw + n_warps;
+    const unsigned long long ticket0 = 2 * n_warps;
     if (item >= job.n_items) return;
 
     const uint4 *ip = reinterpret_cast<const uint4 *>(job.items);
@@ -255,7 +257,7 @@ window_counts_kernel(const WindowJob job, const typename M::Params mp) {
         uint4 na = make_uint4(0, 0, 0, 0), nb = na;
         if (have_next) { na = __ldg(ip + 2 * item_next); nb = __ldg(ip + 2 * item_next + 1); }
         unsigned long long t2 = 0;
-        if (lane == 0) t2 = atomicAdd(job.work_counter, 1ull);
+        if (lane == 0) t2 = ticket0 + atomicAdd(job.work_counter, 1ull);
 
         uint32_t cf[M::NQ], cr[M::NQ];
 #pragma unroll

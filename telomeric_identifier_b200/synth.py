@@ -131,28 +131,40 @@ _HG38 = [248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 15934
          58617616, 64444167, 46709983, 50818468, 156040895, 57227415]
 
 
+_HG38_NAMES = [str(i) for i in range(1, 23)] + ["X", "Y"]
+
+
+def config4_lengths(scale: float = 1.0):
+    return [max(256, int(L * scale)) for L in _HG38]
+
+
+def config4_contig(i: int, scale: float = 1.0, seed: int = 4):
+    """Chromosome i of C4 (keyed by (seed, i): any subset can be generated independently)."""
+    rng = _rng(seed, i)
+    n = max(256, int(_HG38[i] * scale))
+    s = _background(rng, n)
+    cap = max(1, int(10_000 * min(1.0, scale * 100)))
+    reps = lambda: max(2, int(rng.integers(500, 2501) * min(1.0, scale * 10)))
+    _put(s, cap, _array(rng, b"CCCTAA", reps(), 0.001, 0.0002))
+    _put_right(s, n - cap, _array(rng, b"TTAGGG", reps(), 0.001, 0.0002))
+    s[:cap] = ord("N")
+    s[n - cap:] = ord("N")
+    cen = int(3_000_000 * scale)
+    p = int(rng.integers(n // 4, n // 2))
+    s[p:p + cen] = ord("N")
+    gap = max(1, int(50_000 * scale))
+    for _ in range(20):
+        p = int(rng.integers(0, max(1, n - gap)))
+        s[p:p + gap] = ord("N")
+    return f"chr{_HG38_NAMES[i]}", s
+
+
 def config4(scale: float = 1.0, seed: int = 4):
     """C4: 3.1 Gb / 24 chromosomes with N gaps; `search --string TTAGGG --window 10000`."""
     ids, contigs = [], []
-    names = [str(i) for i in range(1, 23)] + ["X", "Y"]
-    for i, L in enumerate(_HG38):
-        rng = _rng(seed, i)
-        n = max(256, int(L * scale))
-        s = _background(rng, n)
-        cap = max(1, int(10_000 * min(1.0, scale * 100)))
-        reps = lambda: max(2, int(rng.integers(500, 2501) * min(1.0, scale * 10)))
-        _put(s, cap, _array(rng, b"CCCTAA", reps(), 0.001, 0.0002))
-        _put_right(s, n - cap, _array(rng, b"TTAGGG", reps(), 0.001, 0.0002))
-        s[:cap] = ord("N")
-        s[n - cap:] = ord("N")
-        cen = int(3_000_000 * scale)
-        p = int(rng.integers(n // 4, n // 2))
-        s[p:p + cen] = ord("N")
-        gap = max(1, int(50_000 * scale))
-        for _ in range(20):
-            p = int(rng.integers(0, max(1, n - gap)))
-            s[p:p + gap] = ord("N")
-        ids.append(f"chr{names[i]}")
+    for i in range(len(_HG38)):
+        rid, s = config4_contig(i, scale, seed)
+        ids.append(rid)
         contigs.append(s)
     return _finish(ids, contigs)
 
