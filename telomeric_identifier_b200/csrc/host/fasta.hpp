@@ -3,13 +3,19 @@
 // unpinned by the reference's tests): record starts at a '>' line, id = first
 // whitespace-delimited token, sequence = following lines with trailing whitespace removed.
 #pragma once
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <stdexcept>
+#include <functional>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace tidk_host {
@@ -49,35 +55,129 @@ inline std::vector<char> slurp(const std::string &path) {
     return data;
 }
 
-inline Fasta read_fasta(const std::string &path) {
-    const std::vector<char> data = slurp(path);
-    Fasta fa;
-    fa.seq.reserve(data.size());
-    const char *p = data.data(), *end = p + data.size();
-    bool started = false;
-    while (p < end) {
-        const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
-        const char *le = nl ? nl : end;
-        if (p < le && *p == '>') {
-            if (started) fa.offsets.push_back(fa.seq.size());
-            const char *q = p + 1, *e = le;
-            while (e > q && (e[-1] == ' ' || e[-1] == '\t' || e[-1] == '\r')) e--;
-            const char *w = q;
-            while (w < e && *w != ' ' && *w != '\t') w++;
-            fa.ids.emplace_back(q, w);
-            started = true;
-        } else {
-            const char *e = le;
-            while (e > p && (e[-1] == ' ' || e[-1] == '\t' || e[-1] == '\r' || e[-1] == '\f' || e[-1] == '\v')) e--;
-            if (!started) {
-                if (e > p) throw std::runtime_error("Expected > at record start.");
-            } else {
-                fa.seq.insert(fa.seq.end(), (const uint8_t *)p, (const uint8_t *)e);
-            }
+// Parse `data` into `fa` with `threads` workers.  Two passes over line-aligned chunks: pass 1
+// finds the headers and counts the (right-trimmed) sequence bytes between them, a serial prefix sum
+// turns that into record offsets and per-chunk write positions, pass 2 copies the sequence lines.
+inline void parse_fasta_buffer(const char *data, size_t size, Fasta &fa, unsigned threads) {
+    struct Header { size_t seq_before; std::string id; }; // sequence bytes of the chunk before this header
+    struct Chunk { size_t beg = 0, end = 0, seq_total = 0, out = 0; std::vector<Header> headers; bool stray = false; };
+    if (threads < 1) threads = 1;
+    if (size < (1u << 20)) threads = 1;
+    std::vector<Chunk> chunks(threads);
+    size_t pos = 0;
+    for (unsigned t = 0; t < threads; t++) {
+        chunks[t].beg = pos;
+        size_t want = size * (t + 1) / threads;
+        if (t + 1 == threads) want = size;
+        if (want < pos) want = pos;
+        if (want < size) {
+            const char *nl = (const char *)memchr(data + want, '\n', size - want);
+            want = nl ? (size_t)(nl - data) + 1 : size;
         }
-        p = nl ? nl + 1 : end;
+        chunks[t].end = pos = want;
     }
-    if (started) fa.offsets.push_back(fa.seq.size());
+    auto trimmed_end = [](const char *p, const char *e) {
+        while (e > p && (e[-1] == ' ' || e[-1] == '\t' || e[-1] == '\r' || e[-1] == '\f' || e[-1] == '\v')) e--;
+        return e;
+    };
+    auto pass1 = [&](Chunk &c) {
+        const char *p = data + c.beg, *end = data + c.end;
+        size_t acc = 0;
+        while (p < end) {
+            const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
+            const char *le = nl ? nl : end;
+            if (p < le && *p == '>') {
+                const char *q = p + 1, *e = trimmed_end(q, le);
+                const char *w = q;
+                while (w < e && *w != ' ' && *w != '\t') w++;
+                c.headers.push_back({acc, std::string(q, w)});
+            } else {
+                acc += (size_t)(trimmed_end(p, le) - p);
+            }
+            p = nl ? nl + 1 : end;
+        }
+        c.seq_total = acc;
+    };
+    {
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < threads; t++) th.emplace_back(pass1, std::ref(chunks[t]));
+        pass1(chunks[0]);
+        for (auto &x : th) x.join();
+    }
+    // serial stitch: record offsets + where each chunk writes
+    size_t total = 0;
+    bool started = false;
+    fa.ids.clear();
+    fa.offsets.assign(1, 0);
+    for (Chunk &c : chunks) {
+        c.out = total;
+        if (!started && (c.headers.empty() ? c.seq_total : c.headers[0].seq_before) > 0)
+            throw std::runtime_error("Expected > at record start.");
+        for (const Header &h : c.headers) {
+            if (started) fa.offsets.push_back(total + h.seq_before);
+            else fa.offsets[0] = 0;
+            fa.ids.push_back(h.id);
+            started = true;
+        }
+        total += c.seq_total;
+    }
+    if (started) fa.offsets.push_back(total);
+    fa.seq.resize(total);
+    auto pass2 = [&](const Chunk &c) {
+        const char *p = data + c.beg, *end = data + c.end;
+        uint8_t *out = fa.seq.data() + c.out;
+        while (p < end) {
+            const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
+            const char *le = nl ? nl : end;
+            if (!(p < le && *p == '>')) {
+                const char *e = trimmed_end(p, le);
+                memcpy(out, p, (size_t)(e - p));
+                out += e - p;
+            }
+            p = nl ? nl + 1 : end;
+        }
+    };
+    {
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < threads; t++) th.emplace_back(pass2, std::cref(chunks[t]));
+        pass2(chunks[0]);
+        for (auto &x : th) x.join();
+    }
+}
+
+inline Fasta read_fasta(const std::string &path, unsigned threads = 0) {
+    if (threads == 0) {
+        threads = std::thread::hardware_concurrency();
+        if (threads == 0) threads = 4;
+        if (threads > 32) threads = 32;
+    }
+    Fasta fa;
+    if (ends_with(path, ".gz")) {
+        const std::vector<char> data = slurp(path);
+        parse_fasta_buffer(data.data(), data.size(), fa, threads);
+        return fa;
+    }
+    int fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) throw std::runtime_error("cannot open " + path);
+    struct stat st;
+    if (fstat(fd, &st) != 0) { close(fd); throw std::runtime_error("cannot stat " + path); }
+    if (st.st_size == 0) { close(fd); return fa; }
+    void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+    if (m == MAP_FAILED) { // pipes, odd filesystems: fall back to read()
+        close(fd);
+        const std::vector<char> data = slurp(path);
+        parse_fasta_buffer(data.data(), data.size(), fa, threads);
+        return fa;
+    }
+    madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+    try {
+        parse_fasta_buffer((const char *)m, (size_t)st.st_size, fa, threads);
+    } catch (...) {
+        munmap(m, (size_t)st.st_size); close(fd);
+        throw;
+    }
+    munmap(m, (size_t)st.st_size);
+    close(fd);
     return fa;
 }
 

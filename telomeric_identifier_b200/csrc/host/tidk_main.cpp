@@ -13,6 +13,7 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../../include/tidk_cuda.h"
@@ -32,6 +33,7 @@ struct Args {
     double distance = 0.01;
     bool print = false, verbose = false, log = false, stats = false;
     int device = 0;
+    unsigned threads = 0; // FASTA parser threads (0 = hardware concurrency, at most 32)
 };
 
 [[noreturn]] void die(const std::string &msg, int code = 2) {
@@ -54,7 +56,8 @@ Args parse(int argc, char **argv) {
     a.sub = argv[1];
     if (a.sub == "-h" || a.sub == "--help") { usage(); exit(0); }
     if (a.sub == "plot" || a.sub == "build") die("`tidk " + a.sub + "` is outside the B200 hot path; use the reference binary");
-    if (a.sub != "search" && a.sub != "find" && a.sub != "explore") die("unrecognized subcommand '" + a.sub + "'");
+    if (a.sub != "search" && a.sub != "find" && a.sub != "explore" && a.sub != "fasta-check")
+        die("unrecognized subcommand '" + a.sub + "'");
     auto need = [&](int &i) -> std::string {
         if (i + 1 >= argc) die(std::string("a value is required for '") + argv[i] + "'");
         return argv[++i];
@@ -82,6 +85,7 @@ Args parse(int argc, char **argv) {
         else if (f == "--log") a.log = true;
         else if (f == "--database") a.database = v();
         else if (f == "--device") a.device = atoi(v().c_str());
+        else if (f == "--threads") a.threads = (unsigned)atoi(v().c_str());
         else if (f == "--gpu-stats") a.stats = true;
         else if (!f.empty() && f[0] == '-') die("unexpected argument '" + f + "'");
         else if (a.fasta.empty()) a.fasta = f;
@@ -101,13 +105,28 @@ void mkdirs(const std::string &dir) { // create_dir_all
     }
 }
 
+// CUDA context creation takes ~1 s on a cold process; it runs on a helper thread while the FASTA
+// is being parsed and is joined when the device is first needed.
 struct Ctx {
     tidk_ctx *h = nullptr;
+    int rc = 0;
+    std::string err;
+    std::thread starter;
     explicit Ctx(int device) {
-        int ids[1] = {device};
-        if (tidk_cuda_create(ids, 1, &h) != 0) die(std::string("tidk_cuda_create: ") + tidk_cuda_last_error(nullptr), 1);
+        starter = std::thread([this, device] {
+            int ids[1] = {device};
+            rc = tidk_cuda_create(ids, 1, &h);
+            if (rc != 0) err = tidk_cuda_last_error(nullptr);
+        });
     }
-    ~Ctx() { tidk_cuda_destroy(h); }
+    void ready() {
+        if (starter.joinable()) starter.join();
+        if (rc != 0) die("tidk_cuda_create: " + err, 1);
+    }
+    ~Ctx() {
+        if (starter.joinable()) starter.join();
+        tidk_cuda_destroy(h);
+    }
     void check(int rc) const {
         if (rc != 0) die(std::string("tidk-cuda error ") + std::to_string(rc) + ": " + tidk_cuda_last_error(h), 1);
     }
@@ -153,13 +172,14 @@ int run_counts(const Args &a, const std::vector<std::string> &queries, const std
                const std::string &path, bool header, bool bedgraph) {
     if (a.window == 0) die("window must be greater than 0", 1);
     const auto t0 = std::chrono::steady_clock::now();
-    Fasta fa = read_fasta(a.fasta);
+    Ctx ctx(a.device); // starts creating the CUDA context in the background
+    Fasta fa = read_fasta(a.fasta, a.threads);
     const auto t1 = std::chrono::steady_clock::now();
     mkdirs(a.dir);
     FILE *out = fopen(path.c_str(), "wb");
     if (!out) die("cannot create " + path, 1);
     if (header) fputs(kHeader, out);
-    Ctx ctx(a.device);
+    ctx.ready();
     uint64_t nwin = 0;
     for (size_t r = 0; r < fa.ids.size(); r++) {
         uint64_t n = fa.offsets[r + 1] - fa.offsets[r];
@@ -246,13 +266,14 @@ int cmd_explore(const Args &a) { // explore::explore, explore.rs:20-149
         for (long long k = a.minimum; k <= a.maximum; k++) fprintf(stderr, "[+]\t\tFinding telomeric repeat length: %lld\n", k);
         kmin = (uint32_t)a.minimum; kmax = (uint32_t)a.maximum;
     }
-    Fasta fa = read_fasta(a.fasta);
+    Ctx ctx(a.device); // starts creating the CUDA context in the background
+    Fasta fa = read_fasta(a.fasta, a.threads);
     std::vector<std::pair<std::string, long long>> rows;
     float ms = 0;
     uint32_t nl = 0;
     uint64_t n = 0;
     if (kmax >= kmin && kmin > 0) {
-        Ctx ctx(a.device);
+        ctx.ready();
         tidk_seqbuf *buf = nullptr;
         ctx.check(tidk_cuda_seqbuf_upload(ctx.h, fa.seq.data(), fa.offsets.data(), (uint32_t)fa.ids.size(), &buf));
         tidk_run *runs = nullptr;
@@ -286,9 +307,21 @@ int cmd_explore(const Args &a) { // explore::explore, explore.rs:20-149
 
 } // namespace
 
+// host-only self check of the FASTA reader (no device): record table + FNV-1a of the sequence
+int cmd_fasta_check(const Args &a) {
+    Fasta fa = read_fasta(a.fasta, a.threads);
+    uint64_t h = 1469598103934665603ull;
+    for (uint8_t c : fa.seq) { h ^= c; h *= 1099511628211ull; }
+    printf("%zu\t%zu\t%016llx\n", fa.ids.size(), fa.seq.size(), (unsigned long long)h);
+    for (size_t i = 0; i < fa.ids.size(); i++)
+        printf("%s\t%llu\n", fa.ids[i].c_str(), (unsigned long long)(fa.offsets[i + 1] - fa.offsets[i]));
+    return 0;
+}
+
 int main(int argc, char **argv) {
     try {
         Args a = parse(argc, argv);
+        if (a.sub == "fasta-check") return cmd_fasta_check(a);
         if (a.sub == "search") return cmd_search(a);
         if (a.sub == "find") return cmd_find(a);
         return cmd_explore(a);

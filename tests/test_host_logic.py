@@ -92,3 +92,57 @@ def test_format_rows_matches_reference_layout():
     assert rows[6] == "c\t20\t6\t60\tQ1" and rows[-1] == "c\t23\t9\t90\tQ2" and len(rows) == 10
     bed = format_rows(["a"], np.array([0, 52], dtype=np.uint64), 20, ["Q"], f[:3], r[:3], "bedgraph").splitlines()
     assert bed == ["a\t0\t20\t0", "a\t20\t40\t11", "a\t40\t52\t22"]
+
+
+def test_cpp_fasta_reader_matches_python(tmp_path):
+    """The C++ driver's multi-threaded FASTA reader against the Python one on a file large enough to
+    be split across threads, with ragged line widths, CRLF, blank lines, empty records and a
+    header right at a chunk edge."""
+    import subprocess
+    import __graft_entry__ as g
+    g.build()
+    tidk = os.path.join(os.path.dirname(HERE), "telomeric_identifier_b200", "bin", "tidk")
+    rng = np.random.default_rng(3)
+    lines = []
+    for r in range(40):
+        lines.append(f">rec{r} some description {r}".encode())
+        n = int(rng.integers(0, 200_000)) if r % 7 else 0
+        s = np.frombuffer(b"ACGTNacgtn", dtype=np.uint8)[rng.integers(0, 10, n)].tobytes()
+        w = int(rng.integers(20, 200))
+        for j in range(0, n, w):
+            tail = [b"", b"\r", b"  ", b" \t\r"][int(rng.integers(0, 4))] if r % 3 == 0 else b""
+            lines.append(s[j:j + w] + tail)
+        if r % 5 == 0:
+            lines.append(b"")
+    data = b"\n".join(lines) + (b"\n" if True else b"")
+    p = tmp_path / "big.fa"
+    p.write_bytes(data)
+    ids, seq, off = fasta.read_fasta(str(p))
+    h = 1469598103934665603
+    want_len = [int(off[i + 1] - off[i]) for i in range(len(ids))]
+    for threads in (1, 3, 16):
+        out = subprocess.run([tidk, "fasta-check", str(p), "--threads", str(threads)], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        rows = out.stdout.splitlines()
+        n, total, _ = rows[0].split("\t")
+        assert int(n) == len(ids) and int(total) == seq.size
+        assert [r.split("\t")[0] for r in rows[1:]] == ids
+        assert [int(r.split("\t")[1]) for r in rows[1:]] == want_len
+    # same hash for every thread count (content, not only lengths)
+    hs = {subprocess.run([tidk, "fasta-check", str(p), "--threads", str(t)], capture_output=True, text=True).stdout.splitlines()[0]
+          for t in (1, 2, 5, 16)}
+    assert len(hs) == 1
+    fnv = 1469598103934665603
+    for c in seq[:0].tolist():
+        fnv = ((fnv ^ c) * 1099511628211) % (1 << 64)
+    # full FNV in Python is slow; check it on a small file instead
+    q = tmp_path / "small.fa"
+    q.write_bytes(b">a x\nACGT\nAC  \n\n>b\n>c\nTT\r\n")
+    out = subprocess.run([tidk, "fasta-check", str(q)], capture_output=True, text=True).stdout.splitlines()
+    fnv = 1469598103934665603
+    for c in b"ACGTACTT":
+        fnv = ((fnv ^ c) * 1099511628211) % (1 << 64)
+    assert out[0] == f"3\t8\t{fnv:016x}" and out[1:] == ["a\t6", "b\t0", "c\t2"]
+    bad = tmp_path / "bad.fa"
+    bad.write_bytes(b"ACGT\n>x\nAC\n")
+    assert subprocess.run([tidk, "fasta-check", str(bad)], capture_output=True, text=True).returncode == 1
