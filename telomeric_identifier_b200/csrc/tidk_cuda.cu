@@ -213,6 +213,44 @@ LaunchFn find_static(const uint8_t *pat, uint32_t L) {
     return nullptr;
 }
 
+// ---- whole clades in one pass ----------------------------------------------------
+// The multi-repeat clades of the curated table (table order = output order).  `find --clade X`
+// with exactly this query list runs ONE fused kernel instead of one pass per repeat.
+#define MOTIF_(s) Motif<cx_len(s), cx_enc(s)>
+using Coleoptera = StaticMultiMatcher<MOTIF_("AACCC"), MOTIF_("AACCT"), MOTIF_("AACAGACCCG"), MOTIF_("ACCTG")>;
+using Hemiptera = StaticMultiMatcher<MOTIF_("AAACCACCCT"), MOTIF_("AACCATCCCT")>;
+using Hymenoptera = StaticMultiMatcher<MOTIF_("AACCCAGACCT"), MOTIF_("AACCCCAACCT"), MOTIF_("AACCCGAACCT"), MOTIF_("AACCT"),
+                                       MOTIF_("ACCCAG"), MOTIF_("AACCCT"), MOTIF_("ACGGCAGCG"), MOTIF_("AAATGTGGAGG"),
+                                       MOTIF_("AAAGAACCT"), MOTIF_("AAAATTGTCCGTCC"), MOTIF_("AAACCC"), MOTIF_("AACCC"),
+                                       MOTIF_("AACCCAGACCC"), MOTIF_("AACCCAGACGC"), MOTIF_("AACCCTGACGC")>;
+#undef MOTIF_
+
+template <class M, int MINB>
+void launch_multi(const WindowJob &job, int sm_count, cudaStream_t st) {
+    typename M::Params mp{0};
+    const int grid = resident_grid(window_counts_kernel<M, MINB>, sm_count, job.n_items);
+    window_counts_kernel<M, MINB><<<grid, kWarpsPerBlock * 32, 0, st>>>(job, mp);
+}
+
+struct CladeSet { std::vector<const char *> motifs; LaunchFn fn; };
+const CladeSet kCladeSets[] = {
+    {{"AACCC", "AACCT", "AACAGACCCG", "ACCTG"}, &launch_multi<Coleoptera, 3>},
+    {{"AAACCACCCT", "AACCATCCCT"}, &launch_multi<Hemiptera, 4>},
+    {{"AACCCAGACCT", "AACCCCAACCT", "AACCCGAACCT", "AACCT", "ACCCAG", "AACCCT", "ACGGCAGCG", "AAATGTGGAGG", "AAAGAACCT",
+      "AAAATTGTCCGTCC", "AAACCC", "AACCC", "AACCCAGACCC", "AACCCAGACGC", "AACCCTGACGC"}, &launch_multi<Hymenoptera, 2>},
+};
+
+LaunchFn find_clade_set(const char *const *queries, const uint32_t *qlens, uint32_t nq) {
+    for (const CladeSet &c : kCladeSets) {
+        if (c.motifs.size() != nq) continue;
+        bool same = true;
+        for (uint32_t q = 0; q < nq && same; q++)
+            same = strlen(c.motifs[q]) == qlens[q] && memcmp(c.motifs[q], queries[q], qlens[q]) == 0;
+        if (same) return c.fn;
+    }
+    return nullptr;
+}
+
 template <int L>
 void launch_runtime(const WindowJob &job, const RuntimeQueries &rq, int sm_count, cudaStream_t st) {
     const int grid = resident_grid(window_counts_kernel<RuntimeMatcher<L>, 3>, sm_count, job.n_items);
@@ -435,6 +473,14 @@ int tidk_cuda_window_counts_resident(tidk_ctx *ctx, const tidk_seqbuf *buf, uint
     // complement) run alone; the rest of the fast ones are fused, up to 16 per launch
     std::vector<uint32_t> fused;
     uint8_t rcbuf[kMaxFastLen];
+    if (LaunchFn clade = (slow.empty() ? find_clade_set(queries, qlens, nq) : nullptr)) {
+        WindowJob j2 = job; // the whole query list is a known clade: one fused pass
+        j2.q0 = 0; j2.nq = nq;
+        j2.work_counter = next_counter();
+        clade(j2, grid, ctx->stream);
+        launches++;
+        fast.clear();
+    }
     for (uint32_t q : fast) {
         const uint8_t *f = (const uint8_t *)queries[q];
         revcomp_host(f, qlens[q], rcbuf);

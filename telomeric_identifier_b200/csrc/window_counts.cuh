@@ -145,6 +145,53 @@ struct StaticMatcher {
     }
 };
 
+// Several compile-time motifs in ONE pass over the sequence (a multi-repeat clade of `tidk find`,
+// e.g. Hymenoptera's 15 repeats): the planes are extracted once, the shifted equality planes are
+// shared between all motifs and both strands (common sub-expressions), and every motif costs only
+// its ANDs and two popcounts.  The reference makes one full pass per repeat (finder.rs:121-176).
+template <int L_, uint64_t F_>
+struct Motif {
+    static constexpr int L = L_;
+    static constexpr uint64_t F = F_;
+};
+
+template <class... Ms>
+struct StaticMultiMatcher {
+    static constexpr int NQ = (int)sizeof...(Ms);
+    struct Params { uint32_t unused; };
+    struct Carry { uint32_t e[4]; };
+    __device__ __forceinline__ static void reset(Carry &c) { c.e[0] = c.e[1] = c.e[2] = c.e[3] = 0; }
+
+    template <class M>
+    __device__ __forceinline__ static void one(const uint32_t (&e)[4], const uint32_t (&p)[4], uint32_t cmask,
+                                               uint32_t &cf, uint32_t &cr) {
+        uint32_t mf = 0xFFFFFFFFu, mr = 0xFFFFFFFFu;
+        StaticMatcher<M::L, M::F>::template steps<0>(e, p, mf, mr);
+        cf += __popc(mf & cmask);
+        cr += __popc(mr & cmask);
+    }
+
+    __device__ __forceinline__ static void step(const Params &, const Planes &P, bool special,
+                                                uint32_t cmask, int lane, Carry &carry,
+                                                uint32_t *cf, uint32_t *cr) {
+        uint32_t e[4], p[4];
+        e[0] = ~P.lo & ~P.hi & P.b0; // A
+        e[1] = P.lo & ~P.hi & P.b0;  // C
+        e[2] = P.lo & P.hi & P.b0;   // G
+        e[3] = ~P.lo & P.hi & ~P.b0; // T
+        if (special) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) e[i] &= P.ok;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) p[i] = lane_lookbehind(e[i], carry.e[i], lane);
+#pragma unroll
+        for (int i = 0; i < 4; i++) carry.e[i] = e[i];
+        int q = 0;
+        ((one<Ms>(e, p, cmask, cf[q], cr[q]), q++), ...);
+    }
+};
+
 // One strand pattern for the runtime matchers: bit s of plo / phi is the expected
 // lo / hi plane bit s bases behind the match end (s = 0 is the LAST base).
 struct StrandPattern {

@@ -216,3 +216,28 @@ def test_sharded_ranks_emulated_on_one_gpu(ctx, world):
     f, r = sharding.merge_counts(plans, per_rank, off, 10000, 1)
     of, orr = O.window_counts(seq, off, 10000, qs, False)
     assert (f == of).all() and (r == orr).all()
+
+
+@pytest.mark.parametrize("clade", ["Coleoptera", "Hemiptera", "Hymenoptera"])
+def test_fused_clade_kernels(ctx, clade):
+    """Multi-repeat clades run as one fused pass; any other order / subset takes the per-query path.
+    Both must equal the oracle."""
+    import os
+    from telomeric_identifier_b200 import clades, synth
+    db = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "clades_min.csv")
+    reps = [r.encode() for r in clades.return_telomere_sequence(clade, db)]
+    ids, seq, off = synth.random_records(21, 4, 120000, b"ACGTNacgt", plant=reps[0] + reps[-1])
+    for r in reps:  # plant every repeat somewhere, both strands
+        p = 1000 + 37 * len(r)
+        seq[p:p + 4 * len(r)] = np.frombuffer(r * 4, dtype=np.uint8)
+        rc = O.revcomp(r)
+        seq[p + 500:p + 500 + 3 * len(r)] = np.frombuffer(rc * 3, dtype=np.uint8)
+    b = ctx.upload(seq, off)
+    for W in (10000, 777, 40000):
+        f, r = ctx.window_counts_resident(b, W, reps)
+        assert ctx.last_kernel_launches <= 2  # (item table +) ONE counting kernel
+        of, orr = O.window_counts(seq, off, W, reps, False)
+        assert (f == of).all() and (r == orr).all()
+    _cmp(ctx, seq, off, 10000, reps[::-1])
+    _cmp(ctx, seq, off, 10000, reps[:-1] if len(reps) > 2 else reps + [b"TTAGG"])
+    b.free()
