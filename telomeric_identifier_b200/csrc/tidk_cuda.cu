@@ -47,6 +47,9 @@ struct tidk_ctx {
     std::string err;
     tidk_seqbuf scratch; // staging for the host-pointer entry points
     DevBuf win_base, out_fwd, out_rev, misc, qbytes, runs, items;
+    uint32_t counter_flip = 0;      // which of the two queue counters the next launch uses
+    bool counters_dirty = false;    // a call failed between taking a counter and finishing: re-zero both
+    uint32_t *h_flags = nullptr;    // pinned: error flags come back with an async copy
     ExploreScratch ex;
     uint64_t next_buf_id = 1;
     // work items cached for (sequence batch, window, query count): several clades or output
@@ -312,6 +315,7 @@ void tidk_cuda_destroy(tidk_ctx *ctx) {
     for (DevBuf *b : {&ctx->win_base, &ctx->out_fwd, &ctx->out_rev, &ctx->misc, &ctx->qbytes, &ctx->runs, &ctx->items})
         if (b->p) cudaFree(b->p);
     explore_scratch_release(ctx->ex);
+    if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
@@ -405,8 +409,17 @@ int tidk_cuda_window_counts_resident(tidk_ctx *ctx, const tidk_seqbuf *buf, uint
     int rc;
     if ((rc = ensure(ctx, ctx->out_fwd, n_out * 8))) return rc;
     if ((rc = ensure(ctx, ctx->out_rev, n_out * 8))) return rc;
-    if ((rc = ensure(ctx, ctx->misc, 256))) return rc;
-    CU(ctx, cudaMemsetAsync(ctx->misc.p, 0, 256, ctx->stream));
+    if (!ctx->misc.p) { // two queue counters (each launch zeroes the other one) + error flags
+        if ((rc = ensure(ctx, ctx->misc, 256))) return rc;
+        CU(ctx, cudaMemsetAsync(ctx->misc.p, 0, 256, ctx->stream));
+        ctx->counter_flip = 0;
+    }
+    if (!ctx->h_flags) CU(ctx, cudaHostAlloc((void **)&ctx->h_flags, 64, cudaHostAllocDefault));
+    if (ctx->counters_dirty) {
+        CU(ctx, cudaMemsetAsync(ctx->misc.p, 0, 256, ctx->stream));
+        ctx->counter_flip = 0;
+    }
+    ctx->counters_dirty = true; // cleared when this call has completed all its launches
     uint64_t *d_fwd = (uint64_t *)ctx->out_fwd.p, *d_rev = (uint64_t *)ctx->out_rev.p;
     if (spw > 1) {
         CU(ctx, cudaMemsetAsync(d_fwd, 0, n_out * 8, ctx->stream));
@@ -459,14 +472,13 @@ int tidk_cuda_window_counts_resident(tidk_ctx *ctx, const tidk_seqbuf *buf, uint
     const uint64_t max_blocks = (uint64_t)ctx->sm_count * 8;
     const int grid = ctx->sm_count; // launch helpers turn the SM count into the resident grid
 
-    unsigned long long *counters = (unsigned long long *)ctx->misc.p; // 16 queue counters
-    uint32_t counter_i = 0;
+    unsigned long long *counters = (unsigned long long *)ctx->misc.p; // two queue counters, used alternately
+    unsigned long long *next_zeroed = nullptr;
     auto next_counter = [&]() -> unsigned long long * {
-        if (counter_i == 16) { // recycle (stream-ordered)
-            cudaMemsetAsync(ctx->misc.p, 0, 128, ctx->stream);
-            counter_i = 0;
-        }
-        return counters + counter_i++;
+        unsigned long long *c = counters + (ctx->counter_flip & 1u) * 8; // 64 bytes apart
+        ctx->counter_flip ^= 1u;
+        next_zeroed = counters + (ctx->counter_flip & 1u) * 8;
+        return c;
     };
 
     // queries that have a compile-time specialised kernel (directly or through their reverse
@@ -476,7 +488,7 @@ int tidk_cuda_window_counts_resident(tidk_ctx *ctx, const tidk_seqbuf *buf, uint
     if (LaunchFn clade = (slow.empty() ? find_clade_set(queries, qlens, nq) : nullptr)) {
         WindowJob j2 = job; // the whole query list is a known clade: one fused pass
         j2.q0 = 0; j2.nq = nq;
-        j2.work_counter = next_counter();
+        j2.work_counter = next_counter(); j2.next_counter = next_zeroed;
         clade(j2, grid, ctx->stream);
         launches++;
         fast.clear();
@@ -491,7 +503,7 @@ int tidk_cuda_window_counts_resident(tidk_ctx *ctx, const tidk_seqbuf *buf, uint
         WindowJob j2 = job;
         j2.q0 = q; j2.nq = 1;
         if (swap) { j2.out_fwd = d_rev; j2.out_rev = d_fwd; }
-        j2.work_counter = next_counter();
+        j2.work_counter = next_counter(); j2.next_counter = next_zeroed;
         fn(j2, grid, ctx->stream);
         launches++;
     }
@@ -510,7 +522,7 @@ int tidk_cuda_window_counts_resident(tidk_ctx *ctx, const tidk_seqbuf *buf, uint
         rq.nq = (uint32_t)(g1 - g0);
         WindowJob j2 = job;
         j2.q0 = fused[g0]; j2.nq = rq.nq;
-        j2.work_counter = next_counter();
+        j2.work_counter = next_counter(); j2.next_counter = next_zeroed;
         launch_planes(rq.nq == 1 ? (int)rq.len[0] : 0, j2, rq, grid, ctx->stream);
         launches++;
         g0 = g1;
@@ -521,7 +533,7 @@ int tidk_cuda_window_counts_resident(tidk_ctx *ctx, const tidk_seqbuf *buf, uint
         SlowJob sj{};
         sj.seq = buf->d_seq; sj.rec_off = buf->d_off; sj.win_base = (const uint64_t *)ctx->win_base.p;
         sj.out_fwd = d_fwd; sj.out_rev = d_rev;
-        sj.work_counter = next_counter();
+        sj.work_counter = next_counter(); sj.next_counter = next_zeroed;
         sj.err_flags = job.err_flags;
         sj.window = window; sj.n_windows = n_windows; sj.n_records = nrec; sj.q = q; sj.nq_total = nq;
         sj.fwd = (const uint8_t *)ctx->qbytes.p + qoff[i];
@@ -535,11 +547,13 @@ int tidk_cuda_window_counts_resident(tidk_ctx *ctx, const tidk_seqbuf *buf, uint
     CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     CU(ctx, cudaGetLastError());
 
-    uint32_t h_err = 0;
     CU(ctx, cudaMemcpyAsync(out_fwd, d_fwd, n_out * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaMemcpyAsync(out_rev, d_rev, n_out * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaMemcpyAsync(&h_err, job.err_flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(ctx->h_flags, job.err_flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->counters_dirty = false;
+    const uint32_t h_err = ctx->h_flags[0];
+    if (h_err) CU(ctx, cudaMemsetAsync(job.err_flags, 0, 4, ctx->stream)); // flags are sticky: clear after reporting
     if (kernel_ms) CU(ctx, cudaEventElapsedTime(kernel_ms, ctx->ev0, ctx->ev1));
     if (kernel_launches) *kernel_launches = launches;
     if (h_err & 1u)

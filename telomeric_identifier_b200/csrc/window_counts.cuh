@@ -89,7 +89,8 @@ struct WindowJob {
     const ItemDesc *items;
     uint64_t *out_fwd;       // [record][query][window]
     uint64_t *out_rev;
-    unsigned long long *work_counter; // zeroed before launch
+    unsigned long long *work_counter; // zero at launch
+    unsigned long long *next_counter; // zeroed by this launch for the next one (no memset per call)
     uint32_t *err_flags;     // bit 0: non-ASCII byte seen
     uint64_t n_items;
     uint32_t q0;             // first query index of this launch
@@ -278,6 +279,7 @@ window_counts_kernel(const WindowJob job, const typename M::Params mp) {
     const unsigned long long gw = (unsigned long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     unsigned long long item = gw, item_next = gw + n_warps;
     const unsigned long long ticket0 = 2 * n_warps;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *job.next_counter = 0ull; // stream order: the next launch starts after this one ends
     if (item >= job.n_items) return;
 
     const uint4 *ip = reinterpret_cast<const uint4 *>(job.items);
@@ -375,7 +377,7 @@ struct SlowJob {
     const uint64_t *rec_off;
     const uint64_t *win_base;
     uint64_t *out_fwd, *out_rev;
-    unsigned long long *work_counter;
+    unsigned long long *work_counter, *next_counter;
     uint32_t *err_flags;
     uint64_t window, n_windows;
     uint32_t n_records, q, nq_total;
@@ -386,6 +388,7 @@ struct SlowJob {
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) window_counts_bytes_kernel(const SlowJob job) {
     const int lane = threadIdx.x & 31;
     uint32_t nonascii = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *job.next_counter = 0ull;
     for (;;) {
         unsigned long long win = 0;
         if (lane == 0) win = atomicAdd(job.work_counter, 1ull);
