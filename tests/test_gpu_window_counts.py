@@ -241,3 +241,44 @@ def test_fused_clade_kernels(ctx, clade):
     _cmp(ctx, seq, off, 10000, reps[::-1])
     _cmp(ctx, seq, off, 10000, reps[:-1] if len(reps) > 2 else reps + [b"TTAGG"])
     b.free()
+
+
+@pytest.mark.parametrize("cfg,query", [("config1", b"TTAGG"), ("config4", b"TTAGGG")])
+def test_full_size_c1_c4_properties(ctx, cfg, query):
+    """BASELINE configs 1 (100 Mb) and 4 (3.1 Gb, N gaps) at FULL size.  The oracle needs ~10 s per Gb,
+    so it checks sampled stretches (both ends of a chromosome, an N-gap edge, a soft-masked block);
+    the whole output is checked through size-independent properties."""
+    from telomeric_identifier_b200 import synth
+    ids, seq, off = getattr(synth, cfg)(scale=1.0)
+    W = 10000
+    b = ctx.upload(seq, off)
+    f, r = ctx.window_counts_resident(b, W, [query])
+    f2, r2 = ctx.window_counts_resident(b, W, [O.revcomp(query)])
+    assert (f == r2).all() and (r == f2).all()                      # strand swap
+    fh, rh = ctx.window_counts_resident(b, W // 2, [query])
+    assert int(f.sum()) >= int(fh.sum()) and int(f.sum()) - int(fh.sum()) < fh.size  # halving loses only straddlers
+    nw = ((off[1:] - off[:-1] + np.uint64(W - 1)) // np.uint64(W)).astype(np.int64)
+    base = np.concatenate([[0], np.cumsum(nw)])
+    lens = (off[1:] - off[:-1]).astype(np.int64)
+    assert f.size == int(nw.sum())
+    rng = np.random.default_rng(0)
+    spots = []
+    for rec in (0, len(ids) // 2, len(ids) - 1):
+        spots += [(rec, 0), (rec, max(0, int(nw[rec]) - 30))]       # both chromosome ends (last partial window too)
+        spots += [(rec, int(rng.integers(0, max(1, int(nw[rec]) - 30))))]
+    # a stretch that crosses into an N gap / a soft-masked block, found from the data itself
+    o0 = int(off[1])
+    sub = seq[o0:o0 + int(lens[1])]
+    odd = np.flatnonzero((sub == ord("N")) | (sub >= 97))
+    if odd.size:
+        spots.append((1, max(0, int(odd[0]) // W - 5)))
+    for rec, w0 in spots:
+        w1 = min(w0 + 30, int(nw[rec]))
+        a = int(off[rec]) + w0 * W
+        e = min(int(off[rec]) + w1 * W, int(off[rec + 1]))
+        piece = seq[a:e]
+        of, orr = O.window_counts(piece, np.array([0, piece.size], dtype=np.uint64), W, [query], False)
+        s = int(base[rec]) + w0
+        assert (f[s:s + of.size] == of).all() and (r[s:s + orr.size] == orr).all(), (rec, w0)
+    assert int(f.sum()) + int(r.sum()) > 1000                       # the planted arrays are seen
+    b.free()
