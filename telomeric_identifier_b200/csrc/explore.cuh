@@ -49,6 +49,21 @@ struct RunEvent {
     uint64_t chunk;
 };
 
+// Packed form of an event: one sortable 64-bit key (k | slice | chunk | type | joins), used whenever
+// the batch fits the bit budget (< 2^26 slices, < 2^28 chunks per slice); sorting the keys puts the
+// events into the reference's arrival order (k, record, slice, position).
+constexpr int kKeySliceBits = 26, kKeyChunkBits = 28;
+__host__ __device__ inline uint64_t pack_event(uint32_t slice, uint32_t k, uint64_t chunk, uint32_t type, uint32_t joins) {
+    return ((uint64_t)k << 56) | ((uint64_t)slice << 30) | (chunk << 2) | ((uint64_t)type << 1) | joins;
+}
+__host__ __device__ inline void unpack_event(uint64_t key, uint32_t &slice, uint32_t &k, uint64_t &chunk, uint32_t &type, uint32_t &joins) {
+    k = (uint32_t)(key >> 56);
+    slice = (uint32_t)((key >> 30) & ((1u << kKeySliceBits) - 1));
+    chunk = (key >> 2) & ((1ull << kKeyChunkBits) - 1);
+    type = (uint32_t)((key >> 1) & 1u);
+    joins = (uint32_t)(key & 1u);
+}
+
 struct ExploreJob {
     const uint8_t *seq;
     const SliceDesc *slices;
@@ -61,15 +76,18 @@ struct ExploreJob {
     uint64_t cap_events;
     unsigned long long *work_counter;
     uint32_t *err_flags;
+    uint32_t packed; // events are 64-bit keys (pack_event) instead of RunEvent structs
 };
 
 struct ExploreScratch {
     void *slices = nullptr, *tile_base = nullptr, *events = nullptr, *misc = nullptr, *items = nullptr;
+    void *keys2 = nullptr, *temp = nullptr, *runs = nullptr, *flags = nullptr, *runs_out = nullptr;
     size_t slices_cap = 0, tile_cap = 0, events_cap = 0, items_cap = 0;
+    size_t keys2_cap = 0, temp_cap = 0, runs_cap = 0, flags_cap = 0, runs_out_cap = 0;
 };
 
 inline void explore_scratch_release(ExploreScratch &s) {
-    for (void *p : {s.slices, s.tile_base, s.events, s.misc, s.items})
+    for (void *p : {s.slices, s.tile_base, s.events, s.misc, s.items, s.keys2, s.temp, s.runs, s.flags, s.runs_out})
         if (p) cudaFree(p);
     s = ExploreScratch();
 }
@@ -139,7 +157,10 @@ __global__ void __launch_bounds__(256) explore_events_kernel(const ExploreJob jo
                     ev.type = 1; ev.joins = 0;
                 }
                 unsigned long long idx = atomicAdd(job.n_events, 1ull);
-                if (idx < job.cap_events) job.events[idx] = ev;
+                if (idx < job.cap_events) {
+                    if (job.packed) ((uint64_t *)job.events)[idx] = pack_event(ev.slice, ev.k, ev.chunk, ev.type, ev.joins);
+                    else job.events[idx] = ev;
+                }
             }
         }
     }

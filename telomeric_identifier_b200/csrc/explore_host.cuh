@@ -3,6 +3,7 @@
 #pragma once
 #include "explore.cuh"
 #include "explore_planes.cuh"
+#include "explore_post.cuh"
 
 namespace tidk {
 
@@ -43,6 +44,11 @@ inline int explore_runs_device(ExploreScratch &sc, cudaStream_t st, cudaEvent_t 
         scanned += 2 * dist;
     }
     const uint64_t n_tiles = tile_base[n_slices];
+    // events as sortable 64-bit keys + device-side run building when the batch fits the key layout
+    uint64_t max_chunks = 0;
+    for (uint32_t sidx = 0; sidx < n_slices; sidx++) max_chunks = std::max(max_chunks, slices[sidx].len / kmin + 2);
+    // TIDK_EXPLORE_HOST_POST=1 forces the struct events + host stitching path (tests exercise both)
+    const bool packed = !getenv("TIDK_EXPLORE_HOST_POST") && n_slices < (1u << kKeySliceBits) && max_chunks < (1ull << kKeyChunkBits);
     std::vector<tidk_run> runs;
     if (n_tiles > 0) {
         cudaError_t e;
@@ -67,7 +73,7 @@ inline int explore_runs_device(ExploreScratch &sc, cudaStream_t st, cudaEvent_t 
         uint32_t launches = 0;
         bool items_ready = false;
         for (int attempt = 0; attempt < 3; attempt++) {
-            if ((e = grow(sc.events, sc.events_cap, cap * sizeof(RunEvent))) != cudaSuccess) return cuerr(e, "cudaMalloc(events)");
+            if ((e = grow(sc.events, sc.events_cap, cap * (packed ? sizeof(uint64_t) : sizeof(RunEvent)))) != cudaSuccess) return cuerr(e, "cudaMalloc(events)");
             if ((e = cudaMemsetAsync(sc.misc, 0, 256, st)) != cudaSuccess) return cuerr(e, "memset");
             const uint64_t want = (n_tiles + 7) / 8, maxb = (uint64_t)sm_count * 8;
             const int grid = (int)std::max<uint64_t>(1, std::min(want, maxb));
@@ -90,6 +96,7 @@ inline int explore_runs_device(ExploreScratch &sc, cudaStream_t st, cudaEvent_t 
                 job.work_counter = (unsigned long long *)sc.misc;
                 job.n_events = (unsigned long long *)sc.misc + 1;
                 job.err_flags = (uint32_t *)((char *)sc.misc + 128);
+                job.packed = packed ? 1u : 0u;
                 if (kmin == 5 && kmax == 12) explore_planes_kernel<5, 12><<<grid, 256, 0, st>>>(job);
                 else explore_planes_kernel<0, 0><<<grid, 256, 0, st>>>(job);
             } else {
@@ -105,6 +112,7 @@ inline int explore_runs_device(ExploreScratch &sc, cudaStream_t st, cudaEvent_t 
                 job.work_counter = (unsigned long long *)sc.misc;
                 job.n_events = (unsigned long long *)sc.misc + 1;
                 job.err_flags = (uint32_t *)((char *)sc.misc + 128);
+                job.packed = packed ? 1u : 0u;
                 explore_events_kernel<<<grid, 256, 0, st>>>(job);
             }
             cudaEventRecord(ev1, st);
@@ -121,6 +129,17 @@ inline int explore_runs_device(ExploreScratch &sc, cudaStream_t st, cudaEvent_t 
             if (h_err & 1u) { err = "sequence contains a byte >= 0x80 (str::from_utf8 panics, explore.rs:212)"; return TIDK_ENONASCII; }
             const uint64_t ne = h_counts[1];
             if (ne > cap) { cap = ne; continue; } // event buffer too small: rerun with the exact size
+            if (packed) { // sort, build runs, filter and compact on the device
+                cudaEventRecord(ev0, st);
+                const int prc = explore_post_device(sc, st, ne, threshold, out_runs, n_runs, &launches, err);
+                cudaEventRecord(ev1, st);
+                cudaStreamSynchronize(st);
+                float pms = 0.f;
+                cudaEventElapsedTime(&pms, ev0, ev1);
+                if (kernel_ms) *kernel_ms = ms_total + pms;
+                if (kernel_launches) *kernel_launches = launches;
+                return prc;
+            }
             events.resize(ne);
             if (ne && (e = cudaMemcpy(events.data(), sc.events, ne * sizeof(RunEvent), cudaMemcpyDeviceToHost)) != cudaSuccess) return cuerr(e, "D2H events");
             break;

@@ -103,6 +103,7 @@ struct ExJob {
     uint64_t cap_events;
     unsigned long long *work_counter;
     uint32_t *err_flags;
+    uint32_t packed; // events are 64-bit keys (pack_event) instead of RunEvent structs
 };
 
 __device__ __forceinline__ void emit_event(const ExJob &job, uint32_t slice, uint32_t k, uint64_t chunk,
@@ -111,7 +112,10 @@ __device__ __forceinline__ void emit_event(const ExJob &job, uint32_t slice, uin
     ev.slice = slice; ev.k = (uint8_t)k; ev.type = start ? 0 : 1; ev.joins = joins ? 1 : 0; ev.pad = 0;
     ev.chunk = chunk;
     unsigned long long idx = atomicAdd(job.n_events, 1ull);
-    if (idx < job.cap_events) job.events[idx] = ev;
+    if (idx < job.cap_events) {
+        if (job.packed) ((uint64_t *)job.events)[idx] = pack_event(slice, k, chunk, ev.type, ev.joins);
+        else job.events[idx] = ev;
+    }
 }
 
 // byte-wise G_k[q] (exact for any bytes)

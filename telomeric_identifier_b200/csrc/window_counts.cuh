@@ -306,7 +306,7 @@ window_counts_kernel(const WindowJob job, const typename M::Params mp) {
         uint4 na = make_uint4(0, 0, 0, 0), nb = na;
         if (have_next) { na = __ldg(ip + 2 * item_next); nb = __ldg(ip + 2 * item_next + 1); }
         unsigned long long t2 = 0;
-        if (lane == 0) t2 = ticket0 + atomicAdd(job.work_counter, 1ull);
+                if (lane == 0) t2 = ticket0 + atomicAdd(job.work_counter, 1ull);
 
         uint32_t cf[M::NQ], cr[M::NQ];
 #pragma unroll

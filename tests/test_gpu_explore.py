@@ -150,3 +150,26 @@ def test_many_tiny_records(ctx):
     seq = np.concatenate(parts).astype(np.uint8)
     _runs_equal(ctx, seq, off, 0.5, 1, 8, 0)
     _runs_equal(ctx, seq, off, 0.2, 3, 5, 1)
+
+
+def test_host_and_device_run_building_agree(ctx):
+    """Runs are normally built on the device (sorted 64-bit event keys); batches that do not fit the key
+    layout fall back to struct events + host stitching.  Force the fallback and compare."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np, telomeric_identifier_b200 as T\n"
+        "from telomeric_identifier_b200 import synth\n"
+        "from oracle import oracle as O\n"
+        "ids, seq, off = synth.random_records(55, 5, 80000, b'ACGTacgtN', plant=b'TTAGGG')\n"
+        "with T.Context(0) as ctx:\n"
+        "    got = ctx.explore_runs(seq, off, 0.5, 2, 9, 1)\n"
+        "want, _ = O.explore_runs(seq, off, 0.5, 2, 9, 1, period_filter=False)\n"
+        "assert got.size == want.size and all((got[f] == want[f]).all() for f in ('record','slice','k','first','start','end'))\n"
+        "print('ok', got.size)\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for env_extra in ({}, {"TIDK_EXPLORE_HOST_POST": "1"}):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root,
+                           env={**os.environ, **env_extra})
+        assert r.returncode == 0 and r.stdout.startswith("ok"), r.stderr[-2000:]
