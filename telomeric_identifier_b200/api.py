@@ -18,6 +18,7 @@ EXPORTS = [
     "tidk_cuda_host_alloc", "tidk_cuda_host_free", "tidk_cuda_window_counts",
     "tidk_cuda_seqbuf_upload", "tidk_cuda_seqbuf_free", "tidk_cuda_window_counts_resident",
     "tidk_cuda_explore_runs", "tidk_cuda_explore_runs_resident", "tidk_cuda_free_runs",
+    "tidk_cuda_last_explore_timings",
 ]
 
 
@@ -83,6 +84,8 @@ def load_library():
     L.tidk_cuda_explore_runs_resident.restype = C.c_int
     L.tidk_cuda_free_runs.argtypes = [C.POINTER(Run)]
     L.tidk_cuda_free_runs.restype = None
+    L.tidk_cuda_last_explore_timings.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
+    L.tidk_cuda_last_explore_timings.restype = C.c_int
     _LIB = L
     return L
 
@@ -215,6 +218,12 @@ class Context:
                                                    len(offsets) - 1, distance, kmin, kmax, threshold,
                                                    C.byref(runs), C.byref(n)))
         return self._runs_out(runs, n)
+
+    def explore_timings(self):
+        """(scan_ms, post_ms) of the last explore call."""
+        out = (C.c_float * 2)()
+        self._L.tidk_cuda_last_explore_timings(self._h, out, 2)
+        return float(out[0]), float(out[1])
 
     def explore_runs_resident(self, batch: SeqBatch, distance: float, kmin: int, kmax: int,
                               threshold: int) -> np.ndarray:

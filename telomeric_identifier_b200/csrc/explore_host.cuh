@@ -12,7 +12,9 @@ inline int explore_runs_device(ExploreScratch &sc, cudaStream_t st, cudaEvent_t 
                                const uint64_t *h_off, uint32_t n_records, double distance,
                                uint32_t kmin, uint32_t kmax, uint64_t threshold, tidk_run **out_runs,
                                uint64_t *n_runs, float *kernel_ms, uint32_t *kernel_launches,
-                               std::string &err) {
+                               std::string &err, float *scan_ms = nullptr, float *post_ms = nullptr) {
+    if (scan_ms) *scan_ms = 0.f;
+    if (post_ms) *post_ms = 0.f;
     (void)d_off;
     auto cuerr = [&](cudaError_t e, const char *what) {
         err = std::string(what) + " failed: " + cudaGetErrorString(e);
@@ -137,6 +139,8 @@ inline int explore_runs_device(ExploreScratch &sc, cudaStream_t st, cudaEvent_t 
                 float pms = 0.f;
                 cudaEventElapsedTime(&pms, ev0, ev1);
                 if (kernel_ms) *kernel_ms = ms_total + pms;
+                if (scan_ms) *scan_ms = ms_total;
+                if (post_ms) *post_ms = pms;
                 if (kernel_launches) *kernel_launches = launches;
                 return prc;
             }
@@ -145,6 +149,7 @@ inline int explore_runs_device(ExploreScratch &sc, cudaStream_t st, cudaEvent_t 
             break;
         }
         if (kernel_ms) *kernel_ms = ms_total;
+        if (scan_ms) *scan_ms = ms_total;
         if (kernel_launches) *kernel_launches = launches;
         events_to_runs(events, threshold, runs);
     }

@@ -106,15 +106,22 @@ struct ExJob {
     uint32_t packed; // events are 64-bit keys (pack_event) instead of RunEvent structs
 };
 
+// Events are appended with one atomicAdd each on a global counter (the compiler aggregates the lanes
+// of a warp that emit together).  A per-warp shared-memory staging queue with one atomic per work
+// item was tried and measured slower on read-like inputs (1.07 vs 0.99 ms): the events are too sparse
+// (about one per KiB) for the same-address atomics to matter, and the staging code costs registers.
 __device__ __forceinline__ void emit_event(const ExJob &job, uint32_t slice, uint32_t k, uint64_t chunk,
                                            bool start, bool joins) {
-    RunEvent ev;
-    ev.slice = slice; ev.k = (uint8_t)k; ev.type = start ? 0 : 1; ev.joins = joins ? 1 : 0; ev.pad = 0;
-    ev.chunk = chunk;
+    const uint32_t type = start ? 0u : 1u, jn = joins ? 1u : 0u;
     unsigned long long idx = atomicAdd(job.n_events, 1ull);
     if (idx < job.cap_events) {
-        if (job.packed) ((uint64_t *)job.events)[idx] = pack_event(slice, k, chunk, ev.type, ev.joins);
-        else job.events[idx] = ev;
+        if (job.packed) ((uint64_t *)job.events)[idx] = pack_event(slice, k, chunk, type, jn);
+        else {
+            RunEvent ev;
+            ev.slice = slice; ev.k = (uint8_t)k; ev.type = (uint8_t)type; ev.joins = (uint8_t)jn; ev.pad = 0;
+            ev.chunk = chunk;
+            job.events[idx] = ev;
+        }
     }
 }
 
@@ -148,37 +155,40 @@ struct Planes3 {
 // One k for one 32-base word.  WITH_VA: honour the validity plane (edge blocks); interior blocks of
 // a clean stretch have va == all ones for both words and skip it.
 //
-// "All K positions of an aligned chunk match K behind" is a zero-field test on F = ~D over the
+// "All K positions of an aligned chunk match K behind" is an all-ones-field test on D over the
 // (previous | current) 64-bit pair, fields = chunks, H = top bit of each field (the chunk ends):
-//     Z = ~(((F & ~H) + ~H)) & ~F & H          -- exact, no carries across fields
-// which costs 2 LOP3 + one 64-bit add + 2 LOP3 regardless of K.
+//     Z = ((D | H) + H + 1) & D & H
+// (equivalently ~((~D & ~H) + ~H) & D & H): inside a field the +1 ripples through the low K-1 bits
+// of D exactly when they are all ones and stops at the field top because H is added there, so no
+// carry crosses a field.  Two LOP3, one 64-bit add, two LOP3 -- regardless of K.
+//
+// s_lo is the bit position (0..K-1) of the first chunk end in the PREVIOUS word: the phase of that
+// word's first base is (rel0 + offset - 32) mod K, recomputed per block with a multiply-shift on
+// the fma pipe (keeping it in a register per k costs a CTA of occupancy).
 template <int K, bool WITH_VA, bool EMIT>
 __device__ __forceinline__ void explore_k(const ExJob &job, const Planes3 &cur, const Planes3 &prv,
-                                          uint32_t &carry_d, int lane, uint32_t x0 /* (rel0 mod K) + offset of bit 0 */,
+                                          uint32_t &carry_d, uint32_t m31, int src_lane, uint32_t s_lo,
                                           uint32_t own, uint32_t slice,
                                           int64_t p /* slice-relative position of bit 0 */) {
     const uint32_t lo_k = __funnelshift_l(prv.lo, cur.lo, K);
     const uint32_t hi_k = __funnelshift_l(prv.hi, cur.hi, K);
     uint32_t d_hi = ~((cur.lo ^ lo_k) | (cur.hi ^ hi_k));
     if (WITH_VA) d_hi &= cur.va & __funnelshift_l(prv.va, cur.va, K);
-    const uint32_t d_lo = lane_lookbehind(d_hi, carry_d, lane);
+    // previous lane's D (lane 0: lane 31's D of the previous block)
+    const uint32_t d_lo = __shfl_sync(0xFFFFFFFFu, bitsel(m31, carry_d, d_hi), src_lane);
     carry_d = d_hi;
     if (!EMIT) return; // special block: only the carries are kept consistent
-    // chunk ends of the word pair: positions b (0..63, bit 0 = first base of the previous word)
-    // with (r_lo + b) mod K == K - 1, r_lo = phase of that base = (x0 - 32) mod K
-    const uint32_t r_lo = (x0 + 32u * (K - 1)) % K; // 32 * (K - 1) == -32 (mod K); compile-time K
-    const uint32_t s_lo = K - 1 - r_lo;
     constexpr uint64_t PER = periodic_mask64<K>();
     const uint32_t h_lo = (uint32_t)PER << s_lo;
     const uint32_t h_hi = __funnelshift_l((uint32_t)PER, (uint32_t)(PER >> 32), s_lo);
-    const uint64_t a = ((uint64_t)(~(d_hi | h_hi)) << 32) | (uint32_t)(~(d_lo | h_lo));
-    const uint64_t nh = ((uint64_t)(~h_hi) << 32) | (uint32_t)(~h_lo);
-    const uint64_t sum = a + nh;
-    const uint32_t z_lo = ~(uint32_t)sum & d_lo & h_lo;
-    const uint32_t z_hi = ~(uint32_t)(sum >> 32) & d_hi & h_hi;
+    const uint64_t u = ((uint64_t)(d_hi | h_hi) << 32) | (d_lo | h_lo);
+    const uint64_t h = ((uint64_t)h_hi << 32) | h_lo;
+    const uint64_t t = u + h + 1ull;
+    const uint32_t z_lo = (uint32_t)t & d_lo & h_lo;
+    const uint32_t z_hi = (uint32_t)(t >> 32) & d_hi & h_hi;
     const uint32_t z_prev = __funnelshift_l(z_lo, z_hi, K); // the chunk before
-    uint32_t ev = (z_hi ^ z_prev) & own;                    // both are subsets of h_hi
-    while (ev) { // rare
+    uint32_t ev = (z_hi ^ z_prev) & own; // both are subsets of h_hi
+    while (ev) {                         // rare
         const int b = __ffs(ev) - 1;
         ev &= ev - 1;
         const int64_t q = p + b;
@@ -212,8 +222,10 @@ __device__ __forceinline__ uint32_t r0_of(const uint4 &v, int i) { // byte i of 
 
 // KMIN > 0: the k range is a compile-time constant (default 5..12); KMIN == 0: run-time range.
 template <int KMIN, int KMAX>
-__global__ void __launch_bounds__(256, 2) explore_planes_kernel(const ExJob job) {
+__global__ void __launch_bounds__(256, 3) explore_planes_kernel(const ExJob job) {
     const int lane = threadIdx.x & 31;
+    const uint32_t m31 = lane == 31 ? 0xFFFFFFFFu : 0u; // look-behind: lane 31 sends its previous-block value
+    const int src_lane = (lane + 31) & 31;
     uint32_t nonascii = 0;
     for (;;) {
         unsigned long long item = 0;
@@ -285,8 +297,10 @@ __global__ void __launch_bounds__(256, 2) explore_planes_kernel(const ExJob job)
             const int64_t p = rel0 + prel;
             const uint32_t xoff = (uint32_t)prel; // < 2^15
 #define TIDK_EXK(K, VA, EM)                                                                       \
-    if ((KMIN > 0) ? (K >= KMIN && K <= KMAX) : (job.kmin <= K && K <= job.kmax))                \
-        explore_k<K, VA, EM>(job, cur, prv, carry_d[K - 1], lane, r0_of(rq0, K - 1) + xoff, own, slice, p);
+    if ((KMIN > 0) ? (K >= KMIN && K <= KMAX) : (job.kmin <= K && K <= job.kmax)) {              \
+        explore_k<K, VA, EM>(job, cur, prv, carry_d[K - 1], m31, src_lane,                      \
+                             (uint32_t)(K - 1) - (r0_of(rq0, K - 1) + xoff + 32u * (K - 1)) % K, own, slice, p); \
+    }
 #define TIDK_EXALL(VA, EM)                                                                        \
     TIDK_EXK(1, VA, EM) TIDK_EXK(2, VA, EM) TIDK_EXK(3, VA, EM) TIDK_EXK(4, VA, EM)               \
     TIDK_EXK(5, VA, EM) TIDK_EXK(6, VA, EM) TIDK_EXK(7, VA, EM) TIDK_EXK(8, VA, EM)               \

@@ -47,6 +47,7 @@ struct tidk_ctx {
     std::string err;
     tidk_seqbuf scratch; // staging for the host-pointer entry points
     DevBuf win_base, out_fwd, out_rev, misc, qbytes, runs, items;
+    float explore_scan_ms = 0.f, explore_post_ms = 0.f;
     uint32_t counter_flip = 0;      // which of the two queue counters the next launch uses
     bool counters_dirty = false;    // a call failed between taking a counter and finishing: re-zero both
     uint32_t *h_flags = nullptr;    // pinned: error flags come back with an async copy
@@ -590,7 +591,8 @@ int tidk_cuda_explore_runs_resident(tidk_ctx *ctx, const tidk_seqbuf *buf, doubl
     std::string err;
     int rc = explore_runs_device(ctx->ex, ctx->stream, ctx->ev0, ctx->ev1, ctx->sm_count, buf->d_seq,
                                  buf->d_off, buf->h_off.data(), buf->n_records, distance, kmin, kmax,
-                                 threshold, out_runs, n_runs, kernel_ms, kernel_launches, err);
+                                 threshold, out_runs, n_runs, kernel_ms, kernel_launches, err,
+                                 &ctx->explore_scan_ms, &ctx->explore_post_ms);
     if (rc) return fail(ctx, rc, "%s", err.c_str());
     return TIDK_OK;
 }
@@ -607,5 +609,12 @@ int tidk_cuda_explore_runs(tidk_ctx *ctx, const uint8_t *seq, const uint64_t *of
 }
 
 void tidk_cuda_free_runs(tidk_run *runs) { free(runs); }
+
+int tidk_cuda_last_explore_timings(const tidk_ctx *ctx, float *out, int n) {
+    if (!ctx || !out || n <= 0) return 0;
+    out[0] = ctx->explore_scan_ms;
+    if (n > 1) out[1] = ctx->explore_post_ms;
+    return n > 1 ? 2 : 1;
+}
 
 } // extern "C"

@@ -17,8 +17,9 @@ with T.Context(0) as ctx:
             runs = ctx.explore_runs_resident(b, 0.5, 5, 12, 100)
             dt = time.perf_counter() - t0
             scanned = sum(2 * int(np.ceil(float(l) * 0.5)) for l in (off[1:] - off[:-1]).tolist())
-            print(f"C5 reads={n_reads} scanned={scanned} kernel_ms={ctx.last_kernel_ms:.3f} "
-                  f"GB/s={scanned / (ctx.last_kernel_ms * 1e-3) / 1e9:.1f} wall_ms={dt * 1e3:.1f} runs={runs.size}")
+            sm, pm = ctx.explore_timings()
+            print(f"C5 reads={n_reads} scanned={scanned} scan_ms={sm:.3f} post_ms={pm:.3f} "
+                  f"scan GB/s={scanned / (sm * 1e-3) / 1e9:.1f} wall_ms={dt * 1e3:.1f} runs={runs.size}")
         b.free()
     if "c3" in which:
         ids, seq, off = synth.config2(scale=float(os.environ.get("TIDK_BENCH_SCALE", "1.0")))
@@ -28,5 +29,6 @@ with T.Context(0) as ctx:
             runs = ctx.explore_runs_resident(b, 0.01, 5, 12, 100)
             dt = time.perf_counter() - t0
             scanned = sum(2 * int(np.ceil(float(l) * 0.01)) for l in (off[1:] - off[:-1]).tolist())
-            print(f"C3 scanned={scanned} kernel_ms={ctx.last_kernel_ms:.3f} GB/s={scanned / (ctx.last_kernel_ms * 1e-3) / 1e9:.1f} "
+            sm, pm = ctx.explore_timings()
+            print(f"C3 scanned={scanned} scan_ms={sm:.3f} post_ms={pm:.3f} scan GB/s={scanned / (sm * 1e-3) / 1e9:.1f} "
                   f"wall_ms={dt * 1e3:.1f} runs={runs.size}")
