@@ -232,6 +232,7 @@ def main():
         ctx.window_counts(pseq, off, WINDOW, REPEATS)
     barrier()
     dt_e2e = time.perf_counter() - t1
+    h2d_bytes, d2h_bytes, host_packed = ctx.last_transfer()
 
     # the bound for e2e: a bare pinned host -> device copy of the same buffer (PCIe Gen5 x16)
     src = torch.from_numpy(pseq)
@@ -278,8 +279,11 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
                 "kernel_ms_per_step": k_ms, "clocks": clocks,
                 "e2e": {"value": total_bases * e2e_steps / dt_e2e / 1e9, "unit": UNIT,
-                        "h2d_bytes_per_step": bases + int(off.nbytes) + 8 * (len(off)),
-                        "d2h_bytes_per_step": nwin * 16 + 4, "steps": e2e_steps,
+                        "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
+                        "host_bytes_per_step": bases,
+                        "upload": ("host-packed bit-planes (3 bits per base), packed by %d host threads inside the timed region"
+                                   % min(32, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
+                                   if host_packed else "ASCII, straight DMA from the caller's pinned buffer"),
                         "ms_per_step": dt_e2e / e2e_steps * 1e3,
                         "h2d_bound_gbs_rank0": h2d_gbs,
                         "frac_of_h2d_bound_rank0": (bases * e2e_steps / dt_e2e / 1e9) / h2d_gbs},

@@ -81,6 +81,12 @@ int tidk_cuda_window_counts(tidk_ctx *ctx, const uint8_t *seq, const uint64_t *o
                             const uint32_t *qlens, uint32_t nq, uint64_t *out_fwd,
                             uint64_t *out_rev);
 
+/* Bytes that crossed PCIe in the last tidk_cuda_window_counts call on ctx, and whether the sequence
+ * went up as host-packed bit-planes (3 bits per base; taken when every query has a compile-time
+ * plane kernel, the batch is >= 32 MiB and >= 12 host threads are available -- TIDK_HOST_PACK=0/1 and
+ * TIDK_PACK_THREADS override) or as ASCII. */
+int tidk_cuda_last_transfer(const tidk_ctx *ctx, uint64_t *h2d_bytes, uint64_t *d2h_bytes, int *host_packed);
+
 /* Same computation on a sequence batch that is already resident in HBM
  * (uploaded once, queried many times: several clades, tsv + bedgraph, ...).
  * kernel_ms (nullable) receives the device time of the counting kernels of this

@@ -18,7 +18,7 @@ EXPORTS = [
     "tidk_cuda_host_alloc", "tidk_cuda_host_free", "tidk_cuda_window_counts",
     "tidk_cuda_seqbuf_upload", "tidk_cuda_seqbuf_free", "tidk_cuda_window_counts_resident",
     "tidk_cuda_explore_runs", "tidk_cuda_explore_runs_resident", "tidk_cuda_free_runs",
-    "tidk_cuda_last_explore_timings",
+    "tidk_cuda_last_explore_timings", "tidk_cuda_last_transfer",
 ]
 
 
@@ -84,6 +84,8 @@ def load_library():
     L.tidk_cuda_explore_runs_resident.restype = C.c_int
     L.tidk_cuda_free_runs.argtypes = [C.POINTER(Run)]
     L.tidk_cuda_free_runs.restype = None
+    L.tidk_cuda_last_transfer.argtypes = [vp, u64p, u64p, C.POINTER(C.c_int)]
+    L.tidk_cuda_last_transfer.restype = C.c_int
     L.tidk_cuda_last_explore_timings.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
     L.tidk_cuda_last_explore_timings.restype = C.c_int
     _LIB = L
@@ -183,6 +185,12 @@ class Context:
                                                     len(offsets) - 1, window, qa, ql, nq,
                                                     fwd.ctypes.data, rev.ctypes.data))
         return fwd[:total], rev[:total]
+
+    def last_transfer(self):
+        """(h2d_bytes, d2h_bytes, host_packed) of the last window_counts call."""
+        a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_int(0)
+        self._L.tidk_cuda_last_transfer(self._h, C.byref(a), C.byref(b), C.byref(c))
+        return a.value, b.value, bool(c.value)
 
     def window_counts_resident(self, batch: SeqBatch, window: int, queries: Sequence[bytes],
                                out: Optional[Tuple[np.ndarray, np.ndarray]] = None):

@@ -1,0 +1,68 @@
+// host_pack.hpp -- host-side packing of ASCII bases into the three bit-planes the matchers use
+// (lo = ASCII bit 1, hi = ASCII bit 2, va = byte is one of ACGTacgt), 32 bases per word, LSB first.
+//
+// Used by the host-pointer entry point tidk_cuda_window_counts: PCIe (about 55 GB/s) is the
+// end-to-end bound, so 3 bits per base cross the bus instead of 8.  The exact same planes are what
+// planes.cuh builds in registers from ASCII on the device path.
+#pragma once
+#include <immintrin.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+
+namespace tidk {
+
+inline void pack_words_scalar(const uint8_t *src, size_t n_bytes, size_t n_words, uint32_t *lo, uint32_t *hi,
+                              uint32_t *va, uint32_t *nonascii) {
+    uint32_t na = 0;
+    for (size_t w = 0; w < n_words; w++) {
+        uint32_t l = 0, h = 0, v = 0;
+        const size_t base = w * 32;
+        const size_t m = base >= n_bytes ? 0 : (n_bytes - base < 32 ? n_bytes - base : 32);
+        for (size_t b = 0; b < m; b++) {
+            const uint8_t c = src[base + b];
+            const uint8_t u = c | 0x20;
+            l |= (uint32_t)((c >> 1) & 1u) << b;
+            h |= (uint32_t)((c >> 2) & 1u) << b;
+            v |= (uint32_t)(u == 'a' || u == 'c' || u == 'g' || u == 't') << b;
+            na |= c & 0x80u;
+        }
+        lo[w] = l; hi[w] = h; va[w] = v;
+    }
+    if (na) *nonascii = 1;
+}
+
+__attribute__((target("avx2"))) inline void pack_words_avx2(const uint8_t *src, size_t n_bytes, size_t n_words,
+                                                            uint32_t *lo, uint32_t *hi, uint32_t *va,
+                                                            uint32_t *nonascii) {
+    const size_t full = n_bytes / 32 < n_words ? n_bytes / 32 : n_words;
+    const __m256i c20 = _mm256_set1_epi8(0x20), ca = _mm256_set1_epi8('a'), cc = _mm256_set1_epi8('c'),
+                  cg = _mm256_set1_epi8('g'), ct = _mm256_set1_epi8('t');
+    uint32_t na = 0;
+    for (size_t w = 0; w < full; w++) {
+        const __m256i v = _mm256_loadu_si256((const __m256i *)(src + w * 32));
+        // movemask takes bit 7 of every byte: shift the wanted bit there (16-bit lanes: bit 1 / 2 of a
+        // byte lands on bit 7 of the same byte)
+        lo[w] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 6));
+        hi[w] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 5));
+        const __m256i u = _mm256_or_si256(v, c20);
+        const __m256i ok = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(u, ca), _mm256_cmpeq_epi8(u, cc)),
+                                           _mm256_or_si256(_mm256_cmpeq_epi8(u, cg), _mm256_cmpeq_epi8(u, ct)));
+        va[w] = (uint32_t)_mm256_movemask_epi8(ok);
+        na |= (uint32_t)_mm256_movemask_epi8(v);
+    }
+    if (na) *nonascii = 1;
+    if (full < n_words)
+        pack_words_scalar(src + full * 32, n_bytes - full * 32, n_words - full, lo + full, hi + full, va + full, nonascii);
+}
+
+// n_words words starting at src; only the first n_bytes bytes exist (the rest packs as invalid)
+inline void pack_words(const uint8_t *src, size_t n_bytes, size_t n_words, uint32_t *lo, uint32_t *hi, uint32_t *va,
+                       uint32_t *nonascii) {
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2) pack_words_avx2(src, n_bytes, n_words, lo, hi, va, nonascii);
+    else pack_words_scalar(src, n_bytes, n_words, lo, hi, va, nonascii);
+}
+
+} // namespace tidk

@@ -10,10 +10,13 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "explore_host.cuh"
+#include "host_pack.hpp"
 #include "window_counts.cuh"
 
 using namespace tidk;
@@ -48,6 +51,12 @@ struct tidk_ctx {
     tidk_seqbuf scratch; // staging for the host-pointer entry points
     DevBuf win_base, out_fwd, out_rev, misc, qbytes, runs, items;
     float explore_scan_ms = 0.f, explore_post_ms = 0.f;
+    uint64_t last_h2d = 0, last_d2h = 0; // bytes moved by the last host-pointer window-count call
+    int last_packed = 0;
+    // host-packed upload path (tidk_cuda_window_counts): device planes + per-thread staging
+    DevBuf packed;
+    struct PackLane { cudaStream_t st = nullptr; cudaEvent_t ev[2] = {nullptr, nullptr}; uint32_t *pin = nullptr; };
+    std::vector<PackLane> pack_lanes;
     uint32_t counter_flip = 0;      // which of the two queue counters the next launch uses
     bool counters_dirty = false;    // a call failed between taking a counter and finishing: re-zero both
     uint32_t *h_flags = nullptr;    // pinned: error flags come back with an async copy
@@ -96,14 +105,14 @@ int ensure(tidk_ctx *ctx, DevBuf &b, size_t bytes) {
 constexpr size_t kSeqPad = 8192; // zeroed bytes behind the data: block loads never leave the buffer
 
 int seqbuf_fill(tidk_ctx *ctx, tidk_seqbuf *b, const uint8_t *seq, const uint64_t *offsets,
-                uint32_t n_records) {
+                uint32_t n_records, bool copy_seq = true) {
     if (n_records && (!offsets)) return fail(ctx, TIDK_EARG, "offsets is NULL");
     const uint64_t total = n_records ? offsets[n_records] : 0;
     if (n_records && offsets[0] != 0) return fail(ctx, TIDK_EARG, "offsets[0] must be 0");
     for (uint32_t r = 0; r < n_records; r++)
         if (offsets[r + 1] < offsets[r]) return fail(ctx, TIDK_EARG, "offsets must be non-decreasing");
     if (total && !seq) return fail(ctx, TIDK_EARG, "seq is NULL");
-    const size_t need = (size_t)total + kSeqPad;
+    const size_t need = copy_seq ? (size_t)total + kSeqPad : 0;
     if (need > b->seq_cap) {
         if (b->d_seq) cudaFree(b->d_seq);
         b->d_seq = nullptr; b->seq_cap = 0;
@@ -124,8 +133,10 @@ int seqbuf_fill(tidk_ctx *ctx, tidk_seqbuf *b, const uint8_t *seq, const uint64_
     b->n_records = n_records;
     b->total = total;
     b->id = ctx->next_buf_id++;
-    if (total) CU(ctx, cudaMemcpyAsync(b->d_seq, seq, total, cudaMemcpyHostToDevice, ctx->stream));
-    CU(ctx, cudaMemsetAsync(b->d_seq + total, 0, kSeqPad, ctx->stream));
+    if (copy_seq) {
+        if (total) CU(ctx, cudaMemcpyAsync(b->d_seq, seq, total, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaMemsetAsync(b->d_seq + total, 0, kSeqPad, ctx->stream));
+    }
     CU(ctx, cudaMemcpyAsync(b->d_off, b->h_off.data(), off_need, cudaMemcpyHostToDevice, ctx->stream));
     return TIDK_OK;
 }
@@ -196,24 +207,24 @@ int resident_grid(K kernel, int sm_count, uint64_t n_items) {
 }
 
 using LaunchFn = void (*)(const WindowJob &, int, cudaStream_t);
-template <int L, uint64_t F>
+template <int L, uint64_t F, class Src>
 void launch_static(const WindowJob &job, int sm_count, cudaStream_t st) {
     using M = StaticMatcher<L, F>;
     typename M::Params mp{0};
-    const int grid = resident_grid(window_counts_kernel<M, 4>, sm_count, job.n_items);
-    window_counts_kernel<M, 4><<<grid, kWarpsPerBlock * 32, 0, st>>>(job, mp);
+    const int grid = resident_grid(window_counts_kernel<M, 4, Src>, sm_count, job.n_items);
+    window_counts_kernel<M, 4, Src><<<grid, kWarpsPerBlock * 32, 0, st>>>(job, mp);
 }
-struct StaticEntry { int L; uint64_t F; LaunchFn fn; };
-#define X_(s) {cx_len(s), cx_enc(s), &launch_static<cx_len(s), cx_enc(s)>},
+struct StaticEntry { int L; uint64_t F; LaunchFn fn, fn_packed; };
+#define X_(s) {cx_len(s), cx_enc(s), &launch_static<cx_len(s), cx_enc(s), AsciiSource>, &launch_static<cx_len(s), cx_enc(s), PackedSource>},
 const StaticEntry kStatic[] = {TIDK_STATIC_MOTIFS(X_)};
 #undef X_
 
-LaunchFn find_static(const uint8_t *pat, uint32_t L) {
+LaunchFn find_static(const uint8_t *pat, uint32_t L, bool packed = false) {
     if (L > 32) return nullptr;
     uint64_t f = 0;
     for (uint32_t j = 0; j < L; j++) f |= cx_code((char)pat[j]) << (2 * j);
     for (const StaticEntry &e : kStatic)
-        if (e.L == (int)L && e.F == f) return e.fn;
+        if (e.L == (int)L && e.F == f) return packed ? e.fn_packed : e.fn;
     return nullptr;
 }
 
@@ -229,28 +240,29 @@ using Hymenoptera = StaticMultiMatcher<MOTIF_("AACCCAGACCT"), MOTIF_("AACCCCAACC
                                        MOTIF_("AACCCAGACCC"), MOTIF_("AACCCAGACGC"), MOTIF_("AACCCTGACGC")>;
 #undef MOTIF_
 
-template <class M, int MINB>
+template <class M, int MINB, class Src>
 void launch_multi(const WindowJob &job, int sm_count, cudaStream_t st) {
     typename M::Params mp{0};
-    const int grid = resident_grid(window_counts_kernel<M, MINB>, sm_count, job.n_items);
-    window_counts_kernel<M, MINB><<<grid, kWarpsPerBlock * 32, 0, st>>>(job, mp);
+    const int grid = resident_grid(window_counts_kernel<M, MINB, Src>, sm_count, job.n_items);
+    window_counts_kernel<M, MINB, Src><<<grid, kWarpsPerBlock * 32, 0, st>>>(job, mp);
 }
 
-struct CladeSet { std::vector<const char *> motifs; LaunchFn fn; };
+struct CladeSet { std::vector<const char *> motifs; LaunchFn fn, fn_packed; };
 const CladeSet kCladeSets[] = {
-    {{"AACCC", "AACCT", "AACAGACCCG", "ACCTG"}, &launch_multi<Coleoptera, 3>},
-    {{"AAACCACCCT", "AACCATCCCT"}, &launch_multi<Hemiptera, 4>},
+    {{"AACCC", "AACCT", "AACAGACCCG", "ACCTG"}, &launch_multi<Coleoptera, 3, AsciiSource>, &launch_multi<Coleoptera, 3, PackedSource>},
+    {{"AAACCACCCT", "AACCATCCCT"}, &launch_multi<Hemiptera, 4, AsciiSource>, &launch_multi<Hemiptera, 4, PackedSource>},
     {{"AACCCAGACCT", "AACCCCAACCT", "AACCCGAACCT", "AACCT", "ACCCAG", "AACCCT", "ACGGCAGCG", "AAATGTGGAGG", "AAAGAACCT",
-      "AAAATTGTCCGTCC", "AAACCC", "AACCC", "AACCCAGACCC", "AACCCAGACGC", "AACCCTGACGC"}, &launch_multi<Hymenoptera, 2>},
+      "AAAATTGTCCGTCC", "AAACCC", "AACCC", "AACCCAGACCC", "AACCCAGACGC", "AACCCTGACGC"},
+     &launch_multi<Hymenoptera, 2, AsciiSource>, &launch_multi<Hymenoptera, 2, PackedSource>},
 };
 
-LaunchFn find_clade_set(const char *const *queries, const uint32_t *qlens, uint32_t nq) {
+LaunchFn find_clade_set(const char *const *queries, const uint32_t *qlens, uint32_t nq, bool packed = false) {
     for (const CladeSet &c : kCladeSets) {
         if (c.motifs.size() != nq) continue;
         bool same = true;
         for (uint32_t q = 0; q < nq && same; q++)
             same = strlen(c.motifs[q]) == qlens[q] && memcmp(c.motifs[q], queries[q], qlens[q]) == 0;
-        if (same) return c.fn;
+        if (same) return packed ? c.fn_packed : c.fn;
     }
     return nullptr;
 }
@@ -317,6 +329,13 @@ void tidk_cuda_destroy(tidk_ctx *ctx) {
         if (b->p) cudaFree(b->p);
     explore_scratch_release(ctx->ex);
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
+    if (ctx->packed.p) cudaFree(ctx->packed.p);
+    for (tidk_ctx::PackLane &L : ctx->pack_lanes) {
+        if (L.pin) cudaFreeHost(L.pin);
+        if (L.ev[0]) cudaEventDestroy(L.ev[0]);
+        if (L.ev[1]) cudaEventDestroy(L.ev[1]);
+        if (L.st) cudaStreamDestroy(L.st);
+    }
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
@@ -367,10 +386,10 @@ void tidk_cuda_seqbuf_free(tidk_ctx *ctx, tidk_seqbuf *buf) {
     delete buf;
 }
 
-int tidk_cuda_window_counts_resident(tidk_ctx *ctx, const tidk_seqbuf *buf, uint64_t window,
-                                     const char *const *queries, const uint32_t *qlens,
-                                     uint32_t nq, uint64_t *out_fwd, uint64_t *out_rev,
-                                     float *kernel_ms, uint32_t *kernel_launches) {
+static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint32_t *packed, uint64_t window,
+                              const char *const *queries, const uint32_t *qlens,
+                              uint32_t nq, uint64_t *out_fwd, uint64_t *out_rev,
+                              float *kernel_ms, uint32_t *kernel_launches) {
     if (!ctx) return TIDK_EARG;
     if (kernel_ms) *kernel_ms = 0.f;
     if (kernel_launches) *kernel_launches = 0;
@@ -443,6 +462,7 @@ int tidk_cuda_window_counts_resident(tidk_ctx *ctx, const tidk_seqbuf *buf, uint
 
     WindowJob job{};
     job.seq = buf->d_seq;
+    job.packed = packed; // non-null: the host-packed planes are the source (every query has a static kernel)
     job.items = (const ItemDesc *)ctx->items.p;
     job.out_fwd = d_fwd;
     job.out_rev = d_rev;
@@ -486,7 +506,8 @@ int tidk_cuda_window_counts_resident(tidk_ctx *ctx, const tidk_seqbuf *buf, uint
     // complement) run alone; the rest of the fast ones are fused, up to 16 per launch
     std::vector<uint32_t> fused;
     uint8_t rcbuf[kMaxFastLen];
-    if (LaunchFn clade = (slow.empty() ? find_clade_set(queries, qlens, nq) : nullptr)) {
+    if (packed && !slow.empty()) return fail(ctx, TIDK_ECUDA, "internal: packed source with a literal query");
+    if (LaunchFn clade = (slow.empty() ? find_clade_set(queries, qlens, nq, packed != nullptr) : nullptr)) {
         WindowJob j2 = job; // the whole query list is a known clade: one fused pass
         j2.q0 = 0; j2.nq = nq;
         j2.work_counter = next_counter(); j2.next_counter = next_zeroed;
@@ -497,9 +518,10 @@ int tidk_cuda_window_counts_resident(tidk_ctx *ctx, const tidk_seqbuf *buf, uint
     for (uint32_t q : fast) {
         const uint8_t *f = (const uint8_t *)queries[q];
         revcomp_host(f, qlens[q], rcbuf);
-        LaunchFn fn = find_static(f, qlens[q]);
+        LaunchFn fn = find_static(f, qlens[q], packed != nullptr);
         bool swap = false;
-        if (!fn && (fn = find_static(rcbuf, qlens[q]))) swap = true;
+        if (!fn && (fn = find_static(rcbuf, qlens[q], packed != nullptr))) swap = true;
+        if (!fn && packed) return fail(ctx, TIDK_ECUDA, "internal: packed source without a static kernel");
         if (!fn) { fused.push_back(q); continue; }
         WindowJob j2 = job;
         j2.q0 = q; j2.nq = 1;
@@ -562,6 +584,80 @@ int tidk_cuda_window_counts_resident(tidk_ctx *ctx, const tidk_seqbuf *buf, uint
     return TIDK_OK;
 }
 
+int tidk_cuda_window_counts_resident(tidk_ctx *ctx, const tidk_seqbuf *buf, uint64_t window,
+                                     const char *const *queries, const uint32_t *qlens,
+                                     uint32_t nq, uint64_t *out_fwd, uint64_t *out_rev,
+                                     float *kernel_ms, uint32_t *kernel_launches) {
+    return window_counts_impl(ctx, buf, nullptr, window, queries, qlens, nq, out_fwd, out_rev, kernel_ms,
+                              kernel_launches);
+}
+
+// ---- host-packed upload ----------------------------------------------------------------------
+// PCIe is the end-to-end bound of the host-pointer entry point (about 55 GB/s against a kernel that
+// streams 5 TB/s), so when every query has a plane kernel the host packs the sequence into the
+// three planes the matchers use (3 bits per base, host_pack.hpp) and only those cross the bus.
+// T worker threads each own a stream and a two-slot pinned staging ring; a worker packs one 4 MiB
+// chunk of sequence (1.5 MiB of planes, contiguous on the device) into a free slot and issues its
+// copy, so packing and DMA overlap without any cross-thread barrier.
+static int pack_threads() {
+    if (const char *e = getenv("TIDK_PACK_THREADS")) return atoi(e);
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw == 0) hw = 1;
+    unsigned share = 1; // ranks of one torchrun job share the host cores
+    if (const char *lws = getenv("LOCAL_WORLD_SIZE")) share = (unsigned)atoi(lws) > 0 ? (unsigned)atoi(lws) : 1;
+    unsigned t = hw / share;
+    return (int)(t > 32 ? 32 : t);
+}
+
+static int upload_packed(tidk_ctx *ctx, const uint8_t *seq, uint64_t total, int T) {
+    const uint64_t n_words = (total + 31) / 32;
+    const uint64_t n_chunks = (n_words + kPackWords - 1) / kPackWords;
+    const size_t chunk_bytes = 3ull * kPackWords * 4;
+    int rc;
+    if ((rc = ensure(ctx, ctx->packed, (n_chunks + 1) * chunk_bytes))) return rc; // + one zero chunk: blocks read past the end
+    CU(ctx, cudaMemsetAsync((char *)ctx->packed.p + n_chunks * chunk_bytes, 0, chunk_bytes, ctx->stream));
+    if ((int)ctx->pack_lanes.size() < T) {
+        const size_t old = ctx->pack_lanes.size();
+        ctx->pack_lanes.resize(T);
+        for (size_t i = old; i < (size_t)T; i++) {
+            tidk_ctx::PackLane &L = ctx->pack_lanes[i];
+            CU(ctx, cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
+            CU(ctx, cudaEventCreateWithFlags(&L.ev[0], cudaEventDisableTiming));
+            CU(ctx, cudaEventCreateWithFlags(&L.ev[1], cudaEventDisableTiming));
+            CU(ctx, cudaHostAlloc((void **)&L.pin, 2 * chunk_bytes, cudaHostAllocDefault));
+        }
+    }
+    std::atomic<uint64_t> next_chunk{0};
+    std::atomic<int> cuda_err{0};
+    std::atomic<uint32_t> nonascii{0};
+    auto worker = [&](int t) {
+        cudaSetDevice(ctx->device);
+        tidk_ctx::PackLane &L = ctx->pack_lanes[t];
+        uint32_t flag = 0;
+        for (int slot = 0;; slot ^= 1) {
+            const uint64_t c = next_chunk.fetch_add(1);
+            if (c >= n_chunks) break;
+            if (cudaEventSynchronize(L.ev[slot]) != cudaSuccess) { cuda_err = 1; break; } // slot's previous copy done
+            uint32_t *buf = L.pin + (size_t)slot * 3 * kPackWords;
+            const uint64_t byte0 = c * (uint64_t)kPackWords * 32;
+            pack_words(seq + byte0, (size_t)(total - byte0 < (uint64_t)kPackWords * 32 ? total - byte0 : (uint64_t)kPackWords * 32),
+                       kPackWords, buf, buf + kPackWords, buf + 2 * kPackWords, &flag);
+            if (cudaMemcpyAsync((char *)ctx->packed.p + c * chunk_bytes, buf, chunk_bytes, cudaMemcpyHostToDevice, L.st) != cudaSuccess ||
+                cudaEventRecord(L.ev[slot], L.st) != cudaSuccess) { cuda_err = 1; break; }
+        }
+        if (cudaStreamSynchronize(L.st) != cudaSuccess) cuda_err = 1;
+        if (flag) nonascii = 1;
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; t++) th.emplace_back(worker, t);
+    worker(0);
+    for (auto &x : th) x.join();
+    if (cuda_err) return fail(ctx, TIDK_ECUDA, "packed upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (nonascii)
+        return fail(ctx, TIDK_ENONASCII, "sequence contains a byte >= 0x80 (the reference fails in str::from_utf8, search.rs:107)");
+    return TIDK_OK;
+}
+
 int tidk_cuda_window_counts(tidk_ctx *ctx, const uint8_t *seq, const uint64_t *offsets,
                             uint32_t n_records, uint64_t window, const char *const *queries,
                             const uint32_t *qlens, uint32_t nq, uint64_t *out_fwd,
@@ -569,10 +665,46 @@ int tidk_cuda_window_counts(tidk_ctx *ctx, const uint8_t *seq, const uint64_t *o
     if (!ctx) return TIDK_EARG;
     if (window == 0) return fail(ctx, TIDK_EARG, "window must be > 0 (slice::chunks(0) panics, search.rs:98)");
     CU(ctx, cudaSetDevice(ctx->device));
+    // host-packed path: worth it when there are enough cores to pack faster than PCIe moves ASCII,
+    // and possible when every query runs on a compile-time plane kernel
+    const uint64_t total = (n_records && offsets) ? offsets[n_records] : 0;
+    const char *env = getenv("TIDK_HOST_PACK");
+    const int T = pack_threads();
+    // 12+ packer threads: 16 cores pack ~76 GB/s of sequence on the B200 hosts (tools/pack_bench.cpp),
+    // 8 only ~58 GB/s shared with whatever the other ranks of the job are doing -- not enough to beat DMA
+    bool packable = total >= (32u << 20) && seq && queries && qlens && nq > 0 && (env ? atoi(env) != 0 : T >= 12) && T >= 1;
+    if (packable && !find_clade_set(queries, qlens, nq, true)) {
+        uint8_t rcbuf[kMaxFastLen];
+        for (uint32_t q = 0; q < nq && packable; q++) {
+            bool ok = queries[q] && qlens[q] >= 1 && qlens[q] <= (uint32_t)kMaxFastLen;
+            for (uint32_t j = 0; ok && j < qlens[q]; j++) ok = is_acgt((uint8_t)queries[q][j]);
+            if (ok) {
+                revcomp_host((const uint8_t *)queries[q], qlens[q], rcbuf);
+                ok = find_static((const uint8_t *)queries[q], qlens[q], true) || find_static(rcbuf, qlens[q], true);
+            }
+            packable = ok;
+        }
+    }
+    uint64_t n_out = 0;
+    for (uint32_t r = 0; r < n_records && offsets; r++) {
+        const uint64_t len = offsets[r + 1] - offsets[r];
+        n_out += (len / window + (len % window != 0)) * nq;
+    }
+    ctx->last_d2h = n_out * 16 + 4;
+    ctx->last_packed = packable ? 1 : 0;
+    ctx->last_h2d = ((uint64_t)n_records + 1) * 16 +
+                    (packable ? (((total + 31) / 32 + kPackWords - 1) / kPackWords) * 3ull * kPackWords * 4 : total);
+    if (packable) {
+        int rc = seqbuf_fill(ctx, &ctx->scratch, seq, offsets, n_records, /*copy_seq=*/false);
+        if (rc) return rc;
+        if ((rc = upload_packed(ctx, seq, total, T))) return rc;
+        return window_counts_impl(ctx, &ctx->scratch, (const uint32_t *)ctx->packed.p, window, queries, qlens, nq,
+                                  out_fwd, out_rev, nullptr, nullptr);
+    }
     int rc = seqbuf_fill(ctx, &ctx->scratch, seq, offsets, n_records);
     if (rc) return rc;
-    return tidk_cuda_window_counts_resident(ctx, &ctx->scratch, window, queries, qlens, nq, out_fwd,
-                                            out_rev, nullptr, nullptr);
+    return window_counts_impl(ctx, &ctx->scratch, nullptr, window, queries, qlens, nq, out_fwd,
+                              out_rev, nullptr, nullptr);
 }
 
 int tidk_cuda_explore_runs_resident(tidk_ctx *ctx, const tidk_seqbuf *buf, double distance,
@@ -609,6 +741,14 @@ int tidk_cuda_explore_runs(tidk_ctx *ctx, const uint8_t *seq, const uint64_t *of
 }
 
 void tidk_cuda_free_runs(tidk_run *runs) { free(runs); }
+
+int tidk_cuda_last_transfer(const tidk_ctx *ctx, uint64_t *h2d_bytes, uint64_t *d2h_bytes, int *host_packed) {
+    if (!ctx) return TIDK_EARG;
+    if (h2d_bytes) *h2d_bytes = ctx->last_h2d;
+    if (d2h_bytes) *d2h_bytes = ctx->last_d2h;
+    if (host_packed) *host_packed = ctx->last_packed;
+    return TIDK_OK;
+}
 
 int tidk_cuda_last_explore_timings(const tidk_ctx *ctx, float *out, int n) {
     if (!ctx || !out || n <= 0) return 0;

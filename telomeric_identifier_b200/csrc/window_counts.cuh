@@ -84,8 +84,12 @@ __global__ void __launch_bounds__(256) window_items_kernel(const PrepJob job) {
     job.items[item] = d;
 }
 
+constexpr int kPackShift = 17;                    // 2^17 words = 4 MiB of sequence per packed chunk
+constexpr uint32_t kPackWords = 1u << kPackShift; // chunk layout: [lo words][hi words][va words]
+
 struct WindowJob {
-    const uint8_t *seq;      // device, 256-B aligned, zero padding behind the data
+    const uint8_t *seq;      // device, 256-B aligned, zero padding behind the data (ASCII source)
+    const uint32_t *packed;  // device bit-planes packed by the host (packed source), else nullptr
     const ItemDesc *items;
     uint64_t *out_fwd;       // [record][query][window]
     uint64_t *out_rev;
@@ -265,8 +269,40 @@ struct RuntimeMatcher {
     }
 };
 
+// ------------------------------------------------------------------ sources
+// Where a lane's 32 bases come from.  AsciiSource: the sequence as uploaded (1 byte per base), turned
+// into planes in registers.  PackedSource: planes built on the host by the upload path of
+// tidk_cuda_window_counts (3 bits per base cross PCIe instead of 8), read as three coalesced words.
+struct AsciiSource {
+    struct Raw { uint32_t w[8]; };
+    using Cooked = Nibbles;
+    __device__ __forceinline__ static void load(const WindowJob &job, uint64_t block_off, int lane, Raw &r) {
+        ld256_stream(job.seq + block_off + (uint32_t)lane * 32u, r.w);
+    }
+    __device__ __forceinline__ static Cooked cook(const Raw &r) { return to_nibbles(r.w); }
+    __device__ __forceinline__ static Planes planes(const Cooked &c, uint32_t &nonascii) { return extract_planes(c, nonascii); }
+};
+
+struct PackedSource {
+    struct Raw { uint32_t lo, hi, va; };
+    using Cooked = Raw;
+    __device__ __forceinline__ static void load(const WindowJob &job, uint64_t block_off, int lane, Raw &r) {
+        const uint64_t word = (block_off >> 5) + (uint32_t)lane;
+        const uint32_t *p = job.packed + (word >> kPackShift) * (3ull * kPackWords) + (word & (kPackWords - 1));
+        r.lo = __ldg(p); r.hi = __ldg(p + kPackWords); r.va = __ldg(p + 2 * kPackWords);
+    }
+    __device__ __forceinline__ static Cooked cook(const Raw &r) { return r; }
+    __device__ __forceinline__ static Planes planes(const Cooked &c, uint32_t &) {
+        Planes P;
+        P.lo = c.lo; P.hi = c.hi;
+        P.b0 = c.va ^ (c.hi & ~c.lo); // the matchers' validity term b0 ^ (hi & ~lo) then equals va
+        P.ok = 0xFFFFFFFFu; P.exact = false;
+        return P;
+    }
+};
+
 // ------------------------------------------------------------------ the kernel
-template <class M, int MINB>
+template <class M, int MINB, class Src = AsciiSource>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
 window_counts_kernel(const WindowJob job, const typename M::Params mp) {
     const int lane = threadIdx.x & 31;
@@ -284,11 +320,8 @@ window_counts_kernel(const WindowJob job, const typename M::Params mp) {
 
     const uint4 *ip = reinterpret_cast<const uint4 *>(job.items);
     uint4 da = __ldg(ip + 2 * item), db = __ldg(ip + 2 * item + 1);
-    uint32_t w[8];
-    {
-        const uint64_t scan0 = ((uint64_t)da.y << 32) | da.x;
-        ld256_stream(job.seq + scan0 + (uint32_t)lane * 32u, w);
-    }
+    typename Src::Raw w;
+    Src::load(job, ((uint64_t)da.y << 32) | da.x, lane, w);
 
     for (;;) {
         // decode the current descriptor
@@ -314,17 +347,16 @@ window_counts_kernel(const WindowJob job, const typename M::Params mp) {
         typename M::Carry carry;
         M::reset(carry);
 
-        const uint8_t *ptr = job.seq + scan0 + (uint32_t)lane * 32u;
+        uint64_t off = scan0;
         for (uint32_t blk = 0; blk < nblk; blk++) {
-            const Nibbles nib = to_nibbles(w); // w is dead from here: refill it
+            const typename Src::Cooked ck = Src::cook(w); // w is dead from here: refill it
             if (blk + 1 < nblk) {
-                ptr += 1024;
-                ld256_stream(ptr, w);
+                off += 1024;
+                Src::load(job, off, lane, w);
             } else if (have_next) {
-                const uint64_t nscan0 = ((uint64_t)na.y << 32) | na.x;
-                ld256_stream(job.seq + nscan0 + (uint32_t)lane * 32u, w);
+                Src::load(job, ((uint64_t)na.y << 32) | na.x, lane, w);
             }
-            Planes P = extract_planes(nib, nonascii);
+            Planes P = Src::planes(ck, nonascii);
             uint32_t cmask = 0xFFFFFFFFu;
             bool special = P.exact;
             if (blk < nlead || blk + 1 == nblk) { // warp-uniform: only edge blocks pay for masks
@@ -336,10 +368,8 @@ window_counts_kernel(const WindowJob job, const typename M::Params mp) {
             M::step(mp, P, special, cmask, lane, carry, cf, cr);
         }
 
-        if (nblk == 0 && have_next) { // empty item (window shorter than its segment grid):
-            const uint64_t nscan0 = ((uint64_t)na.y << 32) | na.x; // nobody prefetched for the next one
-            ld256_stream(job.seq + nscan0 + (uint32_t)lane * 32u, w);
-        }
+        if (nblk == 0 && have_next) // empty item (window shorter than its segment grid): nobody
+            Src::load(job, ((uint64_t)na.y << 32) | na.x, lane, w); // prefetched for the next one
         if (nblk > 0) {
 #pragma unroll
             for (int q = 0; q < M::NQ; q++) {

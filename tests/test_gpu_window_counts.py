@@ -282,3 +282,38 @@ def test_full_size_c1_c4_properties(ctx, cfg, query):
         assert (f[s:s + of.size] == of).all() and (r[s:s + orr.size] == orr).all(), (rec, w0)
     assert int(f.sum()) + int(r.sum()) > 1000                       # the planted arrays are seen
     b.free()
+
+
+def test_host_packed_upload_path(ctx, monkeypatch):
+    """tidk_cuda_window_counts packs the sequence into bit-planes on the host when every query has a
+    compile-time kernel (3 bits per base cross PCIe instead of 8).  Same counts as the oracle; queries
+    without a compile-time kernel, and small inputs, keep taking the plain upload."""
+    import os
+    import telomeric_identifier_b200 as T
+    from telomeric_identifier_b200 import clades, synth
+    db = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "clades_min.csv")
+    ids, seq, off = synth.config4(scale=0.012)          # ~37 Mb with N gaps, above the 32 MiB threshold
+    seq = seq.copy()
+    seq[1_000_000:1_200_000] |= 0x20                     # a soft-masked stretch
+    seq[5_000_000:5_000_100] = np.frombuffer(b"RYKMSWBDHV" * 10, dtype=np.uint8)
+    hym = [r.encode() for r in clades.return_telomere_sequence("Hymenoptera", db)]
+    monkeypatch.setenv("TIDK_HOST_PACK", "1")
+    for qs, W in (([b"TTAGGG"], 10000), ([b"CCCTAA", b"AACCT"], 4321), (hym, 10000), ([b"TTAGGG"], 50000)):
+        f, r = ctx.window_counts(seq, off, W, qs)
+        of, orr = O.window_counts(seq, off, W, qs, False, threads=4)
+        assert (f == of).all() and (r == orr).all(), (qs, W)
+    # a query without a compile-time kernel falls back to the plain upload, same answer
+    f, r = ctx.window_counts(seq, off, 10000, [b"GATTACA", b"TTAGGG"])
+    of, orr = O.window_counts(seq, off, 10000, [b"GATTACA", b"TTAGGG"], False, threads=4)
+    assert (f == of).all() and (r == orr).all()
+    # non-ASCII is caught by the host packer
+    bad = seq.copy()
+    bad[123_457] = 0xE2
+    with pytest.raises(T.TidkCudaError) as e:
+        ctx.window_counts(bad, off, 10000, [b"TTAGGG"])
+    assert e.value.code == -4
+    monkeypatch.setenv("TIDK_HOST_PACK", "0")
+    f2, r2 = ctx.window_counts(seq, off, 10000, [b"TTAGGG"])
+    monkeypatch.setenv("TIDK_HOST_PACK", "1")
+    f3, r3 = ctx.window_counts(seq, off, 10000, [b"TTAGGG"])
+    assert (f2 == f3).all() and (r2 == r3).all()
