@@ -40,18 +40,35 @@ __attribute__((target("avx2"))) inline void pack_words_avx2(const uint8_t *src, 
     const __m256i c20 = _mm256_set1_epi8(0x20), ca = _mm256_set1_epi8('a'), cc = _mm256_set1_epi8('c'),
                   cg = _mm256_set1_epi8('g'), ct = _mm256_set1_epi8('t');
     uint32_t na = 0;
-    for (size_t w = 0; w < full; w++) {
-        const __m256i v = _mm256_loadu_si256((const __m256i *)(src + w * 32));
-        // movemask takes bit 7 of every byte: shift the wanted bit there (16-bit lanes: bit 1 / 2 of a
-        // byte lands on bit 7 of the same byte)
-        lo[w] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 6));
-        hi[w] = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 5));
-        const __m256i u = _mm256_or_si256(v, c20);
-        const __m256i ok = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(u, ca), _mm256_cmpeq_epi8(u, cc)),
-                                           _mm256_or_si256(_mm256_cmpeq_epi8(u, cg), _mm256_cmpeq_epi8(u, ct)));
-        va[w] = (uint32_t)_mm256_movemask_epi8(ok);
-        na |= (uint32_t)_mm256_movemask_epi8(v);
+    // movemask takes bit 7 of every byte: shift the wanted bit there (16-bit lanes: bit 1 / 2 of a byte
+    // lands on bit 7 of the same byte)
+#define TIDK_PACK_ONE(W, L, H, V)                                                                        \
+    do {                                                                                                 \
+        const __m256i v = _mm256_loadu_si256((const __m256i *)(src + (W) * 32));                         \
+        (L) = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 6));                                   \
+        (H) = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 5));                                   \
+        const __m256i u = _mm256_or_si256(v, c20);                                                       \
+        const __m256i ok = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(u, ca), _mm256_cmpeq_epi8(u, cc)), \
+                                           _mm256_or_si256(_mm256_cmpeq_epi8(u, cg), _mm256_cmpeq_epi8(u, ct))); \
+        (V) = (uint32_t)_mm256_movemask_epi8(ok);                                                        \
+        na |= (uint32_t)_mm256_movemask_epi8(v);                                                         \
+    } while (0)
+    size_t w = 0;
+    // eight words at a time with non-temporal stores when the destinations are 32-byte aligned (they
+    // are for the pinned staging buffers): the planes are written once and read only by the DMA engine,
+    // so they should not be pulled into the cache first (no read-for-ownership traffic)
+    if ((((uintptr_t)lo | (uintptr_t)hi | (uintptr_t)va) & 31) == 0) {
+        alignas(32) uint32_t tl[8], th[8], tv[8];
+        for (; w + 8 <= full; w += 8) {
+            for (int i = 0; i < 8; i++) TIDK_PACK_ONE(w + i, tl[i], th[i], tv[i]);
+            _mm256_stream_si256((__m256i *)(lo + w), _mm256_load_si256((const __m256i *)tl));
+            _mm256_stream_si256((__m256i *)(hi + w), _mm256_load_si256((const __m256i *)th));
+            _mm256_stream_si256((__m256i *)(va + w), _mm256_load_si256((const __m256i *)tv));
+        }
+        _mm_sfence();
     }
+    for (; w < full; w++) TIDK_PACK_ONE(w, lo[w], hi[w], va[w]);
+#undef TIDK_PACK_ONE
     if (na) *nonascii = 1;
     if (full < n_words)
         pack_words_scalar(src + full * 32, n_bytes - full * 32, n_words - full, lo + full, hi + full, va + full, nonascii);

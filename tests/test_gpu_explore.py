@@ -173,3 +173,15 @@ def test_host_and_device_run_building_agree(ctx):
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root,
                            env={**os.environ, **env_extra})
         assert r.returncode == 0 and r.stdout.startswith("ok"), r.stderr[-2000:]
+
+
+def test_dense_events_overflow_and_retry(ctx):
+    """Worst case for the event list: 'AACC' repeated makes a raw-run boundary at almost every chunk for
+    k = 1 and k = 2, far more than the first-guess buffer (scanned / 64) holds -- the call must notice
+    the overflow, re-run with the exact size and still agree with the oracle."""
+    n = 3_000_000
+    seq = np.frombuffer((b"AACC" * (n // 4 + 1))[:n], dtype=np.uint8).copy()
+    seq[1_000_000:1_000_400] = ord("G")  # one long run in the middle
+    off = np.array([0, n], dtype=np.uint64)
+    _runs_equal(ctx, seq, off, 0.5, 1, 3, 0)
+    _runs_equal(ctx, seq, off, 0.5, 1, 2, 50)

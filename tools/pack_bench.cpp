@@ -12,7 +12,13 @@ int main() {
     uint64_t x = 88172645463325252ull;
     for (size_t i = 0; i < n; i++) { x ^= x << 13; x ^= x >> 7; x ^= x << 17; s[i] = al[x & 7]; }
     const size_t nw = n / 32;
-    std::vector<uint32_t> lo(nw), hi(nw), va(nw);
+    // 64-byte aligned outputs (like the pinned staging buffers): the packer then uses non-temporal stores;
+    // PACK_BENCH_MISALIGN=1 offsets them by 4 bytes to measure the plain-store path
+    const size_t mis = getenv("PACK_BENCH_MISALIGN") ? 1 : 0;
+    uint32_t *lo_b = (uint32_t *)aligned_alloc(64, (nw + 16) * 4), *hi_b = (uint32_t *)aligned_alloc(64, (nw + 16) * 4),
+             *va_b = (uint32_t *)aligned_alloc(64, (nw + 16) * 4);
+    memset(lo_b, 0, (nw + 16) * 4); memset(hi_b, 0, (nw + 16) * 4); memset(va_b, 0, (nw + 16) * 4);
+    struct V { uint32_t *p; uint32_t *data() { return p; } } lo{lo_b + mis}, hi{hi_b + mis}, va{va_b + mis};
     printf("avx2=%d avx512bw=%d hw_threads=%u\n", __builtin_cpu_supports("avx2"), __builtin_cpu_supports("avx512bw"),
            std::thread::hardware_concurrency());
     for (int T : {1, 2, 4, 8, 16, 32}) {
