@@ -530,9 +530,13 @@ static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint3
         fn(j2, grid, ctx->stream);
         launches++;
     }
+    // Run-time patterns: one unrolled single-query launch each (about 100 us + 6.5 us per base on C2),
+    // unless there are many -- the fused run-time kernel is not unrolled and costs about 130 us per
+    // query on top of one pass, so it only wins from about nine queries up.
+    const bool fuse_runtime = fused.size() >= 9;
     for (size_t g0 = 0; g0 < fused.size();) {
         size_t g1 = g0 + 1; // consecutive query indices only (output addressing is q0 + i)
-        while (g1 < fused.size() && g1 - g0 < (size_t)kMaxFastQueries && fused[g1] == fused[g1 - 1] + 1) g1++;
+        while (fuse_runtime && g1 < fused.size() && g1 - g0 < (size_t)kMaxFastQueries && fused[g1] == fused[g1 - 1] + 1) g1++;
         RuntimeQueries rq{};
         for (size_t i = g0; i < g1; i++) {
             const uint32_t q = fused[i];
