@@ -317,3 +317,20 @@ def test_host_packed_upload_path(ctx, monkeypatch):
     monkeypatch.setenv("TIDK_HOST_PACK", "1")
     f3, r3 = ctx.window_counts(seq, off, 10000, [b"TTAGGG"])
     assert (f2 == f3).all() and (r2 == r3).all()
+
+
+def test_many_runtime_queries_fused_kernel(ctx):
+    """Nine or more queries without a compile-time kernel share one pass of the fused run-time kernel
+    (mixed lengths 3..32, consecutive and non-consecutive query indices)."""
+    from telomeric_identifier_b200 import synth
+    rng = np.random.default_rng(42)
+    ids, seq, off = synth.random_records(31, 3, 90000, b"ACGTNacgt")
+    qs = []
+    for L in (3, 4, 6, 7, 9, 12, 13, 17, 21, 25, 31, 32):
+        p = int(rng.integers(0, seq.size - 40))
+        q = bytes(seq[p:p + L]).upper().replace(b"N", b"A")
+        qs.append(q)
+        seq[p + 100:p + 100 + L] = np.frombuffer(q, dtype=np.uint8)
+    _cmp(ctx, seq, off, 10000, qs)
+    _cmp(ctx, seq, off, 999, qs[:5] + [b"TTAGGG"] + qs[5:])  # a compile-time motif in the middle splits the run
+    _cmp(ctx, seq, off, 40000, qs + qs[:8])                   # 20 run-time queries: two fused launches
