@@ -2,10 +2,13 @@
 // same subcommands, flags and defaults as main.rs:18-146 for search / find / explore, same output
 // files and rows (search.rs:35-54,132-147; finder.rs:66-78,169-172; explore.rs:140-143), same
 // stderr progress lines.  All counting / run detection goes through libtidk_cuda.so (C ABI);
-// there is no CPU path.  `plot`, `build` and `--log` are out of scope.
+// there is no CPU path.  `--log` writes the reference's log files; `plot` and `build` are out of scope
+// (SURVEY.md section 2).
 #include <sys/stat.h>
 
 #include <cerrno>
+#include <charconv>
+#include <ctime>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -91,7 +94,6 @@ Args parse(int argc, char **argv) {
         else if (a.fasta.empty()) a.fasta = f;
         else die("unexpected argument '" + f + "'");
     }
-    if (a.log) fprintf(stderr, "[-]\t--log is not implemented in the B200 driver (out of scope)\n");
     return a;
 }
 
@@ -131,6 +133,35 @@ struct Ctx {
         if (rc != 0) die(std::string("tidk-cuda error ") + std::to_string(rc) + ": " + tidk_cuda_last_error(h), 1);
     }
 };
+
+// --log: the files SubCommand::log writes (lib.rs:65-242), same text; the date is local time in the
+// reference's format "%Y-%m-%d: %H:%M:%S" (lib.rs:59).  The version line names the tidk release whose
+// behaviour this driver reproduces.
+const char *kTidkVersion = "0.2.7";
+
+std::string now_string() {
+    char buf[64];
+    time_t t = time(nullptr);
+    struct tm tmv;
+    localtime_r(&t, &tmv);
+    strftime(buf, sizeof buf, "%Y-%m-%d: %H:%M:%S", &tmv);
+    return buf;
+}
+
+std::string rust_f64(double v) { // Rust `{}` on f64: shortest digits that round-trip, no exponent for these magnitudes
+    char buf[64];
+    auto r = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::fixed);
+    return std::string(buf, r.ptr);
+}
+
+void write_log_file(const std::string &name, const std::string &text) {
+    FILE *f = fopen(name.c_str(), "wb");
+    if (!f) die("cannot create " + name, 1);
+    fputs(text.c_str(), f);
+    fputc('\n', f); // writeln!
+    fclose(f);
+    fprintf(stderr, "[+]\tLog file written to: %s\n", name.c_str());
+}
 
 const char *kHeader = "id\twindow\tforward_repeat_number\treverse_repeat_number\ttelomeric_repeat\n";
 
@@ -218,7 +249,14 @@ int cmd_search(const Args &a) { // search::search, search.rs:10-79
     fprintf(stderr, "[+]\tSearching genome for telomeric repeat: %s\n", a.string_.c_str());
     const std::string fwd = ascii_upper(a.string_); // search.rs:93
     const std::string path = a.dir + "/" + a.output + "_telomeric_repeat_windows." + a.extension;
-    return run_counts(a, {fwd}, {fwd}, path, a.extension == "tsv", a.extension != "tsv");
+    const int rc = run_counts(a, {fwd}, {fwd}, path, a.extension == "tsv", a.extension != "tsv");
+    if (rc == 0 && a.log) // lib.rs:192-239 (the raw string ends with a newline and twenty blanks)
+        write_log_file(a.dir + "/" + a.output + ".log",
+                       std::string("tidk version: ") + kTidkVersion + "\nLog information for output file: " + path +
+                           "\nDate: " + now_string() + "\n`tidk search` was run with the following parameters:\n    Input fasta: " +
+                           a.fasta + "\n    Telomeric repeat search string: " + a.string_ + "\n    Window size: " +
+                           std::to_string(a.window) + "\n                    ");
+    return rc;
 }
 
 int cmd_find(const Args &a) { // finder::finder, finder.rs:13-107
@@ -244,7 +282,18 @@ int cmd_find(const Args &a) { // finder::finder, finder.rs:13-107
         for (auto &r : reps) fprintf(stderr, "[+]\t\t%s\n", r.c_str());
     }
     const std::string path = a.dir + "/" + a.output + "_telomeric_repeat_windows.tsv";
-    return run_counts(a, reps, reps, path, true, false); // repeats verbatim, finder.rs:129-136
+    const int rc = run_counts(a, reps, reps, path, true, false); // repeats verbatim, finder.rs:129-136
+    if (rc == 0 && a.log) { // lib.rs:69-117 (the reference names the output "...windows.csv" in the log; kept)
+        std::string joined;
+        for (size_t i = 0; i < reps.size(); i++) joined += (i ? ", " : "") + reps[i];
+        write_log_file(a.dir + "/" + a.output + ".log",
+                       std::string("tidk version: ") + kTidkVersion + "\nLog information for output file: " + a.dir + "/" +
+                           a.output + "_telomeric_repeat_windows.csv\nDate: " + now_string() +
+                           "\n`tidk find` was run with the following parameters:\n    Input fasta: " + a.fasta +
+                           "\n    Window size: " + std::to_string(a.window) + "\n    Clade chosen: " + a.clade +
+                           "\n    Telomeric repeats queried: " + joined);
+    }
+    return rc;
 }
 
 int cmd_explore(const Args &a) { // explore::explore, explore.rs:20-149
@@ -302,6 +351,14 @@ int cmd_explore(const Args &a) { // explore::explore, explore.rs:20-149
     printf("canonical_repeat_unit\tcount_repeat_runs_gt_%lld\n", a.threshold); // explore.rs:140
     for (auto &r : rows) printf("%s\t%lld\n", r.first.c_str(), r.second);
     if (a.stats) fprintf(stderr, "{\"runs\": %llu, \"kernel_ms\": %.4f, \"kernel_launches\": %u}\n", (unsigned long long)n, ms, nl);
+    if (a.log) // lib.rs:119-190: written to the current directory
+        write_log_file("tidk-explore.log",
+                       std::string("tidk version: ") + kTidkVersion + "\nLog information for output files: printed to STDOUT\nDate: " +
+                           now_string() + "\n`tidk explore` was run with the following parameters:\n    Input fasta: " + a.fasta +
+                           "\n    Explored telomeric repeat units of length: " + std::to_string(length) + "\n    Or from length: " +
+                           std::to_string(a.minimum) + "\n    To length: " + std::to_string(a.maximum) + "\n    Threshold: " +
+                           std::to_string(a.threshold) + "\n    Searching at " + rust_f64(a.distance * 100.0) +
+                           "% distance from chromosome end");
     return 0;
 }
 

@@ -97,3 +97,38 @@ def test_cli_argument_errors(tmp_path):
     assert run("plot", "-t", "x.tsv").returncode == 2
     p = run("find", "--print", "--database", DB)
     assert p.returncode == 1 and "Lepidoptera\tAACCT" in p.stderr
+
+
+@pytest.mark.gpu
+def test_cli_log_files_and_plot_schema(genome, tmp_path):
+    """--log writes the reference's log text (lib.rs:65-242, date aside), and the TSV deserialises into
+    plot's TelomericRepeatRecord (plot.rs:76-96): String, i32, i32, i32, String under the header names."""
+    import csv
+    import re
+    d, fa, ids, seq, off, seqs = genome
+    r = run("search", fa, "-s", "TTAGG", "-o", "lg", "-d", str(tmp_path), "--log")
+    assert r.returncode == 0 and f"[+]\tLog file written to: {tmp_path}/lg.log" in r.stderr
+    text = open(tmp_path / "lg.log").read()
+    want = (f"tidk version: 0.2.7\nLog information for output file: {tmp_path}/lg_telomeric_repeat_windows.tsv\n"
+            f"Date: DATE\n`tidk search` was run with the following parameters:\n    Input fasta: {fa}\n"
+            f"    Telomeric repeat search string: TTAGG\n    Window size: 10000\n                    \n")
+    assert re.sub(r"Date: \d{4}-\d\d-\d\d: \d\d:\d\d:\d\d", "Date: DATE", text) == want
+    r = run("find", fa, "-c", "Coleoptera", "-o", "fl", "-d", str(tmp_path), "--database", DB, "--log")
+    assert r.returncode == 0
+    text = open(tmp_path / "fl.log").read()
+    assert text.endswith("    Window size: 10000\n    Clade chosen: Coleoptera\n    Telomeric repeats queried: AACCC, AACCT, AACAGACCCG, ACCTG\n")
+    assert f"Log information for output file: {tmp_path}/fl_telomeric_repeat_windows.csv\n" in text
+    r = subprocess.run([TIDK, "explore", fa, "-m", "5", "-x", "6", "--distance", "0.07", "--log"], capture_output=True,
+                       text=True, cwd=str(tmp_path))
+    assert r.returncode == 0
+    text = open(tmp_path / "tidk-explore.log").read()
+    assert text.endswith("    Explored telomeric repeat units of length: 0\n    Or from length: 5\n    To length: 6\n"
+                         "    Threshold: 100\n    Searching at 7.000000000000001% distance from chromosome end\n")
+    # plot.rs schema
+    with open(tmp_path / "lg_telomeric_repeat_windows.tsv", newline="") as fh:
+        rows = list(csv.DictReader(fh, delimiter="\t"))
+    assert list(rows[0].keys()) == ["id", "window", "forward_repeat_number", "reverse_repeat_number", "telomeric_repeat"]
+    for row in rows:
+        for col in ("window", "forward_repeat_number", "reverse_repeat_number"):
+            assert 0 <= int(row[col]) < 2 ** 31
+        assert row["telomeric_repeat"] == "TTAGG" and row["id"] in ids
