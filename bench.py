@@ -190,8 +190,8 @@ def main():
     nwin = int(T.api.n_windows(off, WINDOW).sum()) * len(REPEATS)
     # pinned host copies: what a host reader parsing straight into tidk_cuda_host_alloc memory holds
     pseq = ctx.pinned_empty(bases); pseq[:] = seq
-    pf = ctx.pinned_empty(nwin * 8).view(np.uint64)
-    pr = ctx.pinned_empty(nwin * 8).view(np.uint64)
+    pout = ctx.pinned_empty(2 * nwin * 8).view(np.uint64)  # forward and reverse counts back to back: one D2H copy
+    pf, pr = pout[:nwin], pout[nwin:]
     batch = ctx.upload(pseq, off)
 
     # correctness spot check against the oracle before timing anything (rank 0, first 2 Mb)

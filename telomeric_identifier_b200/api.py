@@ -194,7 +194,11 @@ class Context:
 
     def window_counts_resident(self, batch: SeqBatch, window: int, queries: Sequence[bytes],
                                out: Optional[Tuple[np.ndarray, np.ndarray]] = None):
-        qa, ql, nq = _qargs(queries)
+        key = tuple(queries)
+        cached = getattr(self, "_qcache", None)
+        if cached is None or cached[0] != key:  # the ctypes argument arrays are rebuilt only when the queries change
+            self._qcache = cached = (key, _qargs(queries))
+        qa, ql, nq = cached[1]
         total = int(n_windows(batch.offsets, window).sum()) * nq if window > 0 else 0
         if out is None:
             fwd = np.zeros(max(total, 1), dtype=np.uint64)

@@ -427,8 +427,9 @@ static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint3
     const uint64_t n_items = n_windows * spw;
 
     int rc;
-    if ((rc = ensure(ctx, ctx->out_fwd, n_out * 8))) return rc;
-    if ((rc = ensure(ctx, ctx->out_rev, n_out * 8))) return rc;
+    // one allocation, forward counts then reverse counts, so that a caller whose two output arrays are
+    // adjacent in memory gets both with a single copy
+    if ((rc = ensure(ctx, ctx->out_fwd, 2 * n_out * 8))) return rc;
     if (!ctx->misc.p) { // two queue counters (each launch zeroes the other one) + error flags
         if ((rc = ensure(ctx, ctx->misc, 256))) return rc;
         CU(ctx, cudaMemsetAsync(ctx->misc.p, 0, 256, ctx->stream));
@@ -440,10 +441,9 @@ static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint3
         ctx->counter_flip = 0;
     }
     ctx->counters_dirty = true; // cleared when this call has completed all its launches
-    uint64_t *d_fwd = (uint64_t *)ctx->out_fwd.p, *d_rev = (uint64_t *)ctx->out_rev.p;
+    uint64_t *d_fwd = (uint64_t *)ctx->out_fwd.p, *d_rev = d_fwd + n_out;
     if (spw > 1) {
-        CU(ctx, cudaMemsetAsync(d_fwd, 0, n_out * 8, ctx->stream));
-        CU(ctx, cudaMemsetAsync(d_rev, 0, n_out * 8, ctx->stream));
+        CU(ctx, cudaMemsetAsync(d_fwd, 0, 2 * n_out * 8, ctx->stream));
     }
 
     uint32_t launches = 0;
@@ -574,8 +574,12 @@ static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint3
     CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     CU(ctx, cudaGetLastError());
 
-    CU(ctx, cudaMemcpyAsync(out_fwd, d_fwd, n_out * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaMemcpyAsync(out_rev, d_rev, n_out * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_rev == out_fwd + n_out) {
+        CU(ctx, cudaMemcpyAsync(out_fwd, d_fwd, 2 * n_out * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        CU(ctx, cudaMemcpyAsync(out_fwd, d_fwd, n_out * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(out_rev, d_rev, n_out * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CU(ctx, cudaMemcpyAsync(ctx->h_flags, job.err_flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->counters_dirty = false;
