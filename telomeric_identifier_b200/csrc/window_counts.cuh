@@ -21,6 +21,8 @@
 // ahead, and the queue ticket two items ahead, so the memory pipe never drains
 // at a window boundary.
 #pragma once
+#include <type_traits>
+
 #include "planes.cuh"
 
 namespace tidk {
@@ -348,7 +350,11 @@ window_counts_kernel(const WindowJob job, const typename M::Params mp) {
         M::reset(carry);
 
         uint64_t off = scan0;
-        for (uint32_t blk = 0; blk < nblk; blk++) {
+        // One 1 KiB block.  EDGE blocks (the first one, the second one of a later segment, the last one)
+        // confine matching to the window / segment with masks; the blocks in between carry no mask
+        // state at all, so their loop is peeled into its own lean copy.
+        auto block = [&](uint32_t blk, auto edge_tag) {
+            constexpr bool EDGE = decltype(edge_tag)::value;
             const typename Src::Cooked ck = Src::cook(w); // w is dead from here: refill it
             if (blk + 1 < nblk) {
                 off += 1024;
@@ -359,14 +365,18 @@ window_counts_kernel(const WindowJob job, const typename M::Params mp) {
             Planes P = Src::planes(ck, nonascii);
             uint32_t cmask = 0xFFFFFFFFu;
             bool special = P.exact;
-            if (blk < nlead || blk + 1 == nblk) { // warp-uniform: only edge blocks pay for masks
+            if (EDGE) {
                 const int prel = (int)(blk << 10) + lane * 32;
                 P.ok &= range_mask32(vbeg - prel, vend - prel);
                 special = true;
                 if (multi) cmask = range_mask32(cbeg - prel, cend - prel);
             }
             M::step(mp, P, special, cmask, lane, carry, cf, cr);
-        }
+        };
+        uint32_t blk = 0;
+        for (; blk < nlead && blk < nblk; blk++) block(blk, std::true_type{});
+        for (; blk + 1 < nblk; blk++) block(blk, std::false_type{});
+        if (blk < nblk) block(blk, std::true_type{});
 
         if (nblk == 0 && have_next) // empty item (window shorter than its segment grid): nobody
             Src::load(job, ((uint64_t)na.y << 32) | na.x, lane, w); // prefetched for the next one
