@@ -141,6 +141,12 @@ __device__ __forceinline__ bool chunks_equal_upper(const uint8_t *t, int k, uint
     return true;
 }
 
+// per-CTA stash of the run boundaries found in the current block: [k - 1][thread]
+struct EvStash {
+    uint32_t ev[kPlaneMaxK][256];
+    uint32_t z[kPlaneMaxK][256];
+};
+
 template <int K>
 __host__ __device__ constexpr uint64_t periodic_mask64() { // bits at multiples of K below 64
     uint64_t m = 0;
@@ -150,6 +156,7 @@ __host__ __device__ constexpr uint64_t periodic_mask64() { // bits at multiples 
 
 struct Planes3 {
     uint32_t lo, hi, va;
+    uint32_t cs; // letter case (ASCII bit 5); only filled in when the block needs it
 };
 
 // One k for one 32-base word.  WITH_VA: honour the validity plane (edge blocks); interior blocks of
@@ -165,15 +172,17 @@ struct Planes3 {
 // s_lo is the bit position (0..K-1) of the first chunk end in the PREVIOUS word: the phase of that
 // word's first base is (rel0 + offset - 32) mod K, recomputed per block with a multiply-shift on
 // the fma pipe (keeping it in a register per k costs a CTA of occupancy).
-template <int K, bool WITH_VA, bool EMIT>
-__device__ __forceinline__ void explore_k(const ExJob &job, const Planes3 &cur, const Planes3 &prv,
+// WITH_CS: also require equal letter case (mixed-case blocks, soft-mask edges): with the case plane
+// in the comparison, plane equality is byte equality for A/C/G/T in either case.
+template <int K, bool WITH_VA, bool WITH_CS, bool EMIT>
+__device__ __forceinline__ void explore_k(EvStash &stash, uint32_t &any_ev, const Planes3 &cur, const Planes3 &prv,
                                           uint32_t &carry_d, uint32_t m31, int src_lane, uint32_t s_lo,
-                                          uint32_t own, uint32_t slice,
-                                          int64_t p /* slice-relative position of bit 0 */) {
+                                          uint32_t own) {
     const uint32_t lo_k = __funnelshift_l(prv.lo, cur.lo, K);
     const uint32_t hi_k = __funnelshift_l(prv.hi, cur.hi, K);
     uint32_t d_hi = ~((cur.lo ^ lo_k) | (cur.hi ^ hi_k));
     if (WITH_VA) d_hi &= cur.va & __funnelshift_l(prv.va, cur.va, K);
+    if (WITH_CS) d_hi &= ~(cur.cs ^ __funnelshift_l(prv.cs, cur.cs, K));
     // previous lane's D (lane 0: lane 31's D of the previous block)
     const uint32_t d_lo = __shfl_sync(0xFFFFFFFFu, bitsel(m31, carry_d, d_hi), src_lane);
     carry_d = d_hi;
@@ -187,16 +196,13 @@ __device__ __forceinline__ void explore_k(const ExJob &job, const Planes3 &cur, 
     const uint32_t z_lo = (uint32_t)t & d_lo & h_lo;
     const uint32_t z_hi = (uint32_t)(t >> 32) & d_hi & h_hi;
     const uint32_t z_prev = __funnelshift_l(z_lo, z_hi, K); // the chunk before
-    uint32_t ev = (z_hi ^ z_prev) & own; // both are subsets of h_hi
-    while (ev) {                         // rare
-        const int b = __ffs(ev) - 1;
-        ev &= ev - 1;
-        const int64_t q = p + b;
-        const uint64_t j = (uint64_t)((q + 1) / K) - 2;
-        // a run start in a clean block never joins the previous chunk: the two chunks differ as
-        // bytes and have the same letter case, so they differ after upper-casing too
-        emit_event(job, slice, K, j, (z_hi >> b) & 1u, false);
-    }
+    // run boundaries are rare; they are only stashed here (one shared-memory slot per k and lane) and
+    // turned into events after all k of the block, in ONE copy of the emission code: inlining it
+    // after every k made the hot loop three times larger than the instruction cache
+    const uint32_t ev = (z_hi ^ z_prev) & own; // both are subsets of h_hi
+    stash.ev[K - 1][threadIdx.x] = ev;
+    if (ev) stash.z[K - 1][threadIdx.x] = z_hi;
+    any_ev |= ev;
 }
 
 // byte-wise evaluation of this lane's owned chunk ends (special blocks).  x0 = (rel0 mod k) + offset
@@ -223,6 +229,7 @@ __device__ __forceinline__ uint32_t r0_of(const uint4 &v, int i) { // byte i of 
 // KMIN > 0: the k range is a compile-time constant (default 5..12); KMIN == 0: run-time range.
 template <int KMIN, int KMAX>
 __global__ void __launch_bounds__(256, 3) explore_planes_kernel(const ExJob job) {
+    __shared__ EvStash stash;
     const int lane = threadIdx.x & 31;
     const uint32_t m31 = lane == 31 ? 0xFFFFFFFFu : 0u; // look-behind: lane 31 sends its previous-block value
     const int src_lane = (lane + 31) & 31;
@@ -242,12 +249,12 @@ __global__ void __launch_bounds__(256, 3) explore_planes_kernel(const ExJob job)
         const uint4 rq0 = *reinterpret_cast<const uint4 *>(ip->r0);
         const uint8_t *t = job.seq + ((int64_t)scan0 - rel0); // slice start
 
-        Planes3 own_prev = {0u, 0u, 0u};
+        Planes3 own_prev = {0u, 0u, 0u, 0u};
         uint32_t carry_d[kPlaneMaxK];
 #pragma unroll
         for (int i = 0; i < kPlaneMaxK; i++) carry_d[i] = 0;
         bool dirty_prev = false;
-        int case_prev = -1; // -1 unknown, 0 all upper, 1 all lower
+        int case_prev = -1; // -1 unknown (first block), 0 all upper, 1 all lower, 2 mixed
 
         uint32_t w[8];
         const uint8_t *ptr = job.seq + scan0 + (uint32_t)lane * 32u;
@@ -271,9 +278,11 @@ __global__ void __launch_bounds__(256, 3) explore_planes_kernel(const ExJob job)
             cur.lo = P.lo; cur.hi = P.hi;
             cur.va = (P.b0 ^ (P.hi & ~P.lo)) & P.ok & inslice;
 
-            // letter case (ASCII bit 5 = bit 1 of the high nibbles).  Plane equality is byte equality
-            // only under uniform case; a lane that straddles the slice edge is judged on all its 32
-            // bytes, which can only make the block "mixed" more often (slow path, still exact).
+            // Letter case (ASCII bit 5 = bit 1 of the high nibbles).  Without the case plane, plane
+            // equality is byte equality only under uniform case, so a block whose case is mixed, or
+            // differs from the previous block's, compares the case plane as well (WITH_CS variant).  A
+            // lane that straddles the slice edge is judged on all its 32 bytes, which can only make the
+            // block "mixed" more often (still exact).
             const uint32_t all_l = nib.Y[0] & nib.Y[1] & nib.Y[2] & nib.Y[3];
             const uint32_t any_l = nib.Y[0] | nib.Y[1] | nib.Y[2] | nib.Y[3];
             const bool lane_in = inslice != 0;
@@ -281,41 +290,68 @@ __global__ void __launch_bounds__(256, 3) explore_planes_kernel(const ExJob job)
             const bool lane_all_lower = (all_l & 0x22222222u) == 0x22222222u;
             const bool blk_upper = __all_sync(0xFFFFFFFFu, !lane_in || !lane_any_lower);
             const bool blk_lower = __all_sync(0xFFFFFFFFu, !lane_in || lane_all_lower);
-            const bool blk_any = __any_sync(0xFFFFFFFFu, lane_in);
             const int case_now = blk_upper ? 0 : (blk_lower ? 1 : 2);
-            const bool case_bad = case_now == 2 || (case_prev >= 0 && blk_any && case_now != case_prev);
-            const bool dirty_now = __any_sync(0xFFFFFFFFu, (~cur.va & inslice) != 0) || case_bad;
+            const bool need_cs = case_now == 2 || case_now != case_prev; // (the first block of an item too)
+            case_prev = case_now;
+            // bases that are not A/C/G/T (N runs, IUPAC codes): their identity is not in the planes, so
+            // this block and the next one are evaluated byte-wise
+            const bool dirty_now = __any_sync(0xFFFFFFFFu, (~cur.va & inslice) != 0);
             const bool special = dirty_now || dirty_prev;
             dirty_prev = dirty_now;
-            if (blk_any) case_prev = case_now == 2 ? -1 : case_now;
+            // the case plane: extracted when needed, otherwise the constant the block's state implies
+            cur.cs = need_cs ? nibble_plane<1>(nib.Y) : (case_now == 1 ? 0xFFFFFFFFu : 0u);
 
             Planes3 prv;
             prv.lo = lane_lookbehind(cur.lo, own_prev.lo, lane);
             prv.hi = lane_lookbehind(cur.hi, own_prev.hi, lane);
             prv.va = lane_lookbehind(cur.va, own_prev.va, lane);
+            prv.cs = need_cs ? lane_lookbehind(cur.cs, own_prev.cs, lane) : 0u;
             own_prev = cur;
             const int64_t p = rel0 + prel;
             const uint32_t xoff = (uint32_t)prel; // < 2^15
-#define TIDK_EXK(K, VA, EM)                                                                       \
+#define TIDK_EXK(K, VA, CS, EM)                                                                   \
     if ((KMIN > 0) ? (K >= KMIN && K <= KMAX) : (job.kmin <= K && K <= job.kmax)) {              \
-        explore_k<K, VA, EM>(job, cur, prv, carry_d[K - 1], m31, src_lane,                      \
-                             (uint32_t)(K - 1) - (r0_of(rq0, K - 1) + xoff + 32u * (K - 1)) % K, own, slice, p); \
+        explore_k<K, VA, CS, EM>(stash, any_ev, cur, prv, carry_d[K - 1], m31, src_lane,        \
+                             (uint32_t)(K - 1) - (r0_of(rq0, K - 1) + xoff + 32u * (K - 1)) % K, own);   \
     }
-#define TIDK_EXALL(VA, EM)                                                                        \
-    TIDK_EXK(1, VA, EM) TIDK_EXK(2, VA, EM) TIDK_EXK(3, VA, EM) TIDK_EXK(4, VA, EM)               \
-    TIDK_EXK(5, VA, EM) TIDK_EXK(6, VA, EM) TIDK_EXK(7, VA, EM) TIDK_EXK(8, VA, EM)               \
-    TIDK_EXK(9, VA, EM) TIDK_EXK(10, VA, EM) TIDK_EXK(11, VA, EM) TIDK_EXK(12, VA, EM)            \
-    TIDK_EXK(13, VA, EM) TIDK_EXK(14, VA, EM) TIDK_EXK(15, VA, EM) TIDK_EXK(16, VA, EM)
-            // three straight-line variants, chosen per block (warp-uniform):
-            //   interior of a clean stretch (every base of both words valid) -> no va plane
-            //   clean block at a slice edge                                  -> va plane
-            //   special block                                                -> carries only + byte-wise
+#define TIDK_EXALL(VA, CS, EM)                                                                    \
+    TIDK_EXK(1, VA, CS, EM) TIDK_EXK(2, VA, CS, EM) TIDK_EXK(3, VA, CS, EM) TIDK_EXK(4, VA, CS, EM)     \
+    TIDK_EXK(5, VA, CS, EM) TIDK_EXK(6, VA, CS, EM) TIDK_EXK(7, VA, CS, EM) TIDK_EXK(8, VA, CS, EM)     \
+    TIDK_EXK(9, VA, CS, EM) TIDK_EXK(10, VA, CS, EM) TIDK_EXK(11, VA, CS, EM) TIDK_EXK(12, VA, CS, EM)  \
+    TIDK_EXK(13, VA, CS, EM) TIDK_EXK(14, VA, CS, EM) TIDK_EXK(15, VA, CS, EM) TIDK_EXK(16, VA, CS, EM)
+            // four straight-line variants, chosen per block (warp-uniform):
+            //   interior of a clean stretch (every base of both words valid, uniform case) -> lo/hi only
+            //   clean block at a slice edge                                                -> + va plane
+            //   mixed letter case / case change                                            -> + va + case plane
+            //   special block (non-ACGT bases)                                             -> carries only + byte-wise
             const bool all_valid = __all_sync(0xFFFFFFFFu, (cur.va & prv.va) == 0xFFFFFFFFu);
-            if (!special && all_valid) { TIDK_EXALL(false, true) }
-            else if (!special) { TIDK_EXALL(true, true) }
-            else { TIDK_EXALL(true, false) }
+            uint32_t any_ev = 0;
+            if (special) { TIDK_EXALL(true, false, false) }
+            else if (need_cs) { TIDK_EXALL(true, true, true) }
+            else if (all_valid) { TIDK_EXALL(false, false, true) }
+            else { TIDK_EXALL(true, false, true) }
 #undef TIDK_EXALL
 #undef TIDK_EXK
+            if (any_ev) { // rare: this lane found run boundaries in this block
+                const uint32_t k0 = KMIN > 0 ? KMIN : job.kmin, k1 = KMIN > 0 ? KMAX : job.kmax;
+                for (uint32_t k = k0; k <= k1; k++) {
+                    uint32_t ev = stash.ev[k - 1][threadIdx.x];
+                    if (!ev) continue;
+                    const uint32_t z = stash.z[k - 1][threadIdx.x];
+                    while (ev) {
+                        const int b = __ffs(ev) - 1;
+                        ev &= ev - 1;
+                        const uint64_t q1 = (uint64_t)(p + b) + 1; // chunk end + 1, a multiple of k
+                        const uint64_t j = (q1 >> 32 ? q1 / k : (uint64_t)((uint32_t)q1 / k)) - 2;
+                        // a run start in a uniform-case block never joins the previous chunk (they differ
+                        // as bytes and share the case, so they differ after upper-casing too); with mixed
+                        // case the two chunks are compared after upper-casing (explore.rs:212 vs :324)
+                        const bool start = (z >> b) & 1u;
+                        const bool joins = need_cs && start && j > 0 && chunks_equal_upper(t, (int)k, j);
+                        emit_event(job, slice, k, j, start, joins);
+                    }
+                }
+            }
             if (special) { // exact byte-wise evaluation of this block's owned chunk ends
                 const uint32_t k0 = KMIN > 0 ? KMIN : job.kmin, k1 = KMIN > 0 ? KMAX : job.kmax;
                 for (uint32_t k = k0; k <= k1; k++)
