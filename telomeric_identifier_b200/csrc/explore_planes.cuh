@@ -155,8 +155,10 @@ __host__ __device__ constexpr uint64_t periodic_mask64() { // bits at multiples 
 }
 
 struct Planes3 {
-    uint32_t lo, hi, va;
-    uint32_t cs; // letter case (ASCII bit 5); only filled in when the block needs it
+    uint32_t lo, hi;
+    uint32_t va; // base is one of A C G T N (either case) and inside the slice
+    uint32_t cs; // letter case (ASCII bit 5); extracted only when the block needs it
+    uint32_t nn; // base is N / n (shares lo/hi with G, so it needs its own plane)
 };
 
 // One k for one 32-base word.  WITH_VA: honour the validity plane (edge blocks); interior blocks of
@@ -172,9 +174,10 @@ struct Planes3 {
 // s_lo is the bit position (0..K-1) of the first chunk end in the PREVIOUS word: the phase of that
 // word's first base is (rel0 + offset - 32) mod K, recomputed per block with a multiply-shift on
 // the fma pipe (keeping it in a register per k costs a CTA of occupancy).
-// WITH_CS: also require equal letter case (mixed-case blocks, soft-mask edges): with the case plane
-// in the comparison, plane equality is byte equality for A/C/G/T in either case.
-template <int K, bool WITH_VA, bool WITH_CS, bool EMIT>
+// FULL: also require equal letter case and equal N-ness (mixed-case blocks, soft-mask edges, N runs):
+// with the case and N planes in the comparison, plane equality is byte equality for A/C/G/T/N in either
+// case, so only blocks with other bytes (IUPAC codes, gaps) need the byte-wise evaluation.
+template <int K, bool WITH_VA, bool FULL, bool EMIT>
 __device__ __forceinline__ void explore_k(EvStash &stash, uint32_t &any_ev, const Planes3 &cur, const Planes3 &prv,
                                           uint32_t &carry_d, uint32_t m31, int src_lane, uint32_t s_lo,
                                           uint32_t own) {
@@ -182,7 +185,7 @@ __device__ __forceinline__ void explore_k(EvStash &stash, uint32_t &any_ev, cons
     const uint32_t hi_k = __funnelshift_l(prv.hi, cur.hi, K);
     uint32_t d_hi = ~((cur.lo ^ lo_k) | (cur.hi ^ hi_k));
     if (WITH_VA) d_hi &= cur.va & __funnelshift_l(prv.va, cur.va, K);
-    if (WITH_CS) d_hi &= ~(cur.cs ^ __funnelshift_l(prv.cs, cur.cs, K));
+    if (FULL) d_hi &= ~((cur.cs ^ __funnelshift_l(prv.cs, cur.cs, K)) | (cur.nn ^ __funnelshift_l(prv.nn, cur.nn, K)));
     // previous lane's D (lane 0: lane 31's D of the previous block)
     const uint32_t d_lo = __shfl_sync(0xFFFFFFFFu, bitsel(m31, carry_d, d_hi), src_lane);
     carry_d = d_hi;
@@ -249,7 +252,8 @@ __global__ void __launch_bounds__(256, 3) explore_planes_kernel(const ExJob job)
         const uint4 rq0 = *reinterpret_cast<const uint4 *>(ip->r0);
         const uint8_t *t = job.seq + ((int64_t)scan0 - rel0); // slice start
 
-        Planes3 own_prev = {0u, 0u, 0u, 0u};
+        Planes3 own_prev = {0u, 0u, 0u, 0u, 0u};
+        bool had_n_prev = false;
         uint32_t carry_d[kPlaneMaxK];
 #pragma unroll
         for (int i = 0; i < kPlaneMaxK; i++) carry_d[i] = 0;
@@ -276,7 +280,8 @@ __global__ void __launch_bounds__(256, 3) explore_planes_kernel(const ExJob job)
             nonascii |= na & inslice;
             Planes3 cur;
             cur.lo = P.lo; cur.hi = P.hi;
-            cur.va = (P.b0 ^ (P.hi & ~P.lo)) & P.ok & inslice;
+            cur.nn = P.isn & inslice;
+            cur.va = ((P.b0 ^ (P.hi & ~P.lo)) & P.ok & inslice) | cur.nn;
 
             // Letter case (ASCII bit 5 = bit 1 of the high nibbles).  Without the case plane, plane
             // equality is byte equality only under uniform case, so a block whose case is mixed, or
@@ -291,10 +296,12 @@ __global__ void __launch_bounds__(256, 3) explore_planes_kernel(const ExJob job)
             const bool blk_upper = __all_sync(0xFFFFFFFFu, !lane_in || !lane_any_lower);
             const bool blk_lower = __all_sync(0xFFFFFFFFu, !lane_in || lane_all_lower);
             const int case_now = blk_upper ? 0 : (blk_lower ? 1 : 2);
-            const bool need_cs = case_now == 2 || case_now != case_prev; // (the first block of an item too)
+            const bool had_n = P.exact && __any_sync(0xFFFFFFFFu, cur.nn != 0);
+            const bool need_cs = case_now == 2 || case_now != case_prev || had_n || had_n_prev; // FULL variant
             case_prev = case_now;
-            // bases that are not A/C/G/T (N runs, IUPAC codes): their identity is not in the planes, so
-            // this block and the next one are evaluated byte-wise
+            had_n_prev = had_n;
+            // bytes other than A/C/G/T/N (IUPAC codes, gaps, ...): their identity is not in the planes,
+            // so this block and the next one are evaluated byte-wise
             const bool dirty_now = __any_sync(0xFFFFFFFFu, (~cur.va & inslice) != 0);
             const bool special = dirty_now || dirty_prev;
             dirty_prev = dirty_now;
@@ -306,6 +313,7 @@ __global__ void __launch_bounds__(256, 3) explore_planes_kernel(const ExJob job)
             prv.hi = lane_lookbehind(cur.hi, own_prev.hi, lane);
             prv.va = lane_lookbehind(cur.va, own_prev.va, lane);
             prv.cs = need_cs ? lane_lookbehind(cur.cs, own_prev.cs, lane) : 0u;
+            prv.nn = need_cs ? lane_lookbehind(cur.nn, own_prev.nn, lane) : 0u;
             own_prev = cur;
             const int64_t p = rel0 + prel;
             const uint32_t xoff = (uint32_t)prel; // < 2^15
@@ -322,8 +330,8 @@ __global__ void __launch_bounds__(256, 3) explore_planes_kernel(const ExJob job)
             // four straight-line variants, chosen per block (warp-uniform):
             //   interior of a clean stretch (every base of both words valid, uniform case) -> lo/hi only
             //   clean block at a slice edge                                                -> + va plane
-            //   mixed letter case / case change                                            -> + va + case plane
-            //   special block (non-ACGT bases)                                             -> carries only + byte-wise
+            //   mixed letter case / case change / N present                                -> + va + case + N planes
+            //   special block (bytes other than A C G T N)                                 -> carries only + byte-wise
             const bool all_valid = __all_sync(0xFFFFFFFFu, (cur.va & prv.va) == 0xFFFFFFFFu);
             uint32_t any_ev = 0;
             if (special) { TIDK_EXALL(true, false, false) }

@@ -98,7 +98,8 @@ __device__ __forceinline__ Nibbles to_nibbles(const uint32_t (&w)[8]) {
 
 struct Planes {
     uint32_t lo, hi, b0, ok;
-    bool exact; // warp-uniform: ok is not all ones
+    uint32_t isn; // exact path only: byte is 'N' or 'n' (0 on the fast path, where there is none)
+    bool exact;   // warp-uniform: ok is not all ones
 };
 
 // nonascii is OR-ed with a non-zero value if any byte >= 0x80 (exact path only:
@@ -117,6 +118,7 @@ __device__ __forceinline__ Planes extract_planes(const Nibbles &n, uint32_t &non
     P.hi = nibble_plane<2>(n.X);
     P.b0 = nibble_plane<0>(n.X);
     P.ok = 0xFFFFFFFFu;
+    P.isn = 0u;
     P.exact = __any_sync(0xFFFFFFFFu, bad != 0);
     if (P.exact) {
         uint32_t b3 = nibble_plane<3>(n.X);
@@ -125,6 +127,7 @@ __device__ __forceinline__ Planes extract_planes(const Nibbles &n, uint32_t &non
         uint32_t b7 = nibble_plane<3>(n.Y);
         nonascii |= b7;
         P.ok = ~b7 & b6 & ~b3 & (b4 ^ P.b0);
+        P.isn = ~b7 & b6 & b3 & ~b4 & P.hi & P.lo & ~P.b0; // 0x4E / 0x6E (explore treats N as a fifth letter)
     }
     return P;
 }

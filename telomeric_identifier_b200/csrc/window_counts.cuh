@@ -298,7 +298,7 @@ struct PackedSource {
         Planes P;
         P.lo = c.lo; P.hi = c.hi;
         P.b0 = c.va ^ (c.hi & ~c.lo); // the matchers' validity term b0 ^ (hi & ~lo) then equals va
-        P.ok = 0xFFFFFFFFu; P.exact = false;
+        P.ok = 0xFFFFFFFFu; P.isn = 0u; P.exact = false;
         return P;
     }
 };
