@@ -248,6 +248,27 @@ def main():
     h2d_gbs = bases * 3 / (ev[0].elapsed_time(ev[1]) * 1e-3) / 1e9
     del dst
 
+    # the other half of the hot path (explore) on the same resident genome:
+    # C3 (--distance 0.01, 60 slices) and --distance 0.5 (every base scanned once, 8 k's per pass)
+    explore = None
+    if world == 1:
+        explore = {}
+        lens = (off[1:] - off[:-1]).astype(np.float64)
+        for name, d in (("c3_distance_0.01", 0.01), ("distance_0.5", 0.5)):
+            scanned = int(sum(2 * int(np.ceil(l * d)) for l in lens.tolist()))
+            best = None
+            for _ in range(5):
+                t2 = time.perf_counter()
+                runs = ctx.explore_runs_resident(batch, d, 5, 12, 100)
+                wall = time.perf_counter() - t2
+                sm, pm = ctx.explore_timings()
+                if best is None or sm < best[0]:
+                    best = (sm, pm, wall)
+            explore[name] = {"scanned_bases": scanned, "scan_kernel_ms": best[0], "post_ms": best[1],
+                             "call_wall_ms": best[2] * 1e3, "runs": int(runs.size),
+                             "scan_gbases_per_s": scanned / (best[0] * 1e-3) / 1e9,
+                             "kernel": "explore_planes_kernel<5,12>", "k_range": [5, 12], "threshold": 100}
+
     if dist is not None:
         t = torch.tensor([dt, dt_e2e, kernel_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -288,6 +309,10 @@ def main():
                         "h2d_bound_gbs_rank0": h2d_gbs,
                         "frac_of_h2d_bound_rank0": (bases * e2e_steps / dt_e2e / 1e9) / h2d_gbs},
                 "gpu_launches": launches, "roofline": roof, "cpu_baseline": cb}
+        if explore is not None:
+            for v in explore.values():
+                v["frac_of_hbm_peak"] = v["scan_gbases_per_s"] / peak
+            line["explore"] = explore
         print(json.dumps(line))
     ctx.close()
     if dist is not None:

@@ -199,7 +199,10 @@ class Context:
         if cached is None or cached[0] != key:  # the ctypes argument arrays are rebuilt only when the queries change
             self._qcache = cached = (key, _qargs(queries))
         qa, ql, nq = cached[1]
-        total = int(n_windows(batch.offsets, window).sum()) * nq if window > 0 else 0
+        nwc = batch.__dict__.setdefault("_nwin", {})  # windows per batch, computed once per window size
+        if window not in nwc:
+            nwc[window] = int(n_windows(batch.offsets, window).sum()) if window > 0 else 0
+        total = nwc[window] * nq
         if out is None:
             fwd = np.zeros(max(total, 1), dtype=np.uint64)
             rev = np.zeros(max(total, 1), dtype=np.uint64)

@@ -104,6 +104,7 @@ struct ExJob {
     unsigned long long *work_counter;
     uint32_t *err_flags;
     uint32_t packed; // events are 64-bit keys (pack_event) instead of RunEvent structs
+    uint32_t one;    // the constant 1, opaque to the compiler: multiplier of the mad.wide that does a 64-bit add on the fma pipe
 };
 
 // Events are appended with one atomicAdd each on a global counter (the compiler aggregates the lanes
@@ -147,13 +148,6 @@ struct EvStash {
     uint32_t z[kPlaneMaxK][256];
 };
 
-template <int K>
-__host__ __device__ constexpr uint64_t periodic_mask64() { // bits at multiples of K below 64
-    uint64_t m = 0;
-    for (int b = 0; b < 64; b += K) m |= 1ull << b;
-    return m;
-}
-
 struct Planes3 {
     uint32_t lo, hi;
     uint32_t va; // base is one of A C G T N (either case) and inside the slice
@@ -161,50 +155,94 @@ struct Planes3 {
     uint32_t nn; // base is N / n (shares lo/hi with G, so it needs its own plane)
 };
 
+// Chunk-end masks.  htab[K-1][s] = ~H for the (previous | current) 64-bit pair when the first chunk end
+// of the previous word sits at bit s: H has a bit every K positions from s on (the chunk ends).  Filled
+// once per CTA; one LDS.64 per k and block replaces two shifts of a 64-bit constant.
+struct HTable {
+    uint2 nh[kPlaneMaxK][16];
+};
+
+__device__ __forceinline__ void fill_htable(HTable &tab) {
+    for (int e = threadIdx.x; e < kPlaneMaxK * 16; e += blockDim.x) {
+        const int k = e / 16 + 1, sft = e % 16;
+        uint64_t per = 0;
+        for (int b = 0; b < 64; b += k) per |= 1ull << b;
+        const uint64_t nh = ~(per << sft);
+        tab.nh[k - 1][sft] = make_uint2((uint32_t)nh, (uint32_t)(nh >> 32));
+    }
+}
+
+// Per-lane chunk phases, four k per register, one byte each: 8 * s_k, where s_k (0..k-1) is the bit of the
+// first chunk end in the PREVIOUS word.  A block later the phase is (s_k - 1024) mod k; the update runs on
+// all four bytes at once (no byte overflows: 16k - 16 + 128 - 8k < 256 for k <= 16).
+template <int KBASE, int REG>
+struct PhaseConst {
+    __host__ __device__ static constexpr uint32_t byte_of(int k, int what) { // what 0: 8 * ((k - 1024 % k) % k), 1: 0x80 - 8k, 2: 8k
+        return k > kPlaneMaxK ? 0u : what == 0 ? 8u * (uint32_t)((k - 1024 % k) % k) : what == 1 ? 0x80u - 8u * (uint32_t)k : 8u * (uint32_t)k;
+    }
+    __host__ __device__ static constexpr uint32_t word(int what) {
+        return byte_of(KBASE + 4 * REG, what) | byte_of(KBASE + 4 * REG + 1, what) << 8 |
+               byte_of(KBASE + 4 * REG + 2, what) << 16 | byte_of(KBASE + 4 * REG + 3, what) << 24;
+    }
+};
+
+template <int KBASE, int REG>
+__device__ __forceinline__ uint32_t phase_step(uint32_t p) {
+    constexpr uint32_t INC = PhaseConst<KBASE, REG>::word(0), CMP = PhaseConst<KBASE, REG>::word(1),
+                       MOD = PhaseConst<KBASE, REG>::word(2);
+    p += INC;
+    const uint32_t ge = ((p + CMP) >> 7) & 0x01010101u; // byte >= 8k
+    return p - ((ge * 0xFFu) & MOD);
+}
+
 // One k for one 32-base word.  WITH_VA: honour the validity plane (edge blocks); interior blocks of
 // a clean stretch have va == all ones for both words and skip it.
 //
 // "All K positions of an aligned chunk match K behind" is an all-ones-field test on D over the
-// (previous | current) 64-bit pair, fields = chunks, H = top bit of each field (the chunk ends):
-//     Z = ((D | H) + H + 1) & D & H
-// (equivalently ~((~D & ~H) + ~H) & D & H): inside a field the +1 ripples through the low K-1 bits
-// of D exactly when they are all ones and stops at the field top because H is added there, so no
-// carry crosses a field.  Two LOP3, one 64-bit add, two LOP3 -- regardless of K.
+// (previous | current) 64-bit pair, fields = chunks, H = top bit of each field (the chunk ends).  With
+// nD = ~D (the MISMATCH plane, which is what the XORs produce) and nH = ~H:
+//     Z = ~((nD & nH) + nH) & D & H  =  ~(sum | nD | nH)
+// Inside a field the addend nH is all ones below the top bit, so the sum carries into the top bit exactly
+// when some low position mismatches; both addends are 0 at the top bit, so no carry leaves a field.  Two
+// LOP3, one 64-bit add, two LOP3 -- regardless of K.  The 64-bit add is issued as mad.wide.u32
+// (low word * 1 + nH) plus one 32-bit add: it runs on the fma pipe, which this kernel leaves idle, instead
+// of an add / compare / select chain on the saturated alu pipe.
 //
-// s_lo is the bit position (0..K-1) of the first chunk end in the PREVIOUS word: the phase of that
-// word's first base is (rel0 + offset - 32) mod K, recomputed per block with a multiply-shift on
-// the fma pipe (keeping it in a register per k costs a CTA of occupancy).
+// s8 = 8 * s, s = bit position (0..K-1) of the first chunk end in the PREVIOUS word (see PhaseConst).
 // FULL: also require equal letter case and equal N-ness (mixed-case blocks, soft-mask edges, N runs):
 // with the case and N planes in the comparison, plane equality is byte equality for A/C/G/T/N in either
 // case, so only blocks with other bytes (IUPAC codes, gaps) need the byte-wise evaluation.
 template <int K, bool WITH_VA, bool FULL, bool EMIT>
-__device__ __forceinline__ void explore_k(EvStash &stash, uint32_t &any_ev, const Planes3 &cur, const Planes3 &prv,
-                                          uint32_t &carry_d, uint32_t m31, int src_lane, uint32_t s_lo,
-                                          uint32_t own) {
+__device__ __forceinline__ void explore_k(EvStash &stash, const HTable &htab, uint32_t one, uint32_t &any_ev,
+                                          const Planes3 &cur, const Planes3 &prv, uint32_t &carry_nd, uint32_t m31,
+                                          int src_lane, uint32_t s8, uint32_t own) {
     const uint32_t lo_k = __funnelshift_l(prv.lo, cur.lo, K);
     const uint32_t hi_k = __funnelshift_l(prv.hi, cur.hi, K);
-    uint32_t d_hi = ~((cur.lo ^ lo_k) | (cur.hi ^ hi_k));
-    if (WITH_VA) d_hi &= cur.va & __funnelshift_l(prv.va, cur.va, K);
-    if (FULL) d_hi &= ~((cur.cs ^ __funnelshift_l(prv.cs, cur.cs, K)) | (cur.nn ^ __funnelshift_l(prv.nn, cur.nn, K)));
-    // previous lane's D (lane 0: lane 31's D of the previous block)
-    const uint32_t d_lo = __shfl_sync(0xFFFFFFFFu, bitsel(m31, carry_d, d_hi), src_lane);
-    carry_d = d_hi;
+    uint32_t nd_hi = (cur.lo ^ lo_k) | (cur.hi ^ hi_k); // mismatch plane of this word
+    if (WITH_VA) nd_hi |= ~(cur.va & __funnelshift_l(prv.va, cur.va, K));
+    if (FULL) nd_hi |= (cur.cs ^ __funnelshift_l(prv.cs, cur.cs, K)) | (cur.nn ^ __funnelshift_l(prv.nn, cur.nn, K));
+    // previous lane's mismatch plane (lane 0: lane 31's of the previous block)
+    const uint32_t nd_lo = __shfl_sync(0xFFFFFFFFu, bitsel(m31, carry_nd, nd_hi), src_lane);
+    carry_nd = nd_hi;
     if (!EMIT) return; // special block: only the carries are kept consistent
-    constexpr uint64_t PER = periodic_mask64<K>();
-    const uint32_t h_lo = (uint32_t)PER << s_lo;
-    const uint32_t h_hi = __funnelshift_l((uint32_t)PER, (uint32_t)(PER >> 32), s_lo);
-    const uint64_t u = ((uint64_t)(d_hi | h_hi) << 32) | (d_lo | h_lo);
-    const uint64_t h = ((uint64_t)h_hi << 32) | h_lo;
-    const uint64_t t = u + h + 1ull;
-    const uint32_t z_lo = (uint32_t)t & d_lo & h_lo;
-    const uint32_t z_hi = (uint32_t)(t >> 32) & d_hi & h_hi;
-    const uint32_t z_prev = __funnelshift_l(z_lo, z_hi, K); // the chunk before
+    const unsigned long long nh = *reinterpret_cast<const unsigned long long *>(reinterpret_cast<const char *>(&htab.nh[K - 1][0]) + s8);
+    const uint32_t nh_lo = (uint32_t)nh, nh_hi = (uint32_t)(nh >> 32);
+    // high word first (a plain 32-bit add; a carry out of bit 63 is dropped either way), then the low word
+    // and its carry in one mad.wide
+    const unsigned long long addend = ((unsigned long long)(nh_hi + (nd_hi & nh_hi)) << 32) | nh_lo;
+    unsigned long long sum;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(sum) : "r"(nd_lo & nh_lo), "r"(one), "l"(addend));
+    const uint32_t sum_hi = (uint32_t)(sum >> 32);
+    // x = ~Z; a funnel shift commutes with the complement, so the boundary test needs no NOT
+    const uint32_t x_lo = (uint32_t)sum | nd_lo | nh_lo;
+    const uint32_t x_hi = sum_hi | nd_hi | nh_hi;
+    const uint32_t x_prev = __funnelshift_l(x_lo, x_hi, K); // the chunk before
     // run boundaries are rare; they are only stashed here (one shared-memory slot per k and lane) and
     // turned into events after all k of the block, in ONE copy of the emission code: inlining it
     // after every k made the hot loop three times larger than the instruction cache
-    const uint32_t ev = (z_hi ^ z_prev) & own; // both are subsets of h_hi
+    const uint32_t ev = (x_hi ^ x_prev) & own; // x is 1 off the chunk ends in both, so only chunk ends survive
     stash.ev[K - 1][threadIdx.x] = ev;
-    if (ev) stash.z[K - 1][threadIdx.x] = z_hi;
+    if (ev) stash.z[K - 1][threadIdx.x] = ~x_hi;
     any_ev |= ev;
 }
 
@@ -229,10 +267,32 @@ __device__ __forceinline__ uint32_t r0_of(const uint4 &v, int i) { // byte i of 
     return (wsel >> (8 * (i & 3))) & 0xFFu;
 }
 
+template <int KBASE, int NREG, int G = 0>
+__device__ __forceinline__ void phase_step_all(uint32_t (&ph)[NREG]) {
+    if constexpr (G < NREG) {
+        ph[G] = phase_step<KBASE, G>(ph[G]);
+        phase_step_all<KBASE, NREG, G + 1>(ph);
+    }
+}
+
+// 8 * s_K out of the packed phase registers (one PRMT); K outside the registers' range never runs
+template <int KBASE, int NREG, int K>
+__device__ __forceinline__ uint32_t phase_byte(const uint32_t (&ph)[NREG]) {
+    if constexpr (K >= KBASE && K < KBASE + 4 * NREG)
+        return __byte_perm(ph[(K - KBASE) / 4], 0u, 0x4440u + (uint32_t)((K - KBASE) % 4));
+    else
+        return 0u;
+}
+
 // KMIN > 0: the k range is a compile-time constant (default 5..12); KMIN == 0: run-time range.
 template <int KMIN, int KMAX>
 __global__ void __launch_bounds__(256, 3) explore_planes_kernel(const ExJob job) {
     __shared__ EvStash stash;
+    __shared__ HTable htab;
+    constexpr int KBASE = KMIN > 0 ? KMIN : 1;                         // first k of the packed phase registers
+    constexpr int NREG = KMIN > 0 ? (KMAX - KMIN) / 4 + 1 : kPlaneMaxK / 4;
+    fill_htable(htab);
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const uint32_t m31 = lane == 31 ? 0xFFFFFFFFu : 0u; // look-behind: lane 31 sends its previous-block value
     const int src_lane = (lane + 31) & 31;
@@ -254,9 +314,23 @@ __global__ void __launch_bounds__(256, 3) explore_planes_kernel(const ExJob job)
 
         Planes3 own_prev = {0u, 0u, 0u, 0u, 0u};
         bool had_n_prev = false;
-        uint32_t carry_d[kPlaneMaxK];
+        uint32_t carry_nd[kPlaneMaxK]; // mismatch planes of lane 31's word of the previous block
 #pragma unroll
-        for (int i = 0; i < kPlaneMaxK; i++) carry_d[i] = 0;
+        for (int i = 0; i < kPlaneMaxK; i++) carry_nd[i] = 0xFFFFFFFFu;
+        // chunk phases of block 0 for this lane: s_k = (k-1) - (rel0 + 32 * lane - 32) mod k, kept as 8 * s_k
+        uint32_t ph[NREG];
+#pragma unroll
+        for (int g = 0; g < NREG; g++) {
+            ph[g] = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const int k = KBASE + 4 * g + b;
+                if (k <= kPlaneMaxK) {
+                    const uint32_t x = (r0_of(rq0, k - 1) + (uint32_t)lane * 32u + 32u * (uint32_t)(k - 1)) % (uint32_t)k;
+                    ph[g] |= (8u * ((uint32_t)(k - 1) - x)) << (8 * b);
+                }
+            }
+        }
         bool dirty_prev = false;
         int case_prev = -1; // -1 unknown (first block), 0 all upper, 1 all lower, 2 mixed
 
@@ -319,8 +393,8 @@ __global__ void __launch_bounds__(256, 3) explore_planes_kernel(const ExJob job)
             const uint32_t xoff = (uint32_t)prel; // < 2^15
 #define TIDK_EXK(K, VA, CS, EM)                                                                   \
     if ((KMIN > 0) ? (K >= KMIN && K <= KMAX) : (job.kmin <= K && K <= job.kmax)) {              \
-        explore_k<K, VA, CS, EM>(stash, any_ev, cur, prv, carry_d[K - 1], m31, src_lane,        \
-                             (uint32_t)(K - 1) - (r0_of(rq0, K - 1) + xoff + 32u * (K - 1)) % K, own);   \
+        explore_k<K, VA, CS, EM>(stash, htab, job.one, any_ev, cur, prv, carry_nd[K - 1], m31, src_lane,  \
+                                 phase_byte<KBASE, NREG, K>(ph), own);                             \
     }
 #define TIDK_EXALL(VA, CS, EM)                                                                    \
     TIDK_EXK(1, VA, CS, EM) TIDK_EXK(2, VA, CS, EM) TIDK_EXK(3, VA, CS, EM) TIDK_EXK(4, VA, CS, EM)     \
@@ -365,6 +439,7 @@ __global__ void __launch_bounds__(256, 3) explore_planes_kernel(const ExJob job)
                 for (uint32_t k = k0; k <= k1; k++)
                     explore_k_bytes(job, (int)k, r0_of(rq0, (int)k - 1) + xoff, own, slice, t, m, p);
             }
+            phase_step_all<KBASE, NREG>(ph); // the next block lies 1024 bases further on
         }
     }
     if (__any_sync(0xFFFFFFFFu, nonascii != 0) && lane == 0) atomicOr(job.err_flags, 1u);

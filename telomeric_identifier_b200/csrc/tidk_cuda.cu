@@ -59,7 +59,8 @@ struct tidk_ctx {
     std::vector<PackLane> pack_lanes;
     uint32_t counter_flip = 0;      // which of the two queue counters the next launch uses
     bool counters_dirty = false;    // a call failed between taking a counter and finishing: re-zero both
-    uint32_t *h_flags = nullptr;    // pinned: error flags come back with an async copy
+    uint32_t *h_flags = nullptr;    // pinned + mapped: the window kernels store the (rare) error flag straight into host memory
+    uint32_t *d_flags = nullptr;    // device view of h_flags
     ExploreScratch ex;
     uint64_t next_buf_id = 1;
     // work items cached for (sequence batch, window, query count): several clades or output
@@ -435,7 +436,11 @@ static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint3
         CU(ctx, cudaMemsetAsync(ctx->misc.p, 0, 256, ctx->stream));
         ctx->counter_flip = 0;
     }
-    if (!ctx->h_flags) CU(ctx, cudaHostAlloc((void **)&ctx->h_flags, 64, cudaHostAllocDefault));
+    if (!ctx->h_flags) {
+        CU(ctx, cudaHostAlloc((void **)&ctx->h_flags, 64, cudaHostAllocMapped));
+        memset(ctx->h_flags, 0, 64);
+        CU(ctx, cudaHostGetDevicePointer((void **)&ctx->d_flags, ctx->h_flags, 0));
+    }
     if (ctx->counters_dirty) {
         CU(ctx, cudaMemsetAsync(ctx->misc.p, 0, 256, ctx->stream));
         ctx->counter_flip = 0;
@@ -466,7 +471,7 @@ static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint3
     job.items = (const ItemDesc *)ctx->items.p;
     job.out_fwd = d_fwd;
     job.out_rev = d_rev;
-    job.err_flags = (uint32_t *)((char *)ctx->misc.p + 128);
+    job.err_flags = ctx->d_flags; // written only when a byte >= 0x80 is seen: no flag copy per call
     job.n_items = n_items;
 
     // split queries: plane kernels take A/C/G/T-only patterns up to 32 bases
@@ -580,11 +585,10 @@ static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint3
         CU(ctx, cudaMemcpyAsync(out_fwd, d_fwd, n_out * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CU(ctx, cudaMemcpyAsync(out_rev, d_rev, n_out * 8, cudaMemcpyDeviceToHost, ctx->stream));
     }
-    CU(ctx, cudaMemcpyAsync(ctx->h_flags, job.err_flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->counters_dirty = false;
-    const uint32_t h_err = ctx->h_flags[0];
-    if (h_err) CU(ctx, cudaMemsetAsync(job.err_flags, 0, 4, ctx->stream)); // flags are sticky: clear after reporting
+    const uint32_t h_err = *(volatile uint32_t *)ctx->h_flags;
+    if (h_err) ctx->h_flags[0] = 0; // flags are sticky: clear after reporting (the stream is idle here)
     if (kernel_ms) CU(ctx, cudaEventElapsedTime(kernel_ms, ctx->ev0, ctx->ev1));
     if (kernel_launches) *kernel_launches = launches;
     if (h_err & 1u)

@@ -73,9 +73,10 @@ __global__ void __launch_bounds__(256) window_items_kernel(const PrepJob job) {
     d.flags = job.segs_per_window > 1 ? 1 : 0;
     if (sbeg < end) {
         const uint64_t send = (sbeg + kSegBytes < end) ? sbeg + kSegBytes : end;
-        // later segments start one block early so that the look-behind planes are real
+        // Later segments start one lane word (32 bases) early: the look-behind is at most 31 bases, the
+        // early word lies before the counted range, and lane 1 takes its look-behind from lane 0.
         uint64_t scan0 = sbeg & ~31ull;
-        if (seg > 0) scan0 -= 1024;
+        if (seg > 0) scan0 -= 32;
         d.scan0 = scan0;
         d.nblk = (uint16_t)((send - scan0 + 1023) >> 10);
         d.vbeg = (uint16_t)(beg > scan0 ? beg - scan0 : 0);
@@ -97,7 +98,7 @@ struct WindowJob {
     uint64_t *out_rev;
     unsigned long long *work_counter; // zero at launch
     unsigned long long *next_counter; // zeroed by this launch for the next one (no memset per call)
-    uint32_t *err_flags;     // bit 0: non-ASCII byte seen
+    uint32_t *err_flags;     // mapped host word; set to 1 when a non-ASCII byte is seen
     uint64_t n_items;
     uint32_t q0;             // first query index of this launch
     uint32_t nq;             // queries in this launch
@@ -334,7 +335,6 @@ window_counts_kernel(const WindowJob job, const typename M::Params mp) {
         const int cbeg = (int)(db.z & 0xFFFFu), cend = (int)(db.z >> 16);
         const uint32_t nblk = db.w & 0xFFFFu;
         const bool multi = (db.w >> 16) & 1u;
-        const uint32_t nlead = multi ? 2u : 1u; // leading blocks that can hold a window / segment start
 
         // look ahead: descriptor of the next item, ticket of the one after
         const bool have_next = item_next < job.n_items;
@@ -350,7 +350,7 @@ window_counts_kernel(const WindowJob job, const typename M::Params mp) {
         M::reset(carry);
 
         uint64_t off = scan0;
-        // One 1 KiB block.  EDGE blocks (the first one, the second one of a later segment, the last one)
+        // One 1 KiB block.  EDGE blocks (the first and the last one)
         // confine matching to the window / segment with masks; the blocks in between carry no mask
         // state at all, so their loop is peeled into its own lean copy.
         auto block = [&](uint32_t blk, auto edge_tag) {
@@ -374,7 +374,7 @@ window_counts_kernel(const WindowJob job, const typename M::Params mp) {
             M::step(mp, P, special, cmask, lane, carry, cf, cr);
         };
         uint32_t blk = 0;
-        for (; blk < nlead && blk < nblk; blk++) block(blk, std::true_type{});
+        if (nblk > 0) { block(0, std::true_type{}); blk = 1; }
         for (; blk + 1 < nblk; blk++) block(blk, std::false_type{});
         if (blk < nblk) block(blk, std::true_type{});
 
@@ -404,7 +404,7 @@ window_counts_kernel(const WindowJob job, const typename M::Params mp) {
         da = na; db = nb;
         item_next = __shfl_sync(0xFFFFFFFFu, t2, 0);
     }
-    if (__any_sync(0xFFFFFFFFu, nonascii != 0) && lane == 0) atomicOr(job.err_flags, 1u);
+    if (__any_sync(0xFFFFFFFFu, nonascii != 0) && lane == 0) *(volatile uint32_t *)job.err_flags = 1u; // mapped host memory
 }
 
 // Exact byte-wise kernel for queries the plane kernels do not take: letters other
@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) window_counts_bytes_kerne
             job.out_rev[o] = r;
         }
     }
-    if (__any_sync(0xFFFFFFFFu, nonascii != 0) && lane == 0) atomicOr(job.err_flags, 1u);
+    if (__any_sync(0xFFFFFFFFu, nonascii != 0) && lane == 0) *(volatile uint32_t *)job.err_flags = 1u; // mapped host memory
 }
 
 } // namespace tidk
