@@ -143,9 +143,10 @@ __device__ __forceinline__ bool chunks_equal_upper(const uint8_t *t, int k, uint
 }
 
 // per-CTA stash of the run boundaries found in the current block: [k - 1][thread]
+template <int ROWS> // one row per k of the kernel's range (row = k - KBASE)
 struct EvStash {
-    uint32_t ev[kPlaneMaxK][256];
-    uint32_t z[kPlaneMaxK][256];
+    uint32_t ev[ROWS][256];
+    uint32_t z[ROWS][256];
 };
 
 struct Planes3 {
@@ -212,8 +213,8 @@ __device__ __forceinline__ uint32_t phase_step(uint32_t p) {
 // FULL: also require equal letter case and equal N-ness (mixed-case blocks, soft-mask edges, N runs):
 // with the case and N planes in the comparison, plane equality is byte equality for A/C/G/T/N in either
 // case, so only blocks with other bytes (IUPAC codes, gaps) need the byte-wise evaluation.
-template <int K, bool WITH_VA, bool FULL, bool EMIT>
-__device__ __forceinline__ void explore_k(EvStash &stash, const HTable &htab, uint32_t one, uint32_t &any_ev,
+template <int K, int ROW, bool WITH_VA, bool FULL, bool EMIT, class Stash>
+__device__ __forceinline__ void explore_k(Stash &stash, const HTable &htab, uint32_t one, uint32_t &any_ev,
                                           const Planes3 &cur, const Planes3 &prv, uint32_t &carry_nd, uint32_t m31,
                                           int src_lane, uint32_t s8, uint32_t own) {
     const uint32_t lo_k = __funnelshift_l(prv.lo, cur.lo, K);
@@ -240,10 +241,14 @@ __device__ __forceinline__ void explore_k(EvStash &stash, const HTable &htab, ui
     // run boundaries are rare; they are only stashed here (one shared-memory slot per k and lane) and
     // turned into events after all k of the block, in ONE copy of the emission code: inlining it
     // after every k made the hot loop three times larger than the instruction cache
-    const uint32_t ev = (x_hi ^ x_prev) & own; // x is 1 off the chunk ends in both, so only chunk ends survive
-    stash.ev[K - 1][threadIdx.x] = ev;
-    if (ev) stash.z[K - 1][threadIdx.x] = ~x_hi;
-    any_ev |= ev;
+    // x is 1 off the chunk ends in both words, so only chunk ends survive the XOR; interior blocks
+    // (WITH_VA false) own every position of the word
+    const uint32_t ev = WITH_VA ? (x_hi ^ x_prev) & own : (x_hi ^ x_prev);
+    stash.ev[ROW][threadIdx.x] = ev;
+    if (ev) { // predicated store + predicated move: nothing on the alu pipe
+        stash.z[ROW][threadIdx.x] = ~x_hi;
+        any_ev = 1u;
+    }
 }
 
 // byte-wise evaluation of this lane's owned chunk ends (special blocks).  x0 = (rel0 mod k) + offset
@@ -284,10 +289,35 @@ __device__ __forceinline__ uint32_t phase_byte(const uint32_t (&ph)[NREG]) {
         return 0u;
 }
 
+// q / k for k <= 16 with the divisor known per case: a multiply and a shift instead of the generic division
+__device__ __forceinline__ uint32_t div_small(uint32_t q, uint32_t k) {
+    switch (k) {
+    case 1: return q;
+    case 2: return q / 2u;
+    case 3: return q / 3u;
+    case 4: return q / 4u;
+    case 5: return q / 5u;
+    case 6: return q / 6u;
+    case 7: return q / 7u;
+    case 8: return q / 8u;
+    case 9: return q / 9u;
+    case 10: return q / 10u;
+    case 11: return q / 11u;
+    case 12: return q / 12u;
+    case 13: return q / 13u;
+    case 14: return q / 14u;
+    case 15: return q / 15u;
+    default: return q / 16u;
+    }
+}
+
 // KMIN > 0: the k range is a compile-time constant (default 5..12); KMIN == 0: run-time range.
+#ifndef TIDK_EX_MINB
+#define TIDK_EX_MINB 3
+#endif
 template <int KMIN, int KMAX>
-__global__ void __launch_bounds__(256, 3) explore_planes_kernel(const ExJob job) {
-    __shared__ EvStash stash;
+__global__ void __launch_bounds__(256, TIDK_EX_MINB) explore_planes_kernel(const ExJob job) {
+    __shared__ EvStash<(KMIN > 0 ? KMAX - KMIN + 1 : kPlaneMaxK)> stash;
     __shared__ HTable htab;
     constexpr int KBASE = KMIN > 0 ? KMIN : 1;                         // first k of the packed phase registers
     constexpr int NREG = KMIN > 0 ? (KMAX - KMIN) / 4 + 1 : kPlaneMaxK / 4;
@@ -297,12 +327,26 @@ __global__ void __launch_bounds__(256, 3) explore_planes_kernel(const ExJob job)
     const uint32_t m31 = lane == 31 ? 0xFFFFFFFFu : 0u; // look-behind: lane 31 sends its previous-block value
     const int src_lane = (lane + 31) & 31;
     uint32_t nonascii = 0;
-    for (;;) {
-        unsigned long long item = 0;
-        if (lane == 0) item = atomicAdd(job.work_counter, 1ull);
-        item = __shfl_sync(0xFFFFFFFFu, item, 0);
-        if (item >= job.n_items) break;
+    // Work queue, pipelined like the window counter's: the ticket of the item after next is drawn while
+    // an item is scanned, the next item's block 0 address is fetched at the start of the current item,
+    // and its first 1 KiB is requested before the current item's last block is evaluated -- a warp never
+    // sits through ticket -> descriptor -> data round trips between items.
+    unsigned long long item = 0, item_next = 0;
+    if (lane == 0) {
+        item = atomicAdd(job.work_counter, 2ull);
+        item_next = item + 1;
+    }
+    item = __shfl_sync(0xFFFFFFFFu, item, 0);
+    item_next = __shfl_sync(0xFFFFFFFFu, item_next, 0);
+    uint32_t w[8];
+    if (item < job.n_items) ld256_stream(job.seq + job.items[item].scan0 + (uint32_t)lane * 32u, w);
+    while (item < job.n_items) {
         const ExItem *ip = job.items + item;
+        const bool have_next = item_next < job.n_items;
+        uint64_t scan0_next = 0;
+        if (have_next) scan0_next = job.items[item_next].scan0;
+        unsigned long long t2 = 0;
+        if (lane == 0) t2 = atomicAdd(job.work_counter, 1ull);
         const uint64_t scan0 = ip->scan0;
         const int64_t rel0 = ip->rel0;
         const int64_t m = (int64_t)ip->slice_len;
@@ -333,67 +377,92 @@ __global__ void __launch_bounds__(256, 3) explore_planes_kernel(const ExJob job)
         }
         bool dirty_prev = false;
         int case_prev = -1; // -1 unknown (first block), 0 all upper, 1 all lower, 2 mixed
+        bool prev_last_plain = false; // lane 31's word of the previous block: in the slice, A/C/G/T, upper case
+        const uint32_t nlead = own_lo >= 1024 ? 2u : 1u; // a later tile starts one block before its owned range
+        // the slice may end up to kmax + 31 positions before the owned range does: then it ends in the block
+        // before the last one
+        const uint32_t ntail = v_hi <= (int)((nblk - 1u) << 10) ? 2u : 1u;
 
-        uint32_t w[8];
         const uint8_t *ptr = job.seq + scan0 + (uint32_t)lane * 32u;
-        ld256_stream(ptr, w);
+        if (nblk == 0 && have_next) ld256_stream(job.seq + scan0_next + (uint32_t)lane * 32u, w); // (never: every tile owns a position)
         for (uint32_t blk = 0; blk < nblk; blk++) {
-            const Nibbles nib = to_nibbles(w);
+            const Nibbles nib = to_nibbles(w); // w is dead from here: refill it
             if (blk + 1 < nblk) { ptr += 1024; ld256_stream(ptr, w); }
-            uint32_t na = 0;
-            const Planes P = extract_planes(nib, na);
+            else if (have_next) ld256_stream(job.seq + scan0_next + (uint32_t)lane * 32u, w);
+            const PlaneCore core = extract_core(nib);
             const int prel = (int)(blk << 10) + lane * 32;
-            // slice edges (and the item's owned range) can only fall into the first two and the
-            // last two blocks of an item
-            const bool edge = blk < 2 || blk + 2 >= nblk;
-            uint32_t inslice = 0xFFFFFFFFu, own = 0xFFFFFFFFu;
-            if (edge) {
-                inslice = range_mask32(v_lo - prel, v_hi - prel);
-                own = range_mask32(own_lo - prel, own_hi - prel);
-            }
-            nonascii |= na & inslice;
-            Planes3 cur;
-            cur.lo = P.lo; cur.hi = P.hi;
-            cur.nn = P.isn & inslice;
-            cur.va = ((P.b0 ^ (P.hi & ~P.lo)) & P.ok & inslice) | cur.nn;
-
-            // Letter case (ASCII bit 5 = bit 1 of the high nibbles).  Without the case plane, plane
-            // equality is byte equality only under uniform case, so a block whose case is mixed, or
-            // differs from the previous block's, compares the case plane as well (WITH_CS variant).  A
-            // lane that straddles the slice edge is judged on all its 32 bytes, which can only make the
-            // block "mixed" more often (still exact).
-            const uint32_t all_l = nib.Y[0] & nib.Y[1] & nib.Y[2] & nib.Y[3];
-            const uint32_t any_l = nib.Y[0] | nib.Y[1] | nib.Y[2] | nib.Y[3];
-            const bool lane_in = inslice != 0;
-            const bool lane_any_lower = (any_l & 0x22222222u) != 0;
-            const bool lane_all_lower = (all_l & 0x22222222u) == 0x22222222u;
-            const bool blk_upper = __all_sync(0xFFFFFFFFu, !lane_in || !lane_any_lower);
-            const bool blk_lower = __all_sync(0xFFFFFFFFu, !lane_in || lane_all_lower);
-            const int case_now = blk_upper ? 0 : (blk_lower ? 1 : 2);
-            const bool had_n = P.exact && __any_sync(0xFFFFFFFFu, cur.nn != 0);
-            const bool need_cs = case_now == 2 || case_now != case_prev || had_n || had_n_prev; // FULL variant
-            case_prev = case_now;
-            had_n_prev = had_n;
-            // bytes other than A/C/G/T/N (IUPAC codes, gaps, ...): their identity is not in the planes,
-            // so this block and the next one are evaluated byte-wise
-            const bool dirty_now = __any_sync(0xFFFFFFFFu, (~cur.va & inslice) != 0);
-            const bool special = dirty_now || dirty_prev;
-            dirty_prev = dirty_now;
-            // the case plane: extracted when needed, otherwise the constant the block's state implies
-            cur.cs = need_cs ? nibble_plane<1>(nib.Y) : (case_now == 1 ? 0xFFFFFFFFu : 0u);
-
-            Planes3 prv;
-            prv.lo = lane_lookbehind(cur.lo, own_prev.lo, lane);
-            prv.hi = lane_lookbehind(cur.hi, own_prev.hi, lane);
-            prv.va = lane_lookbehind(cur.va, own_prev.va, lane);
-            prv.cs = need_cs ? lane_lookbehind(cur.cs, own_prev.cs, lane) : 0u;
-            prv.nn = need_cs ? lane_lookbehind(cur.nn, own_prev.nn, lane) : 0u;
-            own_prev = cur;
+            // slice edges (and the item's owned range) can only fall into the first block (the first two
+            // of a later tile, which starts one block early) and the last block (or two) of an item
+            const bool edge = blk < nlead || blk + ntail >= nblk;
             const int64_t p = rel0 + prel;
+            uint32_t any_ev = 0;
+            uint32_t own = 0xFFFFFFFFu;
+            bool need_cs = false, special = false;
+            Planes3 cur, prv;
+
+            // The common block -- interior, every base one of A C G T in upper case, and the block before it
+            // of the same kind -- is recognised with ONE warp vote and needs nothing but the lo / hi planes.
+            const uint32_t any_l = nib.Y[0] | nib.Y[1] | nib.Y[2] | nib.Y[3]; // ASCII bit 5 = bit 1 of the high nibbles
+            const bool lane_plain = core.bad == 0u && (core.b0 ^ (core.hi & ~core.lo)) == 0xFFFFFFFFu &&
+                                    (any_l & 0x22222222u) == 0u;
+            const uint32_t plain_lanes = __ballot_sync(0xFFFFFFFFu, lane_plain);
+            // (after a block whose in-slice bases were all upper-case A/C/G/T the case / N / dirty state is
+            // the initial one, whichever path evaluated it; the fast path leaves it untouched)
+            const bool fast = !edge && plain_lanes == 0xFFFFFFFFu && prev_last_plain && case_prev == 0 &&
+                              !had_n_prev && !dirty_prev;
+            uint32_t inslice = 0xFFFFFFFFu;
+            cur.lo = core.lo; cur.hi = core.hi;
+            if (fast) {
+                cur.va = 0xFFFFFFFFu; cur.cs = 0u; cur.nn = 0u;
+                prv.lo = lane_lookbehind(cur.lo, own_prev.lo, lane);
+                prv.hi = lane_lookbehind(cur.hi, own_prev.hi, lane);
+                prv.va = 0xFFFFFFFFu; prv.cs = 0u; prv.nn = 0u;
+            } else {
+                uint32_t na = 0;
+                const Planes P = finish_planes(nib, core, __any_sync(0xFFFFFFFFu, core.bad != 0u), na);
+                if (edge) {
+                    inslice = range_mask32(v_lo - prel, v_hi - prel);
+                    own = range_mask32(own_lo - prel, own_hi - prel);
+                }
+                nonascii |= na & inslice;
+                cur.nn = P.isn & inslice;
+                cur.va = ((P.b0 ^ (P.hi & ~P.lo)) & P.ok & inslice) | cur.nn;
+
+                // Letter case.  Without the case plane, plane equality is byte equality only under uniform
+                // case, so a block whose case is mixed, or differs from the previous block's, compares the
+                // case plane as well (FULL variant).  A lane that straddles the slice edge is judged on all
+                // its 32 bytes, which can only make the block "mixed" more often (still exact).
+                const uint32_t all_l = nib.Y[0] & nib.Y[1] & nib.Y[2] & nib.Y[3];
+                const bool lane_in = inslice != 0;
+                const bool lane_any_lower = (any_l & 0x22222222u) != 0;
+                const bool lane_all_lower = (all_l & 0x22222222u) == 0x22222222u;
+                const bool blk_upper = __all_sync(0xFFFFFFFFu, !lane_in || !lane_any_lower);
+                const bool blk_lower = __all_sync(0xFFFFFFFFu, !lane_in || lane_all_lower);
+                const int case_now = blk_upper ? 0 : (blk_lower ? 1 : 2);
+                const bool had_n = P.exact && __any_sync(0xFFFFFFFFu, cur.nn != 0);
+                need_cs = case_now == 2 || case_now != case_prev || had_n || had_n_prev; // FULL variant
+                case_prev = case_now;
+                had_n_prev = had_n;
+                // bytes other than A/C/G/T/N (IUPAC codes, gaps, ...): their identity is not in the planes,
+                // so this block and the next one are evaluated byte-wise
+                const bool dirty_now = __any_sync(0xFFFFFFFFu, (~cur.va & inslice) != 0);
+                special = dirty_now || dirty_prev;
+                dirty_prev = dirty_now;
+                // the case plane: extracted when needed, otherwise the constant the block's state implies
+                cur.cs = need_cs ? nibble_plane<1>(nib.Y) : (case_now == 1 ? 0xFFFFFFFFu : 0u);
+
+                prv.lo = lane_lookbehind(cur.lo, own_prev.lo, lane);
+                prv.hi = lane_lookbehind(cur.hi, own_prev.hi, lane);
+                prv.va = lane_lookbehind(cur.va, own_prev.va, lane);
+                prv.cs = need_cs ? lane_lookbehind(cur.cs, own_prev.cs, lane) : 0u;
+                prv.nn = need_cs ? lane_lookbehind(cur.nn, own_prev.nn, lane) : 0u;
+            }
+            own_prev = cur;
+            prev_last_plain = (plain_lanes >> 31) != 0u && (!edge || __shfl_sync(0xFFFFFFFFu, inslice, 31) == 0xFFFFFFFFu);
             const uint32_t xoff = (uint32_t)prel; // < 2^15
 #define TIDK_EXK(K, VA, CS, EM)                                                                   \
     if ((KMIN > 0) ? (K >= KMIN && K <= KMAX) : (job.kmin <= K && K <= job.kmax)) {              \
-        explore_k<K, VA, CS, EM>(stash, htab, job.one, any_ev, cur, prv, carry_nd[K - 1], m31, src_lane,  \
+        explore_k<K, (K >= KBASE ? K - KBASE : 0), VA, CS, EM>(stash, htab, job.one, any_ev, cur, prv, carry_nd[K - 1], m31, src_lane,  \
                                  phase_byte<KBASE, NREG, K>(ph), own);                             \
     }
 #define TIDK_EXALL(VA, CS, EM)                                                                    \
@@ -406,25 +475,26 @@ __global__ void __launch_bounds__(256, 3) explore_planes_kernel(const ExJob job)
             //   clean block at a slice edge                                                -> + va plane
             //   mixed letter case / case change / N present                                -> + va + case + N planes
             //   special block (bytes other than A C G T N)                                 -> carries only + byte-wise
-            const bool all_valid = __all_sync(0xFFFFFFFFu, (cur.va & prv.va) == 0xFFFFFFFFu);
-            uint32_t any_ev = 0;
-            if (special) { TIDK_EXALL(true, false, false) }
+            bool lohi_only = fast;
+            if (!fast && !special && !need_cs && !edge) // (edge blocks own only part of their positions: VA variant)
+                lohi_only = __all_sync(0xFFFFFFFFu, (cur.va & prv.va) == 0xFFFFFFFFu);
+            if (lohi_only) { TIDK_EXALL(false, false, true) }
+            else if (special) { TIDK_EXALL(true, false, false) }
             else if (need_cs) { TIDK_EXALL(true, true, true) }
-            else if (all_valid) { TIDK_EXALL(false, false, true) }
             else { TIDK_EXALL(true, false, true) }
 #undef TIDK_EXALL
 #undef TIDK_EXK
             if (any_ev) { // rare: this lane found run boundaries in this block
                 const uint32_t k0 = KMIN > 0 ? KMIN : job.kmin, k1 = KMIN > 0 ? KMAX : job.kmax;
                 for (uint32_t k = k0; k <= k1; k++) {
-                    uint32_t ev = stash.ev[k - 1][threadIdx.x];
+                    uint32_t ev = stash.ev[k - KBASE][threadIdx.x];
                     if (!ev) continue;
-                    const uint32_t z = stash.z[k - 1][threadIdx.x];
+                    const uint32_t z = stash.z[k - KBASE][threadIdx.x];
                     while (ev) {
                         const int b = __ffs(ev) - 1;
                         ev &= ev - 1;
                         const uint64_t q1 = (uint64_t)(p + b) + 1; // chunk end + 1, a multiple of k
-                        const uint64_t j = (q1 >> 32 ? q1 / k : (uint64_t)((uint32_t)q1 / k)) - 2;
+                        const uint64_t j = (q1 >> 32 ? q1 / k : (uint64_t)div_small((uint32_t)q1, k)) - 2;
                         // a run start in a uniform-case block never joins the previous chunk (they differ
                         // as bytes and share the case, so they differ after upper-casing too); with mixed
                         // case the two chunks are compared after upper-casing (explore.rs:212 vs :324)
@@ -441,6 +511,8 @@ __global__ void __launch_bounds__(256, 3) explore_planes_kernel(const ExJob job)
             }
             phase_step_all<KBASE, NREG>(ph); // the next block lies 1024 bases further on
         }
+        item = item_next;
+        item_next = __shfl_sync(0xFFFFFFFFu, t2, 0);
     }
     if (__any_sync(0xFFFFFFFFu, nonascii != 0) && lane == 0) atomicOr(job.err_flags, 1u);
 }

@@ -102,9 +102,13 @@ struct Planes {
     bool exact;   // warp-uniform: ok is not all ones
 };
 
-// nonascii is OR-ed with a non-zero value if any byte >= 0x80 (exact path only:
-// such a byte always fails the aggregate test).
-__device__ __forceinline__ Planes extract_planes(const Nibbles &n, uint32_t &nonascii) {
+// The planes every path needs, plus the per-lane verdict of the aggregate test; no warp vote yet.
+struct PlaneCore {
+    uint32_t lo, hi, b0;
+    uint32_t bad; // non-zero: some byte of this lane is not of the form 010x0xxx with b4 == !b0
+};
+
+__device__ __forceinline__ PlaneCore extract_core(const Nibbles &n) {
     uint32_t accA = 0xFFFFFFFFu, accO = 0u, accB = 0xFFFFFFFFu;
 #pragma unroll
     for (int g = 0; g < 4; g++) {
@@ -112,14 +116,22 @@ __device__ __forceinline__ Planes extract_planes(const Nibbles &n, uint32_t &non
         accO |= n.X[g] | n.Y[g]; // nibble bit 3: b3 | b7 must be 0
         accB &= n.Y[g];          // nibble bit 2: b6 must be 1
     }
-    const uint32_t bad = (~accA & 0x11111111u) | (accO & 0x88888888u) | (~accB & 0x44444444u);
+    PlaneCore c;
+    c.bad = (~accA & 0x11111111u) | (accO & 0x88888888u) | (~accB & 0x44444444u);
+    c.lo = nibble_plane<1>(n.X);
+    c.hi = nibble_plane<2>(n.X);
+    c.b0 = nibble_plane<0>(n.X);
+    return c;
+}
+
+// exact = (warp-uniform) some lane failed the aggregate test: build the exact `ok` and N planes.
+// nonascii is OR-ed with a non-zero value if any byte >= 0x80 (such a byte always fails the aggregate test).
+__device__ __forceinline__ Planes finish_planes(const Nibbles &n, const PlaneCore &c, bool exact, uint32_t &nonascii) {
     Planes P;
-    P.lo = nibble_plane<1>(n.X);
-    P.hi = nibble_plane<2>(n.X);
-    P.b0 = nibble_plane<0>(n.X);
+    P.lo = c.lo; P.hi = c.hi; P.b0 = c.b0;
     P.ok = 0xFFFFFFFFu;
     P.isn = 0u;
-    P.exact = __any_sync(0xFFFFFFFFu, bad != 0);
+    P.exact = exact;
     if (P.exact) {
         uint32_t b3 = nibble_plane<3>(n.X);
         uint32_t b4 = nibble_plane<0>(n.Y);
@@ -132,19 +144,23 @@ __device__ __forceinline__ Planes extract_planes(const Nibbles &n, uint32_t &non
     return P;
 }
 
+__device__ __forceinline__ Planes extract_planes(const Nibbles &n, uint32_t &nonascii) {
+    const PlaneCore c = extract_core(n);
+    return finish_planes(n, c, __any_sync(0xFFFFFFFFu, c.bad != 0), nonascii);
+}
+
 // prev[lane] = lane > 0 ? cur[lane-1] : (this lane 31's value from the previous block)
 __device__ __forceinline__ uint32_t lane_lookbehind(uint32_t cur, uint32_t old, int lane) {
     uint32_t x = (lane == 31) ? old : cur;
     return __shfl_sync(0xFFFFFFFFu, x, (lane + 31) & 31);
 }
 
-// bits b in [0,32) with lo_rel <= b < hi_rel
+// bits b in [0,32) with lo_rel <= b < hi_rel (branch-free: shl.b32 clamps shift counts above 31 to "all out")
 __device__ __forceinline__ uint32_t range_mask32(int lo_rel, int hi_rel) {
-    if (hi_rel <= 0 || lo_rel >= 32 || hi_rel <= lo_rel) return 0u;
-    uint32_t m = 0xFFFFFFFFu;
-    if (lo_rel > 0) m <<= lo_rel;
-    if (hi_rel < 32) m &= 0xFFFFFFFFu >> (32 - hi_rel);
-    return m;
+    uint32_t from_lo, from_hi; // PTX shl.b32 clamps the count: 32 or more shifts everything out
+    asm("shl.b32 %0, %1, %2;" : "=r"(from_lo) : "r"(0xFFFFFFFFu), "r"((uint32_t)max(lo_rel, 0)));
+    asm("shl.b32 %0, %1, %2;" : "=r"(from_hi) : "r"(0xFFFFFFFFu), "r"((uint32_t)max(hi_rel, 0)));
+    return from_lo & ~from_hi;
 }
 
 } // namespace tidk
