@@ -302,7 +302,8 @@ def main():
                 "e2e": {"value": total_bases * e2e_steps / dt_e2e / 1e9, "unit": UNIT,
                         "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
                         "host_bytes_per_step": bases,
-                        "upload": ("host-packed bit-planes (3 bits per base), packed by %d host threads inside the timed region"
+                        "upload": ("two-ended: ASCII chunks by DMA from the front, host-packed lo/hi bit-planes (2 bits per base + validity "
+                                   "exceptions) from the back, packed by %d host threads inside the timed region"
                                    % min(32, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
                                    if host_packed else "ASCII, straight DMA from the caller's pinned buffer"),
                         "ms_per_step": dt_e2e / e2e_steps * 1e3,

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <new>
 #include <atomic>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -49,7 +50,7 @@ struct tidk_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
     tidk_seqbuf scratch; // staging for the host-pointer entry points
-    DevBuf win_base, out_fwd, out_rev, misc, qbytes, runs, items;
+    DevBuf win_base, out_fwd, out_rev, misc, qbytes, runs, items, exc;
     float explore_scan_ms = 0.f, explore_post_ms = 0.f;
     uint64_t last_h2d = 0, last_d2h = 0; // bytes moved by the last host-pointer window-count call
     int last_packed = 0;
@@ -57,6 +58,9 @@ struct tidk_ctx {
     DevBuf packed;
     struct PackLane { cudaStream_t st = nullptr; cudaEvent_t ev[2] = {nullptr, nullptr}; uint32_t *pin = nullptr; };
     std::vector<PackLane> pack_lanes;
+    cudaStream_t dma_st = nullptr;  // hybrid upload: the ASCII share of the sequence
+    static constexpr int kDmaDepth = 4;
+    cudaEvent_t dma_ev[kDmaDepth] = {nullptr, nullptr, nullptr, nullptr};
     uint32_t counter_flip = 0;      // which of the two queue counters the next launch uses
     bool counters_dirty = false;    // a call failed between taking a counter and finishing: re-zero both
     uint32_t *h_flags = nullptr;    // pinned + mapped: the window kernels store the (rare) error flag straight into host memory
@@ -105,15 +109,18 @@ int ensure(tidk_ctx *ctx, DevBuf &b, size_t bytes) {
 
 constexpr size_t kSeqPad = 8192; // zeroed bytes behind the data: block loads never leave the buffer
 
+// seq_mode 1: copy the sequence; 0: offsets only; 2: allocate the sequence buffer, copy nothing (the hybrid
+// upload fills the part of it that travels as ASCII)
 int seqbuf_fill(tidk_ctx *ctx, tidk_seqbuf *b, const uint8_t *seq, const uint64_t *offsets,
-                uint32_t n_records, bool copy_seq = true) {
+                uint32_t n_records, int seq_mode = 1) {
+    const bool copy_seq = seq_mode == 1;
     if (n_records && (!offsets)) return fail(ctx, TIDK_EARG, "offsets is NULL");
     const uint64_t total = n_records ? offsets[n_records] : 0;
     if (n_records && offsets[0] != 0) return fail(ctx, TIDK_EARG, "offsets[0] must be 0");
     for (uint32_t r = 0; r < n_records; r++)
         if (offsets[r + 1] < offsets[r]) return fail(ctx, TIDK_EARG, "offsets must be non-decreasing");
     if (total && !seq) return fail(ctx, TIDK_EARG, "seq is NULL");
-    const size_t need = copy_seq ? (size_t)total + kSeqPad : 0;
+    const size_t need = seq_mode ? (size_t)total + kSeqPad : 0;
     if (need > b->seq_cap) {
         if (b->d_seq) cudaFree(b->d_seq);
         b->d_seq = nullptr; b->seq_cap = 0;
@@ -326,7 +333,7 @@ void tidk_cuda_destroy(tidk_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     seqbuf_release(&ctx->scratch);
-    for (DevBuf *b : {&ctx->win_base, &ctx->out_fwd, &ctx->out_rev, &ctx->misc, &ctx->qbytes, &ctx->runs, &ctx->items})
+    for (DevBuf *b : {&ctx->win_base, &ctx->out_fwd, &ctx->out_rev, &ctx->misc, &ctx->qbytes, &ctx->runs, &ctx->items, &ctx->exc})
         if (b->p) cudaFree(b->p);
     explore_scratch_release(ctx->ex);
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
@@ -337,6 +344,9 @@ void tidk_cuda_destroy(tidk_ctx *ctx) {
         if (L.ev[1]) cudaEventDestroy(L.ev[1]);
         if (L.st) cudaStreamDestroy(L.st);
     }
+    for (cudaEvent_t e : ctx->dma_ev)
+        if (e) cudaEventDestroy(e);
+    if (ctx->dma_st) cudaStreamDestroy(ctx->dma_st);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
@@ -387,10 +397,12 @@ void tidk_cuda_seqbuf_free(tidk_ctx *ctx, tidk_seqbuf *buf) {
     delete buf;
 }
 
+// packed != nullptr: the host-packed planes are the source for the sequence from byte `split` on; the bytes
+// below `split` (a multiple of 32, 0 = none) are resident as ASCII in buf->d_seq (hybrid upload).
 static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint32_t *packed, uint64_t window,
                               const char *const *queries, const uint32_t *qlens,
                               uint32_t nq, uint64_t *out_fwd, uint64_t *out_rev,
-                              float *kernel_ms, uint32_t *kernel_launches) {
+                              float *kernel_ms, uint32_t *kernel_launches, uint64_t split = 0) {
     if (!ctx) return TIDK_EARG;
     if (kernel_ms) *kernel_ms = 0.f;
     if (kernel_launches) *kernel_launches = 0;
@@ -512,28 +524,58 @@ static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint3
     std::vector<uint32_t> fused;
     uint8_t rcbuf[kMaxFastLen];
     if (packed && !slow.empty()) return fail(ctx, TIDK_ECUDA, "internal: packed source with a literal query");
-    if (LaunchFn clade = (slow.empty() ? find_clade_set(queries, qlens, nq, packed != nullptr) : nullptr)) {
+    // Hybrid upload: the windows that start below `split` are resident as ASCII, the rest as packed planes;
+    // a static kernel then runs once per source over its share of the (position-ordered) items.
+    uint64_t n_ascii_items = packed ? 0 : n_items;
+    if (packed && split > 0) {
+        if (spw != 1) return fail(ctx, TIDK_ECUDA, "internal: hybrid upload with multi-segment windows");
+        for (uint32_t r = 0; r < nrec; r++) {
+            const uint64_t rb = buf->h_off[r], re = buf->h_off[r + 1];
+            if (rb >= split) break;
+            const uint64_t nw = (re - rb) / window + ((re - rb) % window != 0);
+            const uint64_t below = (split - rb + window - 1) / window; // windows of this record that start below split
+            n_ascii_items += below < nw ? below : nw;
+        }
+    }
+    auto run_static = [&](LaunchFn f_ascii, LaunchFn f_packed, const WindowJob &j) {
+        if (n_ascii_items > 0) {
+            WindowJob ja = j;
+            ja.packed = nullptr;
+            ja.n_items = n_ascii_items;
+            ja.work_counter = next_counter(); ja.next_counter = next_zeroed;
+            f_ascii(ja, grid, ctx->stream);
+            launches++;
+        }
+        if (n_ascii_items < n_items) {
+            WindowJob jp = j;
+            jp.items = j.items + n_ascii_items;
+            jp.n_items = n_items - n_ascii_items;
+            jp.work_counter = next_counter(); jp.next_counter = next_zeroed;
+            f_packed(jp, grid, ctx->stream);
+            launches++;
+        }
+    };
+    if (LaunchFn clade = (slow.empty() ? find_clade_set(queries, qlens, nq, false) : nullptr)) {
         WindowJob j2 = job; // the whole query list is a known clade: one fused pass
         j2.q0 = 0; j2.nq = nq;
-        j2.work_counter = next_counter(); j2.next_counter = next_zeroed;
-        clade(j2, grid, ctx->stream);
-        launches++;
+        run_static(clade, packed ? find_clade_set(queries, qlens, nq, true) : nullptr, j2);
         fast.clear();
     }
     for (uint32_t q : fast) {
         const uint8_t *f = (const uint8_t *)queries[q];
         revcomp_host(f, qlens[q], rcbuf);
-        LaunchFn fn = find_static(f, qlens[q], packed != nullptr);
+        LaunchFn fn = find_static(f, qlens[q], false), fnp = packed ? find_static(f, qlens[q], true) : nullptr;
         bool swap = false;
-        if (!fn && (fn = find_static(rcbuf, qlens[q], packed != nullptr))) swap = true;
-        if (!fn && packed) return fail(ctx, TIDK_ECUDA, "internal: packed source without a static kernel");
+        if (!fn && (fn = find_static(rcbuf, qlens[q], false))) {
+            swap = true;
+            fnp = packed ? find_static(rcbuf, qlens[q], true) : nullptr;
+        }
+        if (packed && (!fn || !fnp)) return fail(ctx, TIDK_ECUDA, "internal: packed source without a static kernel");
         if (!fn) { fused.push_back(q); continue; }
         WindowJob j2 = job;
         j2.q0 = q; j2.nq = 1;
         if (swap) { j2.out_fwd = d_rev; j2.out_rev = d_fwd; }
-        j2.work_counter = next_counter(); j2.next_counter = next_zeroed;
-        fn(j2, grid, ctx->stream);
-        launches++;
+        run_static(fn, fnp, j2);
     }
     // Run-time patterns: one unrolled single-query launch each (about 100 us + 6.5 us per base on C2),
     // unless there are many -- the fused run-time kernel is not unrolled and costs about 130 us per
@@ -611,6 +653,14 @@ int tidk_cuda_window_counts_resident(tidk_ctx *ctx, const tidk_seqbuf *buf, uint
 // T worker threads each own a stream and a two-slot pinned staging ring; a worker packs one 4 MiB
 // chunk of sequence (1.5 MiB of planes, contiguous on the device) into a free slot and issues its
 // copy, so packing and DMA overlap without any cross-thread barrier.
+// validity-plane exceptions of the host packer: (global word index << 32 | va) -> the va third of the word's chunk
+__global__ void va_scatter_kernel(uint32_t *packed, const uint64_t *exc, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t e = exc[i], word = e >> 32;
+    packed[(word >> tidk::kPackShift) * (3ull * tidk::kPackWords) + 2ull * tidk::kPackWords + (word & (tidk::kPackWords - 1))] = (uint32_t)e;
+}
+
 static int pack_threads() {
     if (const char *e = getenv("TIDK_PACK_THREADS")) return atoi(e);
     unsigned hw = std::thread::hardware_concurrency();
@@ -621,13 +671,27 @@ static int pack_threads() {
     return (int)(t > 32 ? 32 : t);
 }
 
-static int upload_packed(tidk_ctx *ctx, const uint8_t *seq, uint64_t total, int T) {
+//
+// Two-ended ("hybrid") upload.  The packers are bound by the host's memory bandwidth (about 76 GB/s of
+// sequence on 16 vCPUs) while the bus would still have room, and a plain DMA of ASCII needs no CPU at
+// all.  So the 4 MiB chunks are claimed from both ends: chunks of ASCII from the front of the caller's
+// buffer go straight into the sequence buffer by DMA (a few copies in flight, issued by whichever packer
+// passes by), the packers take chunks from the back, and they meet wherever the machine's pack rate and
+// bus rate put the balance.  *split receives the first packed byte; the windows below it are counted
+// from ASCII, the rest from planes.
+static int upload_packed(tidk_ctx *ctx, const uint8_t *seq, uint64_t total, int T, bool allow_ascii, uint64_t *split) {
     const uint64_t n_words = (total + 31) / 32;
     const uint64_t n_chunks = (n_words + kPackWords - 1) / kPackWords;
     const size_t chunk_bytes = 3ull * kPackWords * 4;
+    const uint64_t chunk_seq = (uint64_t)kPackWords * 32; // sequence bytes per chunk
+    const size_t plane2_bytes = 2ull * kPackWords * 4;   // lo + hi planes of a chunk: what a packer sends
+    *split = 0;
     int rc;
     if ((rc = ensure(ctx, ctx->packed, (n_chunks + 1) * chunk_bytes))) return rc; // + one zero chunk: blocks read past the end
     CU(ctx, cudaMemsetAsync((char *)ctx->packed.p + n_chunks * chunk_bytes, 0, chunk_bytes, ctx->stream));
+    // the validity plane (third part of every chunk) is all ones except where the packers say otherwise
+    CU(ctx, cudaMemset2DAsync((char *)ctx->packed.p + 2ull * kPackWords * 4, chunk_bytes, 0xFF, (size_t)kPackWords * 4, n_chunks, ctx->stream));
+    std::vector<std::vector<uint64_t>> exc((size_t)T);
     if ((int)ctx->pack_lanes.size() < T) {
         const size_t old = ctx->pack_lanes.size();
         ctx->pack_lanes.resize(T);
@@ -639,22 +703,66 @@ static int upload_packed(tidk_ctx *ctx, const uint8_t *seq, uint64_t total, int 
             CU(ctx, cudaHostAlloc((void **)&L.pin, 2 * chunk_bytes, cudaHostAllocDefault));
         }
     }
-    std::atomic<uint64_t> next_chunk{0};
+    if (allow_ascii && !ctx->dma_st) {
+        CU(ctx, cudaStreamCreateWithFlags(&ctx->dma_st, cudaStreamNonBlocking));
+        for (int i = 0; i < tidk_ctx::kDmaDepth; i++)
+            CU(ctx, cudaEventCreateWithFlags(&ctx->dma_ev[i], cudaEventDisableTiming));
+    }
+    // chunks [front, back] are unclaimed; the DMA thread takes `front++`, a packer `back--`
+    std::atomic<int64_t> front{0}, back{(int64_t)n_chunks - 1};
+    std::mutex claim_mu;
+    auto claim = [&](bool from_front) -> int64_t {
+        std::lock_guard<std::mutex> g(claim_mu);
+        if (front.load() > back.load()) return -1;
+        return from_front ? front.fetch_add(1) : back.fetch_sub(1);
+    };
     std::atomic<int> cuda_err{0};
     std::atomic<uint32_t> nonascii{0};
+    // The ASCII copies are issued by whichever packer passes by between two chunks (a dedicated thread would
+    // be a 17th runnable thread on 16 busy cores and starve): retire finished copies, top the queue up to
+    // kDmaDepth chunks in flight.  A packer comes by every ~50 us, one copy takes ~80 us.
+    std::mutex dma_mu;
+    int dma_head = 0, dma_tail = 0, dma_inflight = 0;
+    auto pump = [&]() {
+        if (!allow_ascii) return;
+        std::unique_lock<std::mutex> g(dma_mu, std::try_to_lock);
+        if (!g.owns_lock()) return;
+        while (dma_inflight > 0 && cudaEventQuery(ctx->dma_ev[dma_tail]) == cudaSuccess) {
+            dma_tail = (dma_tail + 1) % tidk_ctx::kDmaDepth;
+            dma_inflight--;
+        }
+        while (dma_inflight < tidk_ctx::kDmaDepth) {
+            const int64_t c = claim(true);
+            if (c < 0) break;
+            const uint64_t byte0 = (uint64_t)c * chunk_seq;
+            const uint64_t n = total - byte0 < chunk_seq ? total - byte0 : chunk_seq;
+            if (cudaMemcpyAsync(ctx->scratch.d_seq + byte0, seq + byte0, n, cudaMemcpyHostToDevice, ctx->dma_st) != cudaSuccess ||
+                cudaEventRecord(ctx->dma_ev[dma_head], ctx->dma_st) != cudaSuccess) { cuda_err = 1; break; }
+            dma_head = (dma_head + 1) % tidk_ctx::kDmaDepth;
+            dma_inflight++;
+        }
+    };
     auto worker = [&](int t) {
         cudaSetDevice(ctx->device);
         tidk_ctx::PackLane &L = ctx->pack_lanes[t];
         uint32_t flag = 0;
         for (int slot = 0;; slot ^= 1) {
-            const uint64_t c = next_chunk.fetch_add(1);
-            if (c >= n_chunks) break;
+            pump();
+            const int64_t c = claim(false);
+            if (c < 0) break;
             if (cudaEventSynchronize(L.ev[slot]) != cudaSuccess) { cuda_err = 1; break; } // slot's previous copy done
             uint32_t *buf = L.pin + (size_t)slot * 3 * kPackWords;
-            const uint64_t byte0 = c * (uint64_t)kPackWords * 32;
-            pack_words(seq + byte0, (size_t)(total - byte0 < (uint64_t)kPackWords * 32 ? total - byte0 : (uint64_t)kPackWords * 32),
-                       kPackWords, buf, buf + kPackWords, buf + 2 * kPackWords, &flag);
-            if (cudaMemcpyAsync((char *)ctx->packed.p + c * chunk_bytes, buf, chunk_bytes, cudaMemcpyHostToDevice, L.st) != cudaSuccess ||
+            const uint64_t byte0 = (uint64_t)c * chunk_seq;
+            const uint64_t have = total - byte0 < chunk_seq ? total - byte0 : chunk_seq;
+            constexpr uint32_t kSub = 8; // packed in eighths, looking after the ASCII copy queue in between
+            for (uint32_t s8 = 0; s8 < kSub; s8++) {
+                const uint32_t w0 = s8 * (kPackWords / kSub);
+                const uint64_t b0 = (uint64_t)w0 * 32;
+                pack_words2(seq + byte0 + b0, (size_t)(have > b0 ? have - b0 : 0), kPackWords / kSub, buf + w0,
+                            buf + kPackWords + w0, (uint64_t)c * kPackWords + w0, exc[(size_t)t], &flag);
+                pump();
+            }
+            if (cudaMemcpyAsync((char *)ctx->packed.p + (uint64_t)c * chunk_bytes, buf, plane2_bytes, cudaMemcpyHostToDevice, L.st) != cudaSuccess ||
                 cudaEventRecord(L.ev[slot], L.st) != cudaSuccess) { cuda_err = 1; break; }
         }
         if (cudaStreamSynchronize(L.st) != cudaSuccess) cuda_err = 1;
@@ -664,9 +772,35 @@ static int upload_packed(tidk_ctx *ctx, const uint8_t *seq, uint64_t total, int 
     for (int t = 1; t < T; t++) th.emplace_back(worker, t);
     worker(0);
     for (auto &x : th) x.join();
+    if (allow_ascii && cudaStreamSynchronize(ctx->dma_st) != cudaSuccess) cuda_err = 1;
     if (cuda_err) return fail(ctx, TIDK_ECUDA, "packed upload failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (nonascii)
         return fail(ctx, TIDK_ENONASCII, "sequence contains a byte >= 0x80 (the reference fails in str::from_utf8, search.rs:107)");
+    const uint64_t n_ascii = (uint64_t)front.load() < n_chunks ? (uint64_t)front.load() : n_chunks; // chunks [0, n_ascii) went as ASCII
+    uint64_t sp = n_ascii * chunk_seq;
+    if (sp > total) sp = total;
+    if (n_ascii > 0) {
+        // the last window below the split may reach up to a window (<= 32 KiB here) plus a block beyond it
+        const uint64_t extra = total - sp < (64u << 10) ? total - sp : (64u << 10);
+        if (extra) CU(ctx, cudaMemcpyAsync(ctx->scratch.d_seq + sp, seq + sp, extra, cudaMemcpyHostToDevice, ctx->stream));
+        if (sp + extra == total) CU(ctx, cudaMemsetAsync(ctx->scratch.d_seq + total, 0, kSeqPad, ctx->stream));
+        ctx->last_h2d += sp + extra;
+    }
+    ctx->last_h2d += (n_chunks - n_ascii) * plane2_bytes;
+    size_t n_exc = 0;
+    for (const auto &v : exc) n_exc += v.size();
+    if (n_exc) {
+        std::vector<uint64_t> all;
+        all.reserve(n_exc);
+        for (const auto &v : exc) all.insert(all.end(), v.begin(), v.end());
+        if ((rc = ensure(ctx, ctx->exc, n_exc * 8))) return rc;
+        CU(ctx, cudaMemcpyAsync(ctx->exc.p, all.data(), n_exc * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream)); // `all` is pageable and goes out of scope
+        va_scatter_kernel<<<(unsigned)((n_exc + 255) / 256), 256, 0, ctx->stream>>>((uint32_t *)ctx->packed.p, (const uint64_t *)ctx->exc.p, n_exc);
+        CU(ctx, cudaGetLastError());
+        ctx->last_h2d += n_exc * 8;
+    }
+    *split = sp;
     return TIDK_OK;
 }
 
@@ -704,14 +838,17 @@ int tidk_cuda_window_counts(tidk_ctx *ctx, const uint8_t *seq, const uint64_t *o
     }
     ctx->last_d2h = n_out * 16 + 4;
     ctx->last_packed = packable ? 1 : 0;
-    ctx->last_h2d = ((uint64_t)n_records + 1) * 16 +
-                    (packable ? (((total + 31) / 32 + kPackWords - 1) / kPackWords) * 3ull * kPackWords * 4 : total);
+    ctx->last_h2d = ((uint64_t)n_records + 1) * 16 + (packable ? 0 : total);
     if (packable) {
-        int rc = seqbuf_fill(ctx, &ctx->scratch, seq, offsets, n_records, /*copy_seq=*/false);
+        // windows of one 32 KiB item can be split between the two sources; larger ones travel packed only
+        const char *eh = getenv("TIDK_HYBRID_UPLOAD");
+        const bool hybrid = window <= kSegBytes && (eh ? atoi(eh) != 0 : true);
+        int rc = seqbuf_fill(ctx, &ctx->scratch, seq, offsets, n_records, /*seq_mode=*/hybrid ? 2 : 0);
         if (rc) return rc;
-        if ((rc = upload_packed(ctx, seq, total, T))) return rc;
+        uint64_t split = 0;
+        if ((rc = upload_packed(ctx, seq, total, T, hybrid, &split))) return rc;
         return window_counts_impl(ctx, &ctx->scratch, (const uint32_t *)ctx->packed.p, window, queries, qlens, nq,
-                                  out_fwd, out_rev, nullptr, nullptr);
+                                  out_fwd, out_rev, nullptr, nullptr, split);
     }
     int rc = seqbuf_fill(ctx, &ctx->scratch, seq, offsets, n_records);
     if (rc) return rc;

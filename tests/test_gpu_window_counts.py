@@ -298,10 +298,29 @@ def test_host_packed_upload_path(ctx, monkeypatch):
     seq[5_000_000:5_000_100] = np.frombuffer(b"RYKMSWBDHV" * 10, dtype=np.uint8)
     hym = [r.encode() for r in clades.return_telomere_sequence("Hymenoptera", db)]
     monkeypatch.setenv("TIDK_HOST_PACK", "1")
-    for qs, W in (([b"TTAGGG"], 10000), ([b"CCCTAA", b"AACCT"], 4321), (hym, 10000), ([b"TTAGGG"], 50000)):
-        f, r = ctx.window_counts(seq, off, W, qs)
-        of, orr = O.window_counts(seq, off, W, qs, False, threads=4)
-        assert (f == of).all() and (r == orr).all(), (qs, W)
+    # hybrid (two-ended) upload: ASCII chunks by DMA from the front, packed chunks from the back, the
+    # windows split between the two sources wherever the two meet; "0" = everything packed
+    splits = set()
+    for hybrid, threads in (("1", "2"), ("1", "16"), ("0", "16")):   # 2 packers: the DMA thread takes a real share
+        monkeypatch.setenv("TIDK_HYBRID_UPLOAD", hybrid)
+        monkeypatch.setenv("TIDK_PACK_THREADS", threads)
+        for qs, W in (([b"TTAGGG"], 10000), ([b"CCCTAA", b"AACCT"], 4321), (hym, 10000), ([b"TTAGGG"], 50000),
+                      ([b"TTAGGG"], 32768)):
+            f, r = ctx.window_counts(seq, off, W, qs)
+            h2d, d2h, was_packed = ctx.last_transfer()
+            assert was_packed
+            splits.add((hybrid, threads, h2d))
+            of, orr = O.window_counts(seq, off, W, qs, False, threads=4)
+            assert (f == of).all() and (r == orr).all(), (qs, W, hybrid, threads)
+    monkeypatch.delenv("TIDK_HYBRID_UPLOAD")
+    monkeypatch.delenv("TIDK_PACK_THREADS")
+    assert len({h for hy, th, h in splits if hy == "1"}) > 1 or any(h > seq.size // 2 for hy, th, h in splits if hy == "1")
+    # non-ASCII near the front (the part that may travel as ASCII): caught by the kernel or by the packer
+    bad0 = seq.copy()
+    bad0[77] = 0xC3
+    with pytest.raises(T.TidkCudaError) as e0:
+        ctx.window_counts(bad0, off, 10000, [b"TTAGGG"])
+    assert e0.value.code == -4
     # a query without a compile-time kernel falls back to the plain upload, same answer
     f, r = ctx.window_counts(seq, off, 10000, [b"GATTACA", b"TTAGGG"])
     of, orr = O.window_counts(seq, off, 10000, [b"GATTACA", b"TTAGGG"], False, threads=4)
