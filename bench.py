@@ -156,6 +156,14 @@ def main():
         if scale != 1.0:
             config["scale"] = scale
         cb, per_step = cpu_leg(seq, off, steps, warmup)
+        # for information: the same port sharded by record over every host core -- the
+        # reference itself never does this (search.rs:57 / finder.rs:85 are sequential loops)
+        from oracle import oracle as O
+        ncpu = os.cpu_count() or 1
+        t0 = time.perf_counter()
+        O.window_counts(seq, off, WINDOW, REPEATS, False, threads=ncpu)
+        cb["all_cores_for_information"] = {"value": seq.size / (time.perf_counter() - t0) / 1e9, "unit": UNIT, "cores": ncpu,
+                                           "sample": "whole genome, records sharded over threads, 1 pass"}
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": steps, "warmup": warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,

@@ -7,6 +7,10 @@
 #pragma once
 #include <immintrin.h>
 
+#ifndef TIDK_PACK_NT
+#define TIDK_PACK_NT 1 // non-temporal stores into the pinned staging buffers
+#endif
+
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
@@ -133,8 +137,13 @@ __attribute__((target("avx2"))) inline void pack_words2_avx2(const uint8_t *src,
         for (; w + 8 <= full; w += 8) {
             uint32_t all = 0xFFFFFFFFu;
             for (int i = 0; i < 8; i++) { TIDK_PACK_ONE(w + i, tl[i], th[i], tv[i]); all &= tv[i]; }
+#if TIDK_PACK_NT
             _mm256_stream_si256((__m256i *)(lo + w), _mm256_load_si256((const __m256i *)tl));
             _mm256_stream_si256((__m256i *)(hi + w), _mm256_load_si256((const __m256i *)th));
+#else
+            _mm256_store_si256((__m256i *)(lo + w), _mm256_load_si256((const __m256i *)tl));
+            _mm256_store_si256((__m256i *)(hi + w), _mm256_load_si256((const __m256i *)th));
+#endif
             if (all != 0xFFFFFFFFu)
                 for (int i = 0; i < 8; i++)
                     if (tv[i] != 0xFFFFFFFFu) exc.push_back(((word0 + w + i) << 32) | tv[i]);
