@@ -50,7 +50,9 @@ inline int explore_runs_device(ExploreScratch &sc, cudaStream_t st, cudaEvent_t 
     uint64_t max_chunks = 0;
     for (uint32_t sidx = 0; sidx < n_slices; sidx++) max_chunks = std::max(max_chunks, slices[sidx].len / kmin + 2);
     // TIDK_EXPLORE_HOST_POST=1 forces the struct events + host stitching path (tests exercise both)
-    const bool packed = !getenv("TIDK_EXPLORE_HOST_POST") && n_slices < (1u << kKeySliceBits) && max_chunks < (1ull << kKeyChunkBits);
+    KeyFmt fmt{bits_for(max_chunks), bits_for(n_slices > 0 ? n_slices - 1 : 0)};
+    const int key_bits = (int)fmt.total_bits(kmax);
+    const bool packed = !getenv("TIDK_EXPLORE_HOST_POST") && key_bits <= 64;
     std::vector<tidk_run> runs;
     if (n_tiles > 0) {
         cudaError_t e;
@@ -99,6 +101,7 @@ inline int explore_runs_device(ExploreScratch &sc, cudaStream_t st, cudaEvent_t 
                 job.n_events = (unsigned long long *)sc.misc + 1;
                 job.err_flags = (uint32_t *)((char *)sc.misc + 128);
                 job.packed = packed ? 1u : 0u;
+                job.fmt = fmt;
                 job.one = 1u;
                 if (kmin == 5 && kmax == 12) explore_planes_kernel<5, 12><<<grid, 256, 0, st>>>(job);
                 else explore_planes_kernel<0, 0><<<grid, 256, 0, st>>>(job);
@@ -116,6 +119,7 @@ inline int explore_runs_device(ExploreScratch &sc, cudaStream_t st, cudaEvent_t 
                 job.n_events = (unsigned long long *)sc.misc + 1;
                 job.err_flags = (uint32_t *)((char *)sc.misc + 128);
                 job.packed = packed ? 1u : 0u;
+                job.fmt = fmt;
                 explore_events_kernel<<<grid, 256, 0, st>>>(job);
             }
             cudaEventRecord(ev1, st);
@@ -134,7 +138,7 @@ inline int explore_runs_device(ExploreScratch &sc, cudaStream_t st, cudaEvent_t 
             if (ne > cap) { cap = ne; continue; } // event buffer too small: rerun with the exact size
             if (packed) { // sort, build runs, filter and compact on the device
                 cudaEventRecord(ev0, st);
-                const int prc = explore_post_device(sc, st, ne, threshold, out_runs, n_runs, &launches, err);
+                const int prc = explore_post_device(sc, st, ne, fmt, key_bits, threshold, out_runs, n_runs, &launches, err);
                 cudaEventRecord(ev1, st);
                 cudaStreamSynchronize(st);
                 float pms = 0.f;

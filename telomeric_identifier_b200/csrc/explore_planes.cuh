@@ -104,6 +104,7 @@ struct ExJob {
     unsigned long long *work_counter;
     uint32_t *err_flags;
     uint32_t packed; // events are 64-bit keys (pack_event) instead of RunEvent structs
+    KeyFmt fmt;
     uint32_t one;    // the constant 1, opaque to the compiler: multiplier of the mad.wide that does a 64-bit add on the fma pipe
 };
 
@@ -116,7 +117,7 @@ __device__ __forceinline__ void emit_event(const ExJob &job, uint32_t slice, uin
     const uint32_t type = start ? 0u : 1u, jn = joins ? 1u : 0u;
     unsigned long long idx = atomicAdd(job.n_events, 1ull);
     if (idx < job.cap_events) {
-        if (job.packed) ((uint64_t *)job.events)[idx] = pack_event(slice, k, chunk, type, jn);
+        if (job.packed) ((uint64_t *)job.events)[idx] = pack_event(job.fmt, slice, k, chunk, type, jn);
         else {
             RunEvent ev;
             ev.slice = slice; ev.k = (uint8_t)k; ev.type = (uint8_t)type; ev.joins = (uint8_t)jn; ev.pad = 0;

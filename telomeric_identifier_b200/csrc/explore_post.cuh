@@ -15,19 +15,19 @@
 
 namespace tidk {
 
-__global__ void __launch_bounds__(256) runs_from_keys_kernel(const uint64_t *keys, uint64_t n_pairs, uint64_t threshold,
+__global__ void __launch_bounds__(256) runs_from_keys_kernel(const uint64_t *keys, KeyFmt fmt, uint64_t n_pairs, uint64_t threshold,
                                                             tidk_run *runs, uint8_t *flags, uint32_t *err_flags) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pairs) return;
     uint32_t sl, k, ty, jn, sl2, k2, ty2, jn2;
     uint64_t s, e;
-    unpack_event(keys[2 * i], sl, k, s, ty, jn);
-    unpack_event(keys[2 * i + 1], sl2, k2, e, ty2, jn2);
+    unpack_event(fmt, keys[2 * i], sl, k, s, ty, jn);
+    unpack_event(fmt, keys[2 * i + 1], sl2, k2, e, ty2, jn2);
     if (ty != 0 || ty2 != 1 || sl != sl2 || k != k2 || e <= s) { atomicOr(err_flags, 4u); flags[i] = 0; return; }
     bool first = true, head = true;
     if (i > 0) {
         uint32_t psl, pk, pty, pjn; uint64_t pe;
-        unpack_event(keys[2 * i - 1], psl, pk, pe, pty, pjn);
+        unpack_event(fmt, keys[2 * i - 1], psl, pk, pe, pty, pjn);
         if (psl == sl && pk == k) {
             first = false;
             head = !(jn && s == pe + 1); // same run after upper-casing (explore.rs:324)
@@ -37,9 +37,9 @@ __global__ void __launch_bounds__(256) runs_from_keys_kernel(const uint64_t *key
     uint64_t re = e;
     for (uint64_t j = i + 1; j < n_pairs; j++) { // absorb the raw runs that join this one
         uint32_t nsl, nk, nty, njn; uint64_t ns, ne;
-        unpack_event(keys[2 * j], nsl, nk, ns, nty, njn);
+        unpack_event(fmt, keys[2 * j], nsl, nk, ns, nty, njn);
         if (nsl != sl || nk != k || !njn || ns != re + 1) break;
-        unpack_event(keys[2 * j + 1], nsl, nk, ne, nty, njn);
+        unpack_event(fmt, keys[2 * j + 1], nsl, nk, ne, nty, njn);
         re = ne;
     }
     const uint64_t start = first ? 0 : s * k; // explore.rs:297
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) runs_from_keys_kernel(const uint64_t *key
 }
 
 // keys: n_events packed keys in sc.events.  On success *out_runs (malloc) / *n_runs hold the result.
-inline int explore_post_device(ExploreScratch &sc, cudaStream_t st, uint64_t n_events, uint64_t threshold,
+inline int explore_post_device(ExploreScratch &sc, cudaStream_t st, uint64_t n_events, KeyFmt fmt, int key_bits, uint64_t threshold,
                                tidk_run **out_runs, uint64_t *n_runs, uint32_t *launches, std::string &err) {
     auto cuerr = [&](cudaError_t e, const char *what) {
         err = std::string(what) + " failed: " + cudaGetErrorString(e);
@@ -78,7 +78,7 @@ inline int explore_post_device(ExploreScratch &sc, cudaStream_t st, uint64_t n_e
     cudaError_t e;
     if ((e = grow(sc.keys2, sc.keys2_cap, n_events * 8)) != cudaSuccess) return cuerr(e, "cudaMalloc(keys)");
     size_t temp_sort = 0, temp_sel = 0;
-    cub::DeviceRadixSort::SortKeys(nullptr, temp_sort, (const uint64_t *)sc.events, (uint64_t *)sc.keys2, (int)n_events, 0, 64, st);
+    cub::DeviceRadixSort::SortKeys(nullptr, temp_sort, (const uint64_t *)sc.events, (uint64_t *)sc.keys2, (int)n_events, 0, key_bits, st);
     cub::DeviceSelect::Flagged(nullptr, temp_sel, (const tidk_run *)nullptr, (const uint8_t *)nullptr, (tidk_run *)nullptr,
                                (unsigned long long *)nullptr, (int)n_pairs, st);
     if ((e = grow(sc.temp, sc.temp_cap, std::max(temp_sort, temp_sel))) != cudaSuccess) return cuerr(e, "cudaMalloc(temp)");
@@ -86,11 +86,11 @@ inline int explore_post_device(ExploreScratch &sc, cudaStream_t st, uint64_t n_e
     if ((e = grow(sc.runs_out, sc.runs_out_cap, n_pairs * sizeof(tidk_run))) != cudaSuccess) return cuerr(e, "cudaMalloc(runs_out)");
     if ((e = grow(sc.flags, sc.flags_cap, n_pairs)) != cudaSuccess) return cuerr(e, "cudaMalloc(flags)");
     size_t tb = sc.temp_cap;
-    if ((e = cub::DeviceRadixSort::SortKeys(sc.temp, tb, (const uint64_t *)sc.events, (uint64_t *)sc.keys2, (int)n_events, 0, 64, st)) != cudaSuccess)
+    if ((e = cub::DeviceRadixSort::SortKeys(sc.temp, tb, (const uint64_t *)sc.events, (uint64_t *)sc.keys2, (int)n_events, 0, key_bits, st)) != cudaSuccess)
         return cuerr(e, "radix sort");
     uint32_t *d_err = (uint32_t *)((char *)sc.misc + 128);
     unsigned long long *d_nsel = (unsigned long long *)sc.misc + 4;
-    runs_from_keys_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, st>>>((const uint64_t *)sc.keys2, n_pairs, threshold,
+    runs_from_keys_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, st>>>((const uint64_t *)sc.keys2, fmt, n_pairs, threshold,
                                                                           (tidk_run *)sc.runs, (uint8_t *)sc.flags, d_err);
     tb = sc.temp_cap;
     if ((e = cub::DeviceSelect::Flagged(sc.temp, tb, (const tidk_run *)sc.runs, (const uint8_t *)sc.flags, (tidk_run *)sc.runs_out,
