@@ -130,9 +130,10 @@ int tidk_cuda_explore_runs_resident(tidk_ctx *ctx, const tidk_seqbuf *buf, doubl
                                     uint32_t *kernel_launches);
 void tidk_cuda_free_runs(tidk_run *runs);
 
-/* Device-time breakdown of the last explore call on ctx, in ms (CUDA events on the ctx stream):
- * out[0] = streaming scan kernel(s), out[1] = event sort + run building + compaction.
- * Writes min(n, 2) values and returns how many were written. */
+/* Time breakdown of the last explore call on ctx, in ms.  Device time (CUDA events on the ctx stream):
+ * out[0] = streaming scan kernel(s), out[1] = event sort + run building + compaction.  Host wall clock:
+ * out[2] = slice table + uploads before the scan, out[3] = post-processing including the copy of the runs.
+ * Writes min(n, 4) values and returns how many were written. */
 int tidk_cuda_last_explore_timings(const tidk_ctx *ctx, float *out, int n);
 
 #ifdef __cplusplus

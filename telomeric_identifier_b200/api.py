@@ -218,8 +218,8 @@ class Context:
     # -- explore ------------------------------------------------------------
     def _runs_out(self, runs, n) -> np.ndarray:
         if n.value:
-            raw = np.ctypeslib.as_array(C.cast(runs, C.POINTER(C.c_uint8)), shape=(n.value * C.sizeof(Run),))
-            arr = raw.view(RUN_DTYPE).copy()
+            arr = np.empty(n.value, dtype=RUN_DTYPE)
+            C.memmove(arr.ctypes.data, runs, n.value * C.sizeof(Run))  # one copy out of the library's buffer
             self._L.tidk_cuda_free_runs(runs)
             return arr
         return np.zeros(0, dtype=RUN_DTYPE)
@@ -235,10 +235,16 @@ class Context:
         return self._runs_out(runs, n)
 
     def explore_timings(self):
-        """(scan_ms, post_ms) of the last explore call."""
+        """(scan_ms, post_ms) of the last explore call (device time)."""
         out = (C.c_float * 2)()
         self._L.tidk_cuda_last_explore_timings(self._h, out, 2)
         return float(out[0]), float(out[1])
+
+    def explore_host_timings(self):
+        """(prep_ms, post_wall_ms): host wall clock before the scan / of the post-processing incl. the runs copy."""
+        out = (C.c_float * 4)()
+        self._L.tidk_cuda_last_explore_timings(self._h, out, 4)
+        return float(out[2]), float(out[3])
 
     def explore_runs_resident(self, batch: SeqBatch, distance: float, kmin: int, kmax: int,
                               threshold: int) -> np.ndarray:

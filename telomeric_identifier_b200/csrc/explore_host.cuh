@@ -1,21 +1,47 @@
 // explore_host.cuh -- host driver of the explore path: slice table, kernel choice, event
 // buffer sizing / retry, events -> runs.
 #pragma once
+#include <chrono>
+
+#include <cub/device/device_scan.cuh>
+
 #include "explore.cuh"
 #include "explore_planes.cuh"
 #include "explore_post.cuh"
 
 namespace tidk {
 
+// split_seq_by_distance (explore.rs:151-160) for every record, plus the tiles each slice is cut into
+__global__ void __launch_bounds__(256) explore_slices_kernel(const uint64_t *off, uint32_t n_records, double d, uint64_t tile,
+                                                             uint32_t extra, SliceDesc *slices, uint64_t *tiles) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r == 0) tiles[2 * (uint64_t)n_records] = 0; // the scan's last element is the total
+    if (r >= n_records) return;
+    const uint64_t beg = off[r], len = off[r + 1] - beg;
+    const double v = ceil(__dmul_rn((double)len, d)); // = split_dist() on the host: one IEEE multiply, then ceil
+    const uint64_t dist = v > 0.0 ? (uint64_t)v : 0;
+    slices[2 * (uint64_t)r] = {beg, dist};                    // explore.rs:157
+    slices[2 * (uint64_t)r + 1] = {beg + (len - dist), dist}; // explore.rs:158
+    const uint64_t span = dist == 0 ? 0 : dist + extra;
+    const uint64_t t = (span + tile - 1) / tile;
+    tiles[2 * (uint64_t)r] = t;
+    tiles[2 * (uint64_t)r + 1] = t;
+}
+
 inline int explore_runs_device(ExploreScratch &sc, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1,
                                int sm_count, const uint8_t *d_seq, const uint64_t *d_off,
                                const uint64_t *h_off, uint32_t n_records, double distance,
                                uint32_t kmin, uint32_t kmax, uint64_t threshold, tidk_run **out_runs,
                                uint64_t *n_runs, float *kernel_ms, uint32_t *kernel_launches,
-                               std::string &err, float *scan_ms = nullptr, float *post_ms = nullptr) {
+                               std::string &err, float *scan_ms = nullptr, float *post_ms = nullptr,
+                               float *host_ms = nullptr /* [0] slice table + uploads, [1] post-processing wall incl. D2H */) {
     if (scan_ms) *scan_ms = 0.f;
     if (post_ms) *post_ms = 0.f;
-    (void)d_off;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto since = [](std::chrono::steady_clock::time_point t) {
+        return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t).count();
+    };
+    if (host_ms) host_ms[0] = host_ms[1] = 0.f;
     auto cuerr = [&](cudaError_t e, const char *what) {
         err = std::string(what) + " failed: " + cudaGetErrorString(e);
         return e == cudaErrorMemoryAllocation ? TIDK_ENOMEM : TIDK_ECUDA;
@@ -29,26 +55,21 @@ inline int explore_runs_device(ExploreScratch &sc, cudaStream_t st, cudaEvent_t 
         for (uint32_t r = 0; r < n_records; r++) total += 2 * split_dist(h_off[r + 1] - h_off[r], distance);
         tile = total / kExTile < (uint64_t)sm_count * 32 ? kExTileSmall : kExTile;
     }
-    std::vector<SliceDesc> slices(n_slices);
-    std::vector<uint64_t> tile_base((size_t)n_slices + 1, 0);
-    uint64_t scanned = 0;
+    // The slice table (explore.rs:151-160) and the tile prefix sums are built on the device from the
+    // resident offsets; the host only needs the totals, which one pass over its copy of the offsets gives.
+    uint64_t scanned = 0, n_tiles = 0, max_dist = 0;
+    const uint32_t extra = planes ? kmax : 0; // the plane kernel also evaluates the kmax positions behind the slice end
     for (uint32_t r = 0; r < n_records; r++) {
         const uint64_t len = h_off[r + 1] - h_off[r];
         const uint64_t dist = split_dist(len, distance);
         if (dist > len) { err = "slice longer than record"; return TIDK_EARG; }
-        slices[2 * r] = {h_off[r], dist};                    // explore.rs:157
-        slices[2 * r + 1] = {h_off[r] + (len - dist), dist}; // explore.rs:158
-        // the plane kernel also evaluates the kmax positions behind the slice end (closing events)
-        const uint64_t span = dist == 0 ? 0 : (planes ? dist + kmax : dist);
-        const uint64_t tiles = (span + tile - 1) / tile;
-        tile_base[2 * r + 1] = tile_base[2 * r] + tiles;
-        tile_base[2 * r + 2] = tile_base[2 * r + 1] + tiles;
+        const uint64_t span = dist == 0 ? 0 : dist + extra;
+        n_tiles += 2 * ((span + tile - 1) / tile);
         scanned += 2 * dist;
+        max_dist = std::max(max_dist, dist);
     }
-    const uint64_t n_tiles = tile_base[n_slices];
     // events as sortable 64-bit keys + device-side run building when the batch fits the key layout
-    uint64_t max_chunks = 0;
-    for (uint32_t sidx = 0; sidx < n_slices; sidx++) max_chunks = std::max(max_chunks, slices[sidx].len / kmin + 2);
+    const uint64_t max_chunks = max_dist / kmin + 2;
     // TIDK_EXPLORE_HOST_POST=1 forces the struct events + host stitching path (tests exercise both)
     KeyFmt fmt{bits_for(max_chunks), bits_for(n_slices > 0 ? n_slices - 1 : 0)};
     const int key_bits = (int)fmt.total_bits(kmax);
@@ -64,12 +85,19 @@ inline int explore_runs_device(ExploreScratch &sc, cudaStream_t st, cudaEvent_t 
             if (e2 == cudaSuccess) cap = need + need / 8 + 256; else p = nullptr;
             return e2;
         };
-        if ((e = grow(sc.slices, sc.slices_cap, slices.size() * sizeof(SliceDesc))) != cudaSuccess) return cuerr(e, "cudaMalloc(slices)");
-        if ((e = grow(sc.tile_base, sc.tile_cap, tile_base.size() * 8)) != cudaSuccess) return cuerr(e, "cudaMalloc(tile_base)");
+        if ((e = grow(sc.slices, sc.slices_cap, (size_t)n_slices * sizeof(SliceDesc))) != cudaSuccess) return cuerr(e, "cudaMalloc(slices)");
+        if ((e = grow(sc.tile_base, sc.tile_cap, ((size_t)n_slices + 1) * 8)) != cudaSuccess) return cuerr(e, "cudaMalloc(tile_base)");
+        if ((e = grow(sc.tiles, sc.tiles_cap, ((size_t)n_slices + 1) * 8)) != cudaSuccess) return cuerr(e, "cudaMalloc(tiles)");
         if (planes && (e = grow(sc.items, sc.items_cap, n_tiles * sizeof(ExItem))) != cudaSuccess) return cuerr(e, "cudaMalloc(items)");
         if (!sc.misc && (e = cudaMalloc(&sc.misc, 256)) != cudaSuccess) { sc.misc = nullptr; return cuerr(e, "cudaMalloc(misc)"); }
-        if ((e = cudaMemcpyAsync(sc.slices, slices.data(), slices.size() * sizeof(SliceDesc), cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuerr(e, "H2D slices");
-        if ((e = cudaMemcpyAsync(sc.tile_base, tile_base.data(), tile_base.size() * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuerr(e, "H2D tile_base");
+        size_t scan_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr, (int)(n_slices + 1), st);
+        if ((e = grow(sc.temp, sc.temp_cap, scan_bytes)) != cudaSuccess) return cuerr(e, "cudaMalloc(temp)");
+        explore_slices_kernel<<<(n_records + 255) / 256, 256, 0, st>>>(d_off, n_records, distance, tile, extra, (SliceDesc *)sc.slices,
+                                                                       (uint64_t *)sc.tiles);
+        size_t tb0 = sc.temp_cap;
+        if ((e = cub::DeviceScan::ExclusiveSum(sc.temp, tb0, (const uint64_t *)sc.tiles, (uint64_t *)sc.tile_base, (int)(n_slices + 1), st)) != cudaSuccess)
+            return cuerr(e, "tile prefix sums");
 
         uint64_t cap = std::max<uint64_t>(1u << 16, scanned / 64);
         std::vector<RunEvent> events;
@@ -81,6 +109,7 @@ inline int explore_runs_device(ExploreScratch &sc, cudaStream_t st, cudaEvent_t 
             if ((e = cudaMemsetAsync(sc.misc, 0, 256, st)) != cudaSuccess) return cuerr(e, "memset");
             const uint64_t want = (n_tiles + 7) / 8, maxb = (uint64_t)sm_count * 8;
             const int grid = (int)std::max<uint64_t>(1, std::min(want, maxb));
+            if (host_ms && attempt == 0) host_ms[0] = since(t_begin);
             cudaEventRecord(ev0, st);
             if (planes) {
                 if (!items_ready) {
@@ -137,10 +166,12 @@ inline int explore_runs_device(ExploreScratch &sc, cudaStream_t st, cudaEvent_t 
             const uint64_t ne = h_counts[1];
             if (ne > cap) { cap = ne; continue; } // event buffer too small: rerun with the exact size
             if (packed) { // sort, build runs, filter and compact on the device
+                const auto t_post = std::chrono::steady_clock::now();
                 cudaEventRecord(ev0, st);
                 const int prc = explore_post_device(sc, st, ne, fmt, key_bits, threshold, out_runs, n_runs, &launches, err);
                 cudaEventRecord(ev1, st);
                 cudaStreamSynchronize(st);
+                if (host_ms) host_ms[1] = since(t_post);
                 float pms = 0.f;
                 cudaEventElapsedTime(&pms, ev0, ev1);
                 if (kernel_ms) *kernel_ms = ms_total + pms;

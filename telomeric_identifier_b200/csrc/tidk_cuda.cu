@@ -51,7 +51,7 @@ struct tidk_ctx {
     std::string err;
     tidk_seqbuf scratch; // staging for the host-pointer entry points
     DevBuf win_base, out_fwd, out_rev, misc, qbytes, runs, items, exc;
-    float explore_scan_ms = 0.f, explore_post_ms = 0.f;
+    float explore_scan_ms = 0.f, explore_post_ms = 0.f, explore_host_ms[2] = {0.f, 0.f};
     uint64_t last_h2d = 0, last_d2h = 0; // bytes moved by the last host-pointer window-count call
     int last_packed = 0;
     // host-packed upload path (tidk_cuda_window_counts): device planes + per-thread staging
@@ -873,7 +873,7 @@ int tidk_cuda_explore_runs_resident(tidk_ctx *ctx, const tidk_seqbuf *buf, doubl
     int rc = explore_runs_device(ctx->ex, ctx->stream, ctx->ev0, ctx->ev1, ctx->sm_count, buf->d_seq,
                                  buf->d_off, buf->h_off.data(), buf->n_records, distance, kmin, kmax,
                                  threshold, out_runs, n_runs, kernel_ms, kernel_launches, err,
-                                 &ctx->explore_scan_ms, &ctx->explore_post_ms);
+                                 &ctx->explore_scan_ms, &ctx->explore_post_ms, ctx->explore_host_ms);
     if (rc) return fail(ctx, rc, "%s", err.c_str());
     return TIDK_OK;
 }
@@ -901,9 +901,10 @@ int tidk_cuda_last_transfer(const tidk_ctx *ctx, uint64_t *h2d_bytes, uint64_t *
 
 int tidk_cuda_last_explore_timings(const tidk_ctx *ctx, float *out, int n) {
     if (!ctx || !out || n <= 0) return 0;
-    out[0] = ctx->explore_scan_ms;
-    if (n > 1) out[1] = ctx->explore_post_ms;
-    return n > 1 ? 2 : 1;
+    const float v[4] = {ctx->explore_scan_ms, ctx->explore_post_ms, ctx->explore_host_ms[0], ctx->explore_host_ms[1]};
+    const int m = n < 4 ? n : 4;
+    for (int i = 0; i < m; i++) out[i] = v[i];
+    return m;
 }
 
 } // extern "C"

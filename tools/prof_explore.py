@@ -18,8 +18,9 @@ with T.Context(0) as ctx:
             dt = time.perf_counter() - t0
             scanned = sum(2 * int(np.ceil(float(l) * 0.5)) for l in (off[1:] - off[:-1]).tolist())
             sm, pm = ctx.explore_timings()
+            hp, hq = ctx.explore_host_timings()
             print(f"C5 reads={n_reads} scanned={scanned} scan_ms={sm:.3f} post_ms={pm:.3f} "
-                  f"scan GB/s={scanned / (sm * 1e-3) / 1e9:.1f} wall_ms={dt * 1e3:.1f} runs={runs.size}")
+                  f"scan GB/s={scanned / (sm * 1e-3) / 1e9:.1f} wall_ms={dt * 1e3:.1f} host_prep_ms={hp:.2f} post_wall_ms={hq:.2f} runs={runs.size}")
         b.free()
     if "c3" in which:
         ids, seq, off = synth.config2(scale=float(os.environ.get("TIDK_BENCH_SCALE", "1.0")))
