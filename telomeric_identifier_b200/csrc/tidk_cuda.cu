@@ -816,8 +816,12 @@ int tidk_cuda_window_counts(tidk_ctx *ctx, const uint8_t *seq, const uint64_t *o
     const uint64_t total = (n_records && offsets) ? offsets[n_records] : 0;
     const char *env = getenv("TIDK_HOST_PACK");
     const int T = pack_threads();
-    // 12+ packer threads: 16 cores pack ~76 GB/s of sequence on the B200 hosts (tools/pack_bench.cpp),
-    // 8 only ~58 GB/s shared with whatever the other ranks of the job are doing -- not enough to beat DMA
+    // 12+ packer threads: 16 cores pack ~76 GB/s of sequence on the B200 hosts (tools/pack_bench.cpp).  With
+    // fewer threads per rank (2-, 4-, 8-GPU jobs sharing one host) the box is bound by its memory bandwidth,
+    // not by the bus (8 ranks: 184 GB/s of plain DMA in aggregate), and packing -- which reads the sequence
+    // and writes + re-reads the planes -- only adds to that: measured 180 vs 184 Gbases/s on 8 GPUs.
+    const char *eh = getenv("TIDK_HYBRID_UPLOAD");
+    const bool hybrid = window <= kSegBytes && (eh ? atoi(eh) != 0 : true); // windows of one 32 KiB item can be split between the sources
     bool packable = total >= (32u << 20) && seq && queries && qlens && nq > 0 && (env ? atoi(env) != 0 : T >= 12) && T >= 1;
     if (packable && !find_clade_set(queries, qlens, nq, true)) {
         uint8_t rcbuf[kMaxFastLen];
@@ -840,9 +844,6 @@ int tidk_cuda_window_counts(tidk_ctx *ctx, const uint8_t *seq, const uint64_t *o
     ctx->last_packed = packable ? 1 : 0;
     ctx->last_h2d = ((uint64_t)n_records + 1) * 16 + (packable ? 0 : total);
     if (packable) {
-        // windows of one 32 KiB item can be split between the two sources; larger ones travel packed only
-        const char *eh = getenv("TIDK_HYBRID_UPLOAD");
-        const bool hybrid = window <= kSegBytes && (eh ? atoi(eh) != 0 : true);
         int rc = seqbuf_fill(ctx, &ctx->scratch, seq, offsets, n_records, /*seq_mode=*/hybrid ? 2 : 0);
         if (rc) return rc;
         uint64_t split = 0;
