@@ -185,3 +185,44 @@ def test_dense_events_overflow_and_retry(ctx):
     off = np.array([0, n], dtype=np.uint64)
     _runs_equal(ctx, seq, off, 0.5, 1, 3, 0)
     _runs_equal(ctx, seq, off, 0.5, 1, 2, 50)
+
+
+@pytest.mark.parametrize("case", ["upper", "softmask", "n_caps"])
+def test_slice_ends_around_block_and_tile_edges(ctx, case):
+    """Slices whose length falls just below / at / just above multiples of the 1 KiB block, the 4 KiB and
+    the 16 KiB tile (the slice can end in the last block of an item or in the one before it), at every
+    start alignment, with arrays that touch the slice start, the slice end (closing event beyond it) or
+    cover the slice whole.  Exercises the one-ballot plain path next to the edge blocks."""
+    rng = np.random.default_rng(31)
+    parts = []
+    unit6, unit5 = np.frombuffer(b"TTAGGG", dtype=np.uint8), np.frombuffer(b"AACCT", dtype=np.uint8)
+    for base in (1024, 2048, 4096, 8192, 16384, 32768):
+        for delta in (-33, -12, -7, -1, 0, 1, 5, 11, 12, 13, 31, 32, 40):
+            dist = base + delta
+            n = 2 * dist - int(rng.integers(0, 2))                   # ceil(n / 2) == dist
+            s = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, n)].copy()
+            mode = int(rng.integers(0, 4))
+            if mode == 0:    # arrays at both record ends: first run of the left slice, last run of the right one
+                a = np.tile(unit6, 60)
+                s[:a.size] = a
+                s[n - a.size:] = a
+            elif mode == 1:  # array across the middle: ends the left slice, starts the right one
+                a = np.tile(unit5, 200)
+                p0 = max(0, n // 2 - 500)
+                s[p0:p0 + a.size] = a[: n - p0]
+            elif mode == 2:  # one array over the whole record
+                s[:] = np.tile(unit6, n // 6 + 1)[:n]
+            if case == "softmask":
+                p0 = int(rng.integers(0, max(1, n - 300)))
+                s[p0:p0 + 300] |= 0x20
+            elif case == "n_caps":
+                s[:37] = ord("N")
+                s[n - 41:] = ord("N")
+            parts.append(s)
+            parts.append(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, int(rng.integers(0, 40)))])  # shifts the alignment
+    off = np.zeros(len(parts) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([p.size for p in parts])
+    seq = np.concatenate(parts).astype(np.uint8)
+    _runs_equal(ctx, seq, off, 0.5, 5, 12, 0)
+    _runs_equal(ctx, seq, off, 0.5, 1, 16, 2)
+    _runs_equal(ctx, seq, off, 0.5, 5, 12, 100)
