@@ -409,8 +409,12 @@ __global__ void __launch_bounds__(256, TIDK_EX_MINB) explore_planes_kernel(const
             const uint32_t plain_lanes = __ballot_sync(0xFFFFFFFFu, lane_plain);
             // (after a block whose in-slice bases were all upper-case A/C/G/T the case / N / dirty state is
             // the initial one, whichever path evaluated it; the fast path leaves it untouched)
-            const bool fast = !edge && plain_lanes == 0xFFFFFFFFu && prev_last_plain && case_prev == 0 &&
-                              !had_n_prev && !dirty_prev;
+            const bool all_plain = plain_lanes == 0xFFFFFFFFu, calm = !had_n_prev && !dirty_prev;
+            const bool fast = !edge && all_plain && prev_last_plain && case_prev == 0 && calm;
+            // An edge block whose 32 x 32 bytes are all plain (the bytes beyond the slice edge belong to the
+            // neighbouring slice or read and usually are) only needs the slice masks on top: the word behind
+            // lane 0 is either not in the slice at all (first block of an item: validity 0) or plain.
+            const bool edge_plain = edge && all_plain && calm && (blk == 0 || (prev_last_plain && case_prev == 0));
             uint32_t inslice = 0xFFFFFFFFu;
             cur.lo = core.lo; cur.hi = core.hi;
             if (fast) {
@@ -418,6 +422,15 @@ __global__ void __launch_bounds__(256, TIDK_EX_MINB) explore_planes_kernel(const
                 prv.lo = lane_lookbehind(cur.lo, own_prev.lo, lane);
                 prv.hi = lane_lookbehind(cur.hi, own_prev.hi, lane);
                 prv.va = 0xFFFFFFFFu; prv.cs = 0u; prv.nn = 0u;
+            } else if (edge_plain) {
+                inslice = range_mask32(v_lo - prel, v_hi - prel);
+                own = range_mask32(own_lo - prel, own_hi - prel);
+                cur.va = inslice; cur.cs = 0u; cur.nn = 0u;
+                prv.lo = lane_lookbehind(cur.lo, own_prev.lo, lane);
+                prv.hi = lane_lookbehind(cur.hi, own_prev.hi, lane);
+                prv.va = lane_lookbehind(cur.va, own_prev.va, lane);
+                prv.cs = 0u; prv.nn = 0u;
+                case_prev = 0; // all upper case (the other state stays calm)
             } else {
                 uint32_t na = 0;
                 const Planes P = finish_planes(nib, core, __any_sync(0xFFFFFFFFu, core.bad != 0u), na);
