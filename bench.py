@@ -272,7 +272,16 @@ def main():
                 sm, pm = ctx.explore_timings()
                 if best is None or sm < best[0]:
                     best = (sm, pm, wall)
+            # the same call through the host-pointer entry point (pinned buffer): with d = 0.01 only the
+            # slices are uploaded, with d = 0.5 the whole genome is
+            e2e_ms = None
+            for _ in range(3):
+                t3 = time.perf_counter()
+                ctx.explore_runs(pseq, off, d, 5, 12, 100)
+                w3 = (time.perf_counter() - t3) * 1e3
+                e2e_ms = w3 if e2e_ms is None else min(e2e_ms, w3)
             explore[name] = {"scanned_bases": scanned, "scan_kernel_ms": best[0], "post_ms": best[1],
+                             "e2e_host_pointer_call_ms": e2e_ms,
                              "call_wall_ms": best[2] * 1e3, "runs": int(runs.size),
                              "scan_gbases_per_s": scanned / (best[0] * 1e-3) / 1e9,
                              "kernel": "explore_planes_kernel<5,12>", "k_range": [5, 12], "threshold": 100}

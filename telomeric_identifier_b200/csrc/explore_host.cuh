@@ -28,13 +28,25 @@ __global__ void __launch_bounds__(256) explore_slices_kernel(const uint64_t *off
     tiles[2 * (uint64_t)r + 1] = t;
 }
 
+// tiles per slice for a slice table the host laid out (compacted upload: only the slices are resident)
+__global__ void __launch_bounds__(256) explore_tiles_kernel(const SliceDesc *slices, uint32_t n_slices, uint64_t tile, uint32_t extra,
+                                                            uint64_t *tiles) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) tiles[n_slices] = 0;
+    if (i >= n_slices) return;
+    const uint64_t dist = slices[i].len;
+    const uint64_t span = dist == 0 ? 0 : dist + extra;
+    tiles[i] = (span + tile - 1) / tile;
+}
+
 inline int explore_runs_device(ExploreScratch &sc, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1,
                                int sm_count, const uint8_t *d_seq, const uint64_t *d_off,
                                const uint64_t *h_off, uint32_t n_records, double distance,
                                uint32_t kmin, uint32_t kmax, uint64_t threshold, tidk_run **out_runs,
                                uint64_t *n_runs, float *kernel_ms, uint32_t *kernel_launches,
                                std::string &err, float *scan_ms = nullptr, float *post_ms = nullptr,
-                               float *host_ms = nullptr /* [0] slice table + uploads, [1] post-processing wall incl. D2H */) {
+                               float *host_ms = nullptr /* [0] slice table + uploads, [1] post-processing wall incl. D2H */,
+                               const SliceDesc *h_slices = nullptr /* slices laid out by the caller (compacted upload) */) {
     if (scan_ms) *scan_ms = 0.f;
     if (post_ms) *post_ms = 0.f;
     const auto t_begin = std::chrono::steady_clock::now();
@@ -93,8 +105,14 @@ inline int explore_runs_device(ExploreScratch &sc, cudaStream_t st, cudaEvent_t 
         size_t scan_bytes = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr, (int)(n_slices + 1), st);
         if ((e = grow(sc.temp, sc.temp_cap, scan_bytes)) != cudaSuccess) return cuerr(e, "cudaMalloc(temp)");
-        explore_slices_kernel<<<(n_records + 255) / 256, 256, 0, st>>>(d_off, n_records, distance, tile, extra, (SliceDesc *)sc.slices,
-                                                                       (uint64_t *)sc.tiles);
+        if (h_slices) {
+            if ((e = cudaMemcpyAsync(sc.slices, h_slices, (size_t)n_slices * sizeof(SliceDesc), cudaMemcpyHostToDevice, st)) != cudaSuccess)
+                return cuerr(e, "H2D slices");
+            explore_tiles_kernel<<<(n_slices + 255) / 256, 256, 0, st>>>((const SliceDesc *)sc.slices, n_slices, tile, extra, (uint64_t *)sc.tiles);
+        } else {
+            explore_slices_kernel<<<(n_records + 255) / 256, 256, 0, st>>>(d_off, n_records, distance, tile, extra, (SliceDesc *)sc.slices,
+                                                                           (uint64_t *)sc.tiles);
+        }
         size_t tb0 = sc.temp_cap;
         if ((e = cub::DeviceScan::ExclusiveSum(sc.temp, tb0, (const uint64_t *)sc.tiles, (uint64_t *)sc.tile_base, (int)(n_slices + 1), st)) != cudaSuccess)
             return cuerr(e, "tile prefix sums");

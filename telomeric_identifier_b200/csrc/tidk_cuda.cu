@@ -884,6 +884,49 @@ int tidk_cuda_explore_runs(tidk_ctx *ctx, const uint8_t *seq, const uint64_t *of
                            uint64_t threshold, tidk_run **out_runs, uint64_t *n_runs) {
     if (!ctx) return TIDK_EARG;
     CU(ctx, cudaSetDevice(ctx->device));
+    // Compacted upload: with --distance 0.01 only 2 % of a genome is ever looked at, so only the slices
+    // cross the bus (C3: 10 MB instead of 500 MB), laid out back to back with room for the block
+    // over-read; the slice table then points into that buffer.  Per-slice copies only pay for few, long
+    // records -- read sets (d = 0.5 anyway) and small d over many records keep the whole-batch upload.
+    if (out_runs && n_runs && seq && offsets && n_records > 0 && n_records <= 4096 && distance > 0.0 && distance < 0.4 &&
+        kmin >= 1 && kmax >= kmin && kmax <= (uint32_t)kMaxExploreK) {
+        *out_runs = nullptr; *n_runs = 0;
+        if (offsets[0] != 0) return fail(ctx, TIDK_EARG, "offsets[0] must be 0");
+        std::vector<SliceDesc> sl((size_t)n_records * 2);
+        std::vector<uint64_t> src((size_t)n_records * 2);
+        uint64_t cur = 0;
+        for (uint32_t r = 0; r < n_records; r++) {
+            if (offsets[r + 1] < offsets[r]) return fail(ctx, TIDK_EARG, "offsets must be non-decreasing");
+            const uint64_t len = offsets[r + 1] - offsets[r];
+            const uint64_t dist = split_dist(len, distance);
+            if (dist > len) return fail(ctx, TIDK_EARG, "slice longer than record");
+            for (int side = 0; side < 2; side++) {
+                sl[2 * (size_t)r + side] = {cur, dist};
+                src[2 * (size_t)r + side] = side == 0 ? offsets[r] : offsets[r] + (len - dist); // explore.rs:157-158
+                cur += (dist + 2048 + 255) & ~255ull; // the scan reads whole 1 KiB blocks, up to kmax bases behind the slice
+            }
+        }
+        tidk_seqbuf *b = &ctx->scratch;
+        int rc = seqbuf_fill(ctx, b, seq, offsets, n_records, /*seq_mode=*/0); // offsets only (totals, record lengths)
+        if (rc) return rc;
+        const size_t need = (size_t)cur + kSeqPad;
+        if (need > b->seq_cap) {
+            if (b->d_seq) cudaFree(b->d_seq);
+            b->d_seq = nullptr; b->seq_cap = 0;
+            CU(ctx, cudaMalloc((void **)&b->d_seq, need));
+            b->seq_cap = need;
+        }
+        for (size_t i = 0; i < sl.size(); i++)
+            if (sl[i].len)
+                CU(ctx, cudaMemcpyAsync(b->d_seq + sl[i].beg, seq + src[i], sl[i].len, cudaMemcpyHostToDevice, ctx->stream));
+        std::string err;
+        rc = explore_runs_device(ctx->ex, ctx->stream, ctx->ev0, ctx->ev1, ctx->sm_count, b->d_seq, b->d_off, b->h_off.data(),
+                                 n_records, distance, kmin, kmax, threshold, out_runs, n_runs, nullptr, nullptr, err,
+                                 &ctx->explore_scan_ms, &ctx->explore_post_ms, ctx->explore_host_ms, sl.data());
+        b->id = ctx->next_buf_id++; // the buffer no longer holds the batch as uploaded: nothing cached may refer to it
+        if (rc) return fail(ctx, rc, "%s", err.c_str());
+        return TIDK_OK;
+    }
     int rc = seqbuf_fill(ctx, &ctx->scratch, seq, offsets, n_records);
     if (rc) return rc;
     return tidk_cuda_explore_runs_resident(ctx, &ctx->scratch, distance, kmin, kmax, threshold,
