@@ -323,13 +323,16 @@ int cmd_explore(const Args &a) { // explore::explore, explore.rs:20-149
     uint64_t n = 0;
     if (kmax >= kmin && kmin > 0) {
         ctx.ready();
-        tidk_seqbuf *buf = nullptr;
-        ctx.check(tidk_cuda_seqbuf_upload(ctx.h, fa.seq.data(), fa.offsets.data(), (uint32_t)fa.ids.size(), &buf));
         tidk_run *runs = nullptr;
         // `threshold as usize` (explore.rs:71,116): a negative i32 wraps to a huge usize
         const uint64_t thr = a.threshold < 0 ? (uint64_t)(int64_t)a.threshold : (uint64_t)a.threshold;
-        ctx.check(tidk_cuda_explore_runs_resident(ctx.h, buf, a.distance, kmin, kmax, thr, &runs, &n, &ms, &nl));
-        tidk_cuda_seqbuf_free(ctx.h, buf);
+        // the host-pointer entry point uploads only the chromosome-end slices when --distance is small
+        ctx.check(tidk_cuda_explore_runs(ctx.h, fa.seq.data(), fa.offsets.data(), (uint32_t)fa.ids.size(), a.distance, kmin, kmax,
+                                         thr, &runs, &n));
+        float tms[2] = {0.f, 0.f};
+        tidk_cuda_last_explore_timings(ctx.h, tms, 2);
+        ms = tms[0] + tms[1];
+        nl = 1;
         std::vector<std::string> labels;
         std::vector<long long> counts;
         for (uint64_t i = 0; i < n; i++) {
