@@ -1,0 +1,90 @@
+"""The host packers of the two-ended upload (host_pack.hpp) against a numpy model: lo = ASCII bit 1,
+hi = ASCII bit 2, valid = byte is one of ACGTacgt, 32 bases per word, LSB first; the two-plane variant
+reports every word whose validity plane is not all ones as (global word index << 32 | va)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def shim(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("shim") / "host_pack_shim.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, os.path.join(HERE, "host_pack_shim.cpp")])
+    L = C.CDLL(so)
+    L.shim_pack2.restype = C.c_uint64
+    return L
+
+
+def model(buf: np.ndarray, n_words: int):
+    pad = np.zeros(n_words * 32, dtype=np.uint8)
+    pad[: buf.size] = buf
+    exists = np.zeros(n_words * 32, dtype=bool)
+    exists[: buf.size] = True
+    w = (np.uint64(1) << np.arange(32, dtype=np.uint64))
+    lo = (((pad >> 1) & 1).astype(np.uint64) * exists).reshape(n_words, 32) @ w
+    hi = (((pad >> 2) & 1).astype(np.uint64) * exists).reshape(n_words, 32) @ w
+    up = pad | 0x20
+    ok = ((up == ord("a")) | (up == ord("c")) | (up == ord("g")) | (up == ord("t"))) & exists
+    va = ok.astype(np.uint64).reshape(n_words, 32) @ w
+    return lo.astype(np.uint32), hi.astype(np.uint32), va.astype(np.uint32)
+
+
+def _aligned(n_words):
+    raw = np.zeros(n_words + 16, dtype=np.uint32)
+    shift = (-raw.ctypes.data // 4) % 8
+    return raw[shift: shift + n_words]
+
+
+@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("scalar", [0, 1])
+def test_packers_match_model(shim, seed, scalar):
+    rng = np.random.default_rng(seed)
+    alphabet = [b"ACGT", b"ACGTacgt", b"ACGTN", b"ACGTNRYKMacgtn-*", b"ACGT\xc3", b"N"][seed]
+    n = int(rng.integers(1, 5000))
+    buf = np.frombuffer(alphabet, dtype=np.uint8)[rng.integers(0, len(alphabet), n)].copy()
+    if seed == 2:
+        buf[100:400] = ord("N")  # an N run: one exception per word
+    n_words = (n + 31) // 32 + int(rng.integers(0, 20))      # words beyond the data pack as invalid
+    lo, hi, va = model(buf, n_words)
+    flag = C.c_uint32(0)
+    # three planes
+    l3, h3, v3 = _aligned(n_words), _aligned(n_words), _aligned(n_words)
+    shim.shim_pack3(buf.ctypes.data, C.c_uint64(n), C.c_uint64(n_words), l3.ctypes.data, h3.ctypes.data, v3.ctypes.data,
+                    C.byref(flag), scalar)
+    assert (l3 == lo).all() and (h3 == hi).all() and (v3 == va).all()
+    assert bool(flag.value) == bool((buf >= 0x80).any())
+    # two planes + exceptions
+    l2, h2 = _aligned(n_words), _aligned(n_words)
+    exc = np.zeros(n_words + 1, dtype=np.uint64)
+    flag2 = C.c_uint32(0)
+    word0 = int(rng.integers(0, 1 << 20))
+    ne = shim.shim_pack2(buf.ctypes.data, C.c_uint64(n), C.c_uint64(n_words), l2.ctypes.data, h2.ctypes.data, C.c_uint64(word0),
+                         exc.ctypes.data, C.c_uint64(exc.size), C.byref(flag2), scalar)
+    assert (l2 == lo).all() and (h2 == hi).all()
+    want = [((word0 + i) << 32) | int(v) for i, v in enumerate(va) if v != 0xFFFFFFFF]
+    assert ne == len(want) and exc[:ne].tolist() == want      # in word order, nothing else
+    assert bool(flag2.value) == bool((buf >= 0x80).any())
+    # the device's view: a validity plane of ones with the exceptions scattered over it
+    rebuilt = np.full(n_words, 0xFFFFFFFF, dtype=np.uint32)
+    for e in exc[:ne].tolist():
+        rebuilt[(e >> 32) - word0] = e & 0xFFFFFFFF
+    assert (rebuilt == va).all()
+
+
+def test_empty_and_exact_multiples(shim):
+    for n in (0, 32, 64, 256, 257):
+        buf = np.frombuffer(b"ACGT" * 100, dtype=np.uint8)[:n].copy()
+        n_words = max(1, (n + 31) // 32)
+        lo, hi, va = model(buf, n_words)
+        l2, h2 = _aligned(n_words), _aligned(n_words)
+        exc = np.zeros(n_words + 1, dtype=np.uint64)
+        flag = C.c_uint32(0)
+        ne = shim.shim_pack2(buf.ctypes.data if n else None, C.c_uint64(n), C.c_uint64(n_words), l2.ctypes.data, h2.ctypes.data,
+                             C.c_uint64(0), exc.ctypes.data, C.c_uint64(exc.size), C.byref(flag), 0)
+        assert (l2 == lo).all() and (h2 == hi).all()
+        assert ne == int((va != 0xFFFFFFFF).sum())
