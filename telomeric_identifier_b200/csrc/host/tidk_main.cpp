@@ -36,6 +36,7 @@ struct Args {
     double distance = 0.01;
     bool print = false, verbose = false, log = false, stats = false;
     int device = 0;
+    int gpus = 1;         // search / find: shard the windows over this many devices (device, device + 1, ...)
     unsigned threads = 0; // FASTA parser threads (0 = hardware concurrency, at most 32)
 };
 
@@ -50,7 +51,7 @@ void usage() {
             "Usage: tidk search  <FASTA> -s <STRING> [-w 10000] -o <OUTPUT> -d <DIR> [-e tsv|bedgraph]\n"
             "       tidk find    <FASTA> -c <CLADE>  [-w 10000] -o <OUTPUT> -d <DIR> [-p] [--database CSV]\n"
             "       tidk explore <FASTA> [-l LENGTH | -m 5 -x 12] [-t 100] [--distance 0.01] [-v]\n"
-            "Extra: --device N, --gpu-stats (kernel time and Gbases/s on stderr)\n");
+            "Extra: --device N, --gpus N (search / find: windows sharded over N devices), --gpu-stats (kernel time and Gbases/s on stderr)\n");
 }
 
 Args parse(int argc, char **argv) {
@@ -88,6 +89,7 @@ Args parse(int argc, char **argv) {
         else if (f == "--log") a.log = true;
         else if (f == "--database") a.database = v();
         else if (f == "--device") a.device = atoi(v().c_str());
+        else if (f == "--gpus") a.gpus = atoi(v().c_str());
         else if (f == "--threads") a.threads = (unsigned)atoi(v().c_str());
         else if (f == "--gpu-stats") a.stats = true;
         else if (!f.empty() && f[0] == '-') die("unexpected argument '" + f + "'");
@@ -199,10 +201,98 @@ void write_rows(FILE *out, const Fasta &fa, uint64_t W, const std::vector<std::s
     fwrite(buf.data(), 1, buf.size(), out);
 }
 
+// Multi-GPU search / find: windows are independent (an occurrence never spans two windows,
+// search.rs:98,105-110), so the global window sequence is cut into `world` contiguous, equally long ranges
+// -- whole records where possible, long records split at multiples of W, hence no halo -- and every device
+// counts its range through its own context on its own thread.  A range is one contiguous stretch of the
+// concatenated sequence, so nothing is copied on the host; the per-range counts ([piece][query][window])
+// are placed into the global [record][query][window] arrays.  No collective: the counts are 16 B per window.
+struct Piece { uint32_t rec; uint64_t first, n; };
+
+std::vector<std::vector<Piece>> plan_shards(const std::vector<uint64_t> &offsets, uint64_t window, int world) {
+    const size_t nrec = offsets.size() - 1;
+    std::vector<uint64_t> base(nrec + 1, 0);
+    for (size_t r = 0; r < nrec; r++) {
+        const uint64_t n = offsets[r + 1] - offsets[r];
+        base[r + 1] = base[r] + n / window + (n % window != 0);
+    }
+    const uint64_t total = base[nrec];
+    std::vector<std::vector<Piece>> plans((size_t)world);
+    size_t rec = 0;
+    for (int g = 0; g < world; g++) {
+        uint64_t lo = total / world * g + std::min<uint64_t>(total % world, g);     // floor(total * g / world) without overflow
+        const uint64_t hi = total / world * (g + 1) + std::min<uint64_t>(total % world, g + 1);
+        while (lo < hi) {
+            while (base[rec + 1] <= lo) rec++;
+            const uint64_t n = std::min(hi, base[rec + 1]) - lo;
+            plans[(size_t)g].push_back({(uint32_t)rec, lo - base[rec], n});
+            lo += n;
+        }
+    }
+    return plans;
+}
+
+void sharded_counts(const Args &a, const Fasta &fa, const std::vector<const char *> &qp, const std::vector<uint32_t> &ql,
+                    std::vector<uint64_t> &f, std::vector<uint64_t> &r, float *kernel_ms_max) {
+    const int world = a.gpus;
+    const uint32_t nq = (uint32_t)qp.size();
+    const auto plans = plan_shards(fa.offsets, a.window, world);
+    std::vector<uint64_t> nw(fa.ids.size()), obase(fa.ids.size() + 1, 0);
+    for (size_t i = 0; i < fa.ids.size(); i++) {
+        const uint64_t n = fa.offsets[i + 1] - fa.offsets[i];
+        nw[i] = n / a.window + (n % a.window != 0);
+        obase[i + 1] = obase[i] + nw[i] * nq;
+    }
+    // TIDK_GPUS_SAME_DEVICE=1 (tests on a one-GPU box): every shard runs on --device
+    const bool same = getenv("TIDK_GPUS_SAME_DEVICE") && atoi(getenv("TIDK_GPUS_SAME_DEVICE")) != 0;
+    setenv("LOCAL_WORLD_SIZE", std::to_string(world).c_str(), 0); // the shards share the host cores (packer threads per context)
+    std::vector<std::string> errs((size_t)world);
+    std::vector<std::thread> th;
+    for (int g = 0; g < world; g++) {
+        th.emplace_back([&, g] {
+            const std::vector<Piece> &pieces = plans[(size_t)g];
+            if (pieces.empty()) return;
+            int ids[1] = {same ? a.device : a.device + g};
+            tidk_ctx *h = nullptr;
+            if (tidk_cuda_create(ids, 1, &h) != 0) { errs[(size_t)g] = std::string("tidk_cuda_create: ") + tidk_cuda_last_error(nullptr); return; }
+            std::vector<uint64_t> loc_off(pieces.size() + 1, 0);
+            uint64_t a0 = 0, n_loc = 0;
+            for (size_t i = 0; i < pieces.size(); i++) {
+                const Piece &p = pieces[i];
+                const uint64_t o = fa.offsets[p.rec], e = fa.offsets[p.rec + 1];
+                const uint64_t beg = o + p.first * a.window, end = std::min(o + (p.first + p.n) * a.window, e);
+                if (i == 0) a0 = beg;
+                loc_off[i + 1] = end - a0; // consecutive window ranges of consecutive records: one contiguous stretch
+                n_loc += p.n * nq;
+            }
+            std::vector<uint64_t> lf(n_loc + 1), lr(n_loc + 1);
+            const int rc = tidk_cuda_window_counts(h, fa.seq.data() + a0, loc_off.data(), (uint32_t)pieces.size(), a.window, qp.data(),
+                                                   ql.data(), nq, lf.data(), lr.data());
+            if (rc != 0) errs[(size_t)g] = std::string("tidk-cuda error ") + std::to_string(rc) + ": " + tidk_cuda_last_error(h);
+            else {
+                uint64_t pos = 0;
+                for (const Piece &p : pieces)
+                    for (uint32_t q = 0; q < nq; q++) {
+                        const uint64_t dst = obase[p.rec] + q * nw[p.rec] + p.first;
+                        memcpy(&f[dst], &lf[pos], p.n * 8);
+                        memcpy(&r[dst], &lr[pos], p.n * 8);
+                        pos += p.n;
+                    }
+            }
+            tidk_cuda_destroy(h);
+        });
+    }
+    for (auto &t : th) t.join();
+    for (const std::string &e : errs)
+        if (!e.empty()) die(e, 1);
+    if (kernel_ms_max) *kernel_ms_max = 0.f; // per-shard kernel times are not collected on this path
+}
+
 int run_counts(const Args &a, const std::vector<std::string> &queries, const std::vector<std::string> &labels,
                const std::string &path, bool header, bool bedgraph) {
     if (a.window == 0) die("window must be greater than 0", 1);
     const auto t0 = std::chrono::steady_clock::now();
+    if (a.gpus < 1 || a.gpus > 64) die("--gpus must be between 1 and 64", 1);
     Ctx ctx(a.device); // starts creating the CUDA context in the background
     Fasta fa = read_fasta(a.fasta, a.threads);
     const auto t1 = std::chrono::steady_clock::now();
@@ -220,13 +310,18 @@ int run_counts(const Args &a, const std::vector<std::string> &queries, const std
     std::vector<const char *> qp;
     std::vector<uint32_t> ql;
     for (auto &q : queries) { qp.push_back(q.c_str()); ql.push_back((uint32_t)q.size()); }
-    tidk_seqbuf *buf = nullptr;
-    ctx.check(tidk_cuda_seqbuf_upload(ctx.h, fa.seq.data(), fa.offsets.data(), (uint32_t)fa.ids.size(), &buf));
     float ms = 0;
     uint32_t nl = 0;
-    ctx.check(tidk_cuda_window_counts_resident(ctx.h, buf, a.window, qp.data(), ql.data(), (uint32_t)qp.size(), f.data(),
-                                               r.data(), &ms, &nl));
-    tidk_cuda_seqbuf_free(ctx.h, buf);
+    if (a.gpus > 1) {
+        sharded_counts(a, fa, qp, ql, f, r, &ms);
+        nl = (uint32_t)a.gpus;
+    } else {
+        tidk_seqbuf *buf = nullptr;
+        ctx.check(tidk_cuda_seqbuf_upload(ctx.h, fa.seq.data(), fa.offsets.data(), (uint32_t)fa.ids.size(), &buf));
+        ctx.check(tidk_cuda_window_counts_resident(ctx.h, buf, a.window, qp.data(), ql.data(), (uint32_t)qp.size(), f.data(),
+                                                   r.data(), &ms, &nl));
+        tidk_cuda_seqbuf_free(ctx.h, buf);
+    }
     const auto t2 = std::chrono::steady_clock::now();
     write_rows(out, fa, a.window, labels, f, r, bedgraph);
     fclose(out);

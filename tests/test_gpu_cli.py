@@ -132,3 +132,24 @@ def test_cli_log_files_and_plot_schema(genome, tmp_path):
         for col in ("window", "forward_repeat_number", "reverse_repeat_number"):
             assert 0 <= int(row[col]) < 2 ** 31
         assert row["telomeric_repeat"] == "TTAGG" and row["id"] in ids
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gpus", [2, 3, 8])
+def test_cli_sharded_over_several_contexts(genome, gpus):
+    """`--gpus N`: the windows are cut into N contiguous ranges (long records split at multiples of W),
+    one context and one thread per range; same files as the oracle's text.  On a one-GPU box every
+    range runs on device 0 (TIDK_GPUS_SAME_DEVICE=1), which exercises the plan and the merge."""
+    d, fa, ids, seq, off, seqs = genome
+    env = dict(os.environ, TIDK_GPUS_SAME_DEVICE="1")
+    out = str(d / f"g{gpus}")
+    r = subprocess.run([TIDK, "search", fa, "-s", "TTAGG", "-w", "7777", "-o", "s", "-d", out, "--gpus", str(gpus)],
+                       capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stderr
+    assert open(os.path.join(out, "s_telomeric_repeat_windows.tsv")).read() == O.search_text(ids, seqs, b"TTAGG", 7777)
+    from telomeric_identifier_b200 import clades
+    reps = clades.return_telomere_sequence("Coleoptera", DB)
+    r = subprocess.run([TIDK, "find", fa, "-c", "Coleoptera", "-o", "f", "-d", out, "--database", DB, "--gpus", str(gpus)],
+                       capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stderr
+    assert open(os.path.join(out, "f_telomeric_repeat_windows.tsv")).read() == O.find_text(ids, seqs, [x.encode() for x in reps], 10000)
