@@ -11,17 +11,19 @@
 // the end of the slice is closed (G is 0 beyond the slice: a partial chunk equals nothing).
 //
 // A lane owns 32 bases per 1 KiB block (one 256-bit load) as planes lo / hi / va
-// (va = base is A/C/G/T in any case AND inside the slice).  D_k costs three funnel shifts and
-// three LOP3 for the lane's word; the previous lane's D_k arrives by SHFL; G_k is built with
-// log2(k) shift-AND doubling steps on the (previous | current) word pair; the chunk-end phase
-// mask is a constant shifted by (q mod k).  Events are rare (4^-k per chunk on random
+// (va = base is A/C/G/T/N in any case AND inside the slice).  The mismatch plane nD_k = ~D_k costs two
+// funnel shifts and two LOP3 for the lane's word (one more of each with the validity plane); the
+// previous lane's nD_k arrives by SHFL.  G_k at the chunk ends is an all-ones-field test on D over the
+// (previous | current) word pair -- one 64-bit add, explore_k() -- with the chunk-end mask of the lane's
+// phase (q mod k) read from a small shared-memory table.  Events are rare (4^-k per chunk on random
 // sequence), so the append path is off the hot path.
 //
-// Exactness.  Plane equality is byte equality only for bases in {A,C,G,T} of uniform case.  A
-// block (and the one after it) in which any in-slice base is something else, or whose letter
-// case is mixed or differs from the previous block's, is evaluated byte-wise instead
-// (warp-uniform branch) -- N runs and soft-mask edges take the slow path, everything else the
-// fast one.
+// Exactness.  Plane equality on lo / hi is byte equality only for bases in {A,C,G,T} of uniform case.
+// Blocks are sorted (warp-uniformly) into: plain (one ballot: interior, all upper-case A/C/G/T) ->
+// lo / hi only; clean at a slice or tile edge -> + validity plane; mixed case, case change or N present
+// -> + case and N planes (then plane equality is byte equality for A/C/G/T/N in either case); any other
+// byte (IUPAC codes, gaps) in this or the previous block -> the block's owned chunk ends are evaluated
+// byte-wise while the plane path only keeps its carries consistent.
 #pragma once
 #include <cstddef>
 
