@@ -82,9 +82,10 @@ int tidk_cuda_window_counts(tidk_ctx *ctx, const uint8_t *seq, const uint64_t *o
                             uint64_t *out_rev);
 
 /* Bytes that crossed PCIe in the last tidk_cuda_window_counts call on ctx, and whether the sequence
- * went up as host-packed bit-planes (3 bits per base; taken when every query has a compile-time
- * plane kernel, the batch is >= 32 MiB and >= 12 host threads are available -- TIDK_HOST_PACK=0/1 and
- * TIDK_PACK_THREADS override) or as ASCII. */
+ * went up (at least in part) as host-packed bit-planes -- 2 bits per base plus validity exceptions for
+ * the chunks packed from the back, ASCII by DMA for the chunks taken from the front; taken when every
+ * query has a compile-time plane kernel, the batch is >= 32 MiB and >= 12 host threads are available
+ * (TIDK_HOST_PACK=0/1, TIDK_HYBRID_UPLOAD=0 and TIDK_PACK_THREADS override) -- or entirely as ASCII. */
 int tidk_cuda_last_transfer(const tidk_ctx *ctx, uint64_t *h2d_bytes, uint64_t *d2h_bytes, int *host_packed);
 
 /* Same computation on a sequence batch that is already resident in HBM

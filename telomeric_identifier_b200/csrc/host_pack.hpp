@@ -1,9 +1,10 @@
 // host_pack.hpp -- host-side packing of ASCII bases into the three bit-planes the matchers use
 // (lo = ASCII bit 1, hi = ASCII bit 2, va = byte is one of ACGTacgt), 32 bases per word, LSB first.
 //
-// Used by the host-pointer entry point tidk_cuda_window_counts: PCIe (about 55 GB/s) is the
-// end-to-end bound, so 3 bits per base cross the bus instead of 8.  The exact same planes are what
-// planes.cuh builds in registers from ASCII on the device path.
+// Used by the host-pointer entry point tidk_cuda_window_counts: moving the bases (PCIe about 55 GB/s,
+// host memory bandwidth) is the end-to-end bound, so 2 bits per base plus the rare validity exceptions
+// cross the bus instead of 8 (pack_words2; pack_words is the three-plane form).  The exact same planes
+// are what planes.cuh builds in registers from ASCII on the device path.
 #pragma once
 #include <immintrin.h>
 

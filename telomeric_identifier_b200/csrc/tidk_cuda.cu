@@ -647,12 +647,13 @@ int tidk_cuda_window_counts_resident(tidk_ctx *ctx, const tidk_seqbuf *buf, uint
 }
 
 // ---- host-packed upload ----------------------------------------------------------------------
-// PCIe is the end-to-end bound of the host-pointer entry point (about 55 GB/s against a kernel that
-// streams 5 TB/s), so when every query has a plane kernel the host packs the sequence into the
-// three planes the matchers use (3 bits per base, host_pack.hpp) and only those cross the bus.
-// T worker threads each own a stream and a two-slot pinned staging ring; a worker packs one 4 MiB
-// chunk of sequence (1.5 MiB of planes, contiguous on the device) into a free slot and issues its
-// copy, so packing and DMA overlap without any cross-thread barrier.
+// Getting the bases to the device is the end-to-end bound of the host-pointer entry point (about 55 GB/s
+// against a kernel that streams 5 TB/s), so when every query has a plane kernel the host packs the
+// sequence into the lo / hi planes the matchers use (2 bits per base, host_pack.hpp) and reports the rare
+// words whose validity plane is not all ones; only those cross the bus.  T worker threads each own a
+// stream and a two-slot pinned staging ring; a worker packs one 4 MiB chunk of sequence (1 MiB of planes,
+// contiguous on the device) into a free slot and issues its copy, so packing and DMA overlap without any
+// cross-thread barrier.  See upload_packed() for the two-ended variant that is actually used.
 // validity-plane exceptions of the host packer: (global word index << 32 | va) -> the va third of the word's chunk
 __global__ void va_scatter_kernel(uint32_t *packed, const uint64_t *exc, uint64_t n) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -279,7 +279,8 @@ struct RuntimeMatcher {
 // ------------------------------------------------------------------ sources
 // Where a lane's 32 bases come from.  AsciiSource: the sequence as uploaded (1 byte per base), turned
 // into planes in registers.  PackedSource: planes built on the host by the upload path of
-// tidk_cuda_window_counts (3 bits per base cross PCIe instead of 8), read as three coalesced words.
+// tidk_cuda_window_counts (lo / hi cross PCIe, the validity plane is rebuilt on the device from its
+// exceptions), read as three coalesced words.
 struct AsciiSource {
     struct Raw { uint32_t w[8]; };
     using Cooked = Nibbles;

@@ -286,7 +286,7 @@ def test_full_size_c1_c4_properties(ctx, cfg, query):
 
 def test_host_packed_upload_path(ctx, monkeypatch):
     """tidk_cuda_window_counts packs the sequence into bit-planes on the host when every query has a
-    compile-time kernel (3 bits per base cross PCIe instead of 8).  Same counts as the oracle; queries
+    compile-time kernel (2 bits per base + validity exceptions cross PCIe instead of 8).  Same counts as the oracle; queries
     without a compile-time kernel, and small inputs, keep taking the plain upload."""
     import os
     import telomeric_identifier_b200 as T
