@@ -6,6 +6,7 @@
 // (SURVEY.md section 2).
 #include <sys/stat.h>
 
+#include <algorithm>
 #include <cerrno>
 #include <charconv>
 #include <ctime>
@@ -36,7 +37,7 @@ struct Args {
     double distance = 0.01;
     bool print = false, verbose = false, log = false, stats = false;
     int device = 0;
-    int gpus = 1;         // search / find: shard the windows over this many devices (device, device + 1, ...)
+    int gpus = 1;         // shard the windows (search / find) or the records (explore) over this many devices (device, device + 1, ...)
     unsigned threads = 0; // FASTA parser threads (0 = hardware concurrency, at most 32)
 };
 
@@ -51,7 +52,7 @@ void usage() {
             "Usage: tidk search  <FASTA> -s <STRING> [-w 10000] -o <OUTPUT> -d <DIR> [-e tsv|bedgraph]\n"
             "       tidk find    <FASTA> -c <CLADE>  [-w 10000] -o <OUTPUT> -d <DIR> [-p] [--database CSV]\n"
             "       tidk explore <FASTA> [-l LENGTH | -m 5 -x 12] [-t 100] [--distance 0.01] [-v]\n"
-            "Extra: --device N, --gpus N (search / find: windows sharded over N devices), --gpu-stats (kernel time and Gbases/s on stderr)\n");
+            "Extra: --device N, --gpus N (search / find: windows, explore: records sharded over N devices), --gpu-stats (kernel time and Gbases/s on stderr)\n");
 }
 
 Args parse(int argc, char **argv) {
@@ -288,6 +289,62 @@ void sharded_counts(const Args &a, const Fasta &fa, const std::vector<const char
     if (kernel_ms_max) *kernel_ms_max = 0.f; // per-shard kernel times are not collected on this path
 }
 
+// explore --gpus N: whole records in N contiguous groups balanced by scanned bases (2 * ceil(d * len) per record,
+// explore.rs:151-160), one context and one thread per device, each scanning its stretch of the parsed sequence in
+// place.  A record's runs do not depend on other records and every shard returns them in (k, record, slice, start)
+// order, so the reference's arrival order is the shards in record order within each k: a stable sort on k.
+std::vector<tidk_run> sharded_explore(const Args &a, const Fasta &fa, uint32_t kmin, uint32_t kmax, uint64_t thr) {
+    const int world = a.gpus;
+    const size_t nrec = fa.ids.size();
+    std::vector<uint64_t> cost(nrec + 1, 0);
+    for (size_t i = 0; i < nrec; i++) {
+        const double v = std::ceil((double)(fa.offsets[i + 1] - fa.offsets[i]) * a.distance);
+        cost[i + 1] = cost[i] + 2 * (v > 0 ? (uint64_t)v : 0) + 1; // + 1: empty records still spread out
+    }
+    std::vector<size_t> cut((size_t)world + 1, nrec);
+    cut[0] = 0;
+    for (int g = 1; g < world; g++) {
+        const uint64_t want = cost[nrec] / (uint64_t)world * (uint64_t)g;
+        cut[(size_t)g] = (size_t)(std::lower_bound(cost.begin(), cost.end(), want) - cost.begin());
+        if (cut[(size_t)g] < cut[(size_t)g - 1]) cut[(size_t)g] = cut[(size_t)g - 1];
+        if (cut[(size_t)g] > nrec) cut[(size_t)g] = nrec;
+    }
+    const bool same = getenv("TIDK_GPUS_SAME_DEVICE") && atoi(getenv("TIDK_GPUS_SAME_DEVICE")) != 0;
+    setenv("LOCAL_WORLD_SIZE", std::to_string(world).c_str(), 0);
+    std::vector<std::string> errs((size_t)world);
+    std::vector<std::vector<tidk_run>> part((size_t)world);
+    std::vector<std::thread> th;
+    for (int g = 0; g < world; g++) {
+        th.emplace_back([&, g] {
+            const size_t r0 = cut[(size_t)g], r1 = cut[(size_t)g + 1];
+            if (r1 <= r0) return;
+            int ids[1] = {same ? a.device : a.device + g};
+            tidk_ctx *h = nullptr;
+            if (tidk_cuda_create(ids, 1, &h) != 0) { errs[(size_t)g] = std::string("tidk_cuda_create: ") + tidk_cuda_last_error(nullptr); return; }
+            std::vector<uint64_t> loc_off(r1 - r0 + 1);
+            for (size_t i = r0; i <= r1; i++) loc_off[i - r0] = fa.offsets[i] - fa.offsets[r0];
+            tidk_run *runs = nullptr;
+            uint64_t n = 0;
+            const int rc = tidk_cuda_explore_runs(h, fa.seq.data() + fa.offsets[r0], loc_off.data(), (uint32_t)(r1 - r0), a.distance, kmin,
+                                                  kmax, thr, &runs, &n);
+            if (rc != 0) errs[(size_t)g] = std::string("tidk-cuda error ") + std::to_string(rc) + ": " + tidk_cuda_last_error(h);
+            else {
+                part[(size_t)g].assign(runs, runs + n);
+                for (tidk_run &r : part[(size_t)g]) r.record += (uint32_t)r0;
+                tidk_cuda_free_runs(runs);
+            }
+            tidk_cuda_destroy(h);
+        });
+    }
+    for (auto &t : th) t.join();
+    for (const std::string &e : errs)
+        if (!e.empty()) die(e, 1);
+    std::vector<tidk_run> all;
+    for (auto &p : part) all.insert(all.end(), p.begin(), p.end());
+    std::stable_sort(all.begin(), all.end(), [](const tidk_run &x, const tidk_run &y) { return x.k < y.k; });
+    return all;
+}
+
 int run_counts(const Args &a, const std::vector<std::string> &queries, const std::vector<std::string> &labels,
                const std::string &path, bool header, bool bedgraph) {
     if (a.window == 0) die("window must be greater than 0", 1);
@@ -416,18 +473,27 @@ int cmd_explore(const Args &a) { // explore::explore, explore.rs:20-149
     float ms = 0;
     uint32_t nl = 0;
     uint64_t n = 0;
+    if (a.gpus < 1 || a.gpus > 64) die("--gpus must be between 1 and 64", 1);
     if (kmax >= kmin && kmin > 0) {
         ctx.ready();
-        tidk_run *runs = nullptr;
         // `threshold as usize` (explore.rs:71,116): a negative i32 wraps to a huge usize
         const uint64_t thr = a.threshold < 0 ? (uint64_t)(int64_t)a.threshold : (uint64_t)a.threshold;
-        // the host-pointer entry point uploads only the chromosome-end slices when --distance is small
-        ctx.check(tidk_cuda_explore_runs(ctx.h, fa.seq.data(), fa.offsets.data(), (uint32_t)fa.ids.size(), a.distance, kmin, kmax,
-                                         thr, &runs, &n));
-        float tms[2] = {0.f, 0.f};
-        tidk_cuda_last_explore_timings(ctx.h, tms, 2);
-        ms = tms[0] + tms[1];
-        nl = 1;
+        std::vector<tidk_run> sharded;
+        tidk_run *runs = nullptr;
+        if (a.gpus > 1) {
+            sharded = sharded_explore(a, fa, kmin, kmax, thr);
+            runs = sharded.data();
+            n = sharded.size();
+            nl = (uint32_t)a.gpus;
+        } else {
+            // the host-pointer entry point uploads only the chromosome-end slices when --distance is small
+            ctx.check(tidk_cuda_explore_runs(ctx.h, fa.seq.data(), fa.offsets.data(), (uint32_t)fa.ids.size(), a.distance, kmin, kmax,
+                                             thr, &runs, &n));
+            float tms[2] = {0.f, 0.f};
+            tidk_cuda_last_explore_timings(ctx.h, tms, 2);
+            ms = tms[0] + tms[1];
+            nl = 1;
+        }
         std::vector<std::string> labels;
         std::vector<long long> counts;
         for (uint64_t i = 0; i < n; i++) {
@@ -442,7 +508,7 @@ int cmd_explore(const Args &a) { // explore::explore, explore.rs:20-149
             labels.push_back(lab);
             counts.push_back((long long)((r.end - r.start) / r.k));
         }
-        tidk_cuda_free_runs(runs);
+        if (a.gpus <= 1) tidk_cuda_free_runs(runs);
         rows = estimates(labels, counts);
     }
     fprintf(stderr, "[+]\tFinished searching genome\n[+]\tGenerating output\n");

@@ -122,13 +122,18 @@ struct StaticMatcher {
     __host__ __device__ static constexpr int fwd_at(int j) { return (int)((F >> (2 * j)) & 3); }
     __device__ __forceinline__ static void reset(Carry &c) { c.e[0] = c.e[1] = c.e[2] = c.e[3] = 0; }
 
+    // The forward chain is ANDed from the motif's FIRST base (largest shift) down, the reverse-complement
+    // chain from its LAST base (shift 0) up: motifs of one clade that share a prefix (AACCC..., six of
+    // length 11 in Hymenoptera) then share the leading sub-chains of both strands, which the compiler
+    // merges when several motifs are fused into one kernel.
     template <int S>
     __device__ __forceinline__ static void steps(const uint32_t (&e)[4], const uint32_t (&p)[4],
                                                  uint32_t &mf, uint32_t &mr) {
         if constexpr (S < L) {
-            constexpr int fb = fwd_at(L - 1 - S); // forward letter S bases behind the end
+            constexpr int SF = L - 1 - S;         // forward strand: shift of the motif's base S
+            constexpr int fb = fwd_at(S);         // forward letter SF bases behind the end
             constexpr int rb = 3 - fwd_at(S);     // revcomp letter S bases behind the end
-            mf &= S == 0 ? e[fb] : __funnelshift_l(p[fb], e[fb], S);
+            mf &= SF == 0 ? e[fb] : __funnelshift_l(p[fb], e[fb], SF);
             mr &= S == 0 ? e[rb] : __funnelshift_l(p[rb], e[rb], S);
             steps<S + 1>(e, p, mf, mr);
         }

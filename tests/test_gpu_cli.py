@@ -153,3 +153,9 @@ def test_cli_sharded_over_several_contexts(genome, gpus):
                        capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stderr
     assert open(os.path.join(out, "f_telomeric_repeat_windows.tsv")).read() == O.find_text(ids, seqs, [x.encode() for x in reps], 10000)
+    # explore: whole records in N contiguous groups, run lists merged in (k, record) order -- the table is the
+    # same text as on one device (the estimator depends on the arrival order, explore.rs:395-423)
+    r = subprocess.run([TIDK, "explore", fa, "--minimum", "5", "--maximum", "12", "-t", "20", "--distance", "0.05",
+                        "--gpus", str(gpus)], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == O.explore_text(seqs, 0.05, 5, 12, 20, literal=True)
