@@ -149,7 +149,6 @@ inline int explore_runs_device(ExploreScratch &sc, cudaStream_t st, cudaEvent_t 
                 job.err_flags = (uint32_t *)((char *)sc.misc + 128);
                 job.packed = packed ? 1u : 0u;
                 job.fmt = fmt;
-                job.one = 1u;
                 if (kmin == 5 && kmax == 12) explore_planes_kernel<5, 12><<<grid, 256, 0, st>>>(job);
                 else explore_planes_kernel<0, 0><<<grid, 256, 0, st>>>(job);
             } else {

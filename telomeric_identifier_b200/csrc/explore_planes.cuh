@@ -107,7 +107,6 @@ struct ExJob {
     uint32_t *err_flags;
     uint32_t packed; // events are 64-bit keys (pack_event) instead of RunEvent structs
     KeyFmt fmt;
-    uint32_t one;    // the constant 1, opaque to the compiler: multiplier of the mad.wide that does a 64-bit add on the fma pipe
 };
 
 // Events are appended with one atomicAdd each on a global counter (the compiler aggregates the lanes
@@ -145,11 +144,12 @@ __device__ __forceinline__ bool chunks_equal_upper(const uint8_t *t, int k, uint
     return true;
 }
 
-// per-CTA stash of the run boundaries found in the current block: [k - 1][thread]
+// per-CTA stash of the run boundaries found in the current block: [k - KBASE][thread].  The hot loop only stores
+// the boundary word of a k and sets the k's bit in a per-lane mask; whether a boundary starts or ends a run is
+// read back from the sequence on the (rare) emission path.
 template <int ROWS> // one row per k of the kernel's range (row = k - KBASE)
 struct EvStash {
     uint32_t ev[ROWS][256];
-    uint32_t z[ROWS][256];
 };
 
 struct Planes3 {
@@ -208,16 +208,14 @@ __device__ __forceinline__ uint32_t phase_step(uint32_t p) {
 //     Z = ~((nD & nH) + nH) & D & H  =  ~(sum | nD | nH)
 // Inside a field the addend nH is all ones below the top bit, so the sum carries into the top bit exactly
 // when some low position mismatches; both addends are 0 at the top bit, so no carry leaves a field.  Two
-// LOP3, one 64-bit add, two LOP3 -- regardless of K.  The 64-bit add is issued as mad.wide.u32
-// (low word * 1 + nH) plus one 32-bit add: it runs on the fma pipe, which this kernel leaves idle, instead
-// of an add / compare / select chain on the saturated alu pipe.
+// LOP3, one 64-bit add, two LOP3 -- regardless of K.
 //
 // s8 = 8 * s, s = bit position (0..K-1) of the first chunk end in the PREVIOUS word (see PhaseConst).
 // FULL: also require equal letter case and equal N-ness (mixed-case blocks, soft-mask edges, N runs):
 // with the case and N planes in the comparison, plane equality is byte equality for A/C/G/T/N in either
 // case, so only blocks with other bytes (IUPAC codes, gaps) need the byte-wise evaluation.
 template <int K, int ROW, bool WITH_VA, bool FULL, bool EMIT, class Stash>
-__device__ __forceinline__ void explore_k(Stash &stash, const HTable &htab, uint32_t one, uint32_t &any_ev,
+__device__ __forceinline__ void explore_k(Stash &stash, const HTable &htab, uint32_t &any_ev,
                                           const Planes3 &cur, const Planes3 &prv, uint32_t &carry_nd, uint32_t m31,
                                           int src_lane, uint32_t s8, uint32_t own) {
     const uint32_t lo_k = __funnelshift_l(prv.lo, cur.lo, K);
@@ -231,11 +229,9 @@ __device__ __forceinline__ void explore_k(Stash &stash, const HTable &htab, uint
     if (!EMIT) return; // special block: only the carries are kept consistent
     const unsigned long long nh = *reinterpret_cast<const unsigned long long *>(reinterpret_cast<const char *>(&htab.nh[K - 1][0]) + s8);
     const uint32_t nh_lo = (uint32_t)nh, nh_hi = (uint32_t)(nh >> 32);
-    // high word first (a plain 32-bit add; a carry out of bit 63 is dropped either way), then the low word
-    // and its carry in one mad.wide
-    const unsigned long long addend = ((unsigned long long)(nh_hi + (nd_hi & nh_hi)) << 32) | nh_lo;
-    unsigned long long sum;
-    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(sum) : "r"(nd_lo & nh_lo), "r"(one), "l"(addend));
+    // one 64-bit add: IADD3 + IMAD.X (issuing the low word as mad.wide to reach the fma pipe was tried: ptxas
+    // splits it into IMAD.WIDE + IADD3 + IADD3.X, one instruction more)
+    const unsigned long long sum = (((unsigned long long)(nd_hi & nh_hi) << 32) | (nd_lo & nh_lo)) + nh;
     const uint32_t sum_hi = (uint32_t)(sum >> 32);
     // x = ~Z; a funnel shift commutes with the complement, so the boundary test needs no NOT
     const uint32_t x_lo = (uint32_t)sum | nd_lo | nh_lo;
@@ -246,12 +242,15 @@ __device__ __forceinline__ void explore_k(Stash &stash, const HTable &htab, uint
     // after every k made the hot loop three times larger than the instruction cache
     // x is 1 off the chunk ends in both words, so only chunk ends survive the XOR; interior blocks
     // (WITH_VA false) own every position of the word
-    const uint32_t ev = WITH_VA ? (x_hi ^ x_prev) & own : (x_hi ^ x_prev);
+    // ev = (x_hi ^ x_prev) [& own] and "ev != 0" out of ONE LOP3 (lop3 with a predicate result), then a
+    // predicated OR of the k's bit: which k to look at afterwards
+    uint32_t ev;
+    asm("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, 0, 0;\n\t"
+        "lop3.or.b32 %0|p, %2, %3, %4, %5, q;\n\t"
+        "@p or.b32 %1, %1, %6;\n\t}"
+        : "=r"(ev), "+r"(any_ev)
+        : "r"(x_hi), "r"(x_prev), "r"(WITH_VA ? own : 0xFFFFFFFFu), "n"(0x28), "n"(1u << ROW)); // 0x28 = (a ^ b) & c
     stash.ev[ROW][threadIdx.x] = ev;
-    if (ev) { // predicated store + predicated move: nothing on the alu pipe
-        stash.z[ROW][threadIdx.x] = ~x_hi;
-        any_ev = 1u;
-    }
 }
 
 // byte-wise evaluation of this lane's owned chunk ends (special blocks).  x0 = (rel0 mod k) + offset
@@ -478,7 +477,7 @@ __global__ void __launch_bounds__(256, TIDK_EX_MINB) explore_planes_kernel(const
             const uint32_t xoff = (uint32_t)prel; // < 2^15
 #define TIDK_EXK(K, VA, CS, EM)                                                                   \
     if ((KMIN > 0) ? (K >= KMIN && K <= KMAX) : (job.kmin <= K && K <= job.kmax)) {              \
-        explore_k<K, (K >= KBASE ? K - KBASE : 0), VA, CS, EM>(stash, htab, job.one, any_ev, cur, prv, carry_nd[K - 1], m31, src_lane,  \
+        explore_k<K, (K >= KBASE ? K - KBASE : 0), VA, CS, EM>(stash, htab, any_ev, cur, prv, carry_nd[K - 1], m31, src_lane,  \
                                  phase_byte<KBASE, NREG, K>(ph), own);                             \
     }
 #define TIDK_EXALL(VA, CS, EM)                                                                    \
@@ -501,11 +500,9 @@ __global__ void __launch_bounds__(256, TIDK_EX_MINB) explore_planes_kernel(const
 #undef TIDK_EXALL
 #undef TIDK_EXK
             if (any_ev) { // rare: this lane found run boundaries in this block
-                const uint32_t k0 = KMIN > 0 ? KMIN : job.kmin, k1 = KMIN > 0 ? KMAX : job.kmax;
-                for (uint32_t k = k0; k <= k1; k++) {
+                for (uint32_t rows = any_ev; rows; rows &= rows - 1) { // only the k that have one
+                    const uint32_t k = (uint32_t)KBASE + (uint32_t)(__ffs(rows) - 1);
                     uint32_t ev = stash.ev[k - KBASE][threadIdx.x];
-                    if (!ev) continue;
-                    const uint32_t z = stash.z[k - KBASE][threadIdx.x];
                     while (ev) {
                         const int b = __ffs(ev) - 1;
                         ev &= ev - 1;
@@ -514,7 +511,9 @@ __global__ void __launch_bounds__(256, TIDK_EX_MINB) explore_planes_kernel(const
                         // a run start in a uniform-case block never joins the previous chunk (they differ
                         // as bytes and share the case, so they differ after upper-casing too); with mixed
                         // case the two chunks are compared after upper-casing (explore.rs:212 vs :324)
-                        const bool start = (z >> b) & 1u;
+                        // the boundary says G[q] != G[q - k]; which of the two holds is read from the slice
+                        // (the planes' verdict and the bytes agree wherever the plane path emits)
+                        const bool start = g_bytes(t, m, (int)k, p + b);
                         const bool joins = need_cs && start && j > 0 && chunks_equal_upper(t, (int)k, j);
                         emit_event(job, slice, k, j, start, joins);
                     }

@@ -99,6 +99,37 @@ def test_config5_scaled(ctx):
     _runs_equal(ctx, seq, off, 0.5, 5, 12, 100)
 
 
+def test_config5_in_batches(ctx):
+    """C5's batched launch path: a read set handed over in batches of records.  A read's runs do not depend on
+    the other reads and every call returns (k, record, slice, start) order, so per k the batches' run lists
+    concatenated in batch order are the run list of the whole set (explore.rs:88-121 walks the records once
+    per k); the table from the merged runs is the oracle's table."""
+    from telomeric_identifier_b200 import synth
+    from telomeric_identifier_b200.explore import run_labels
+    from telomeric_identifier_b200.hostlogic import estimates, period
+    ids, seq, off = synth.config5(n_reads=1500)
+    want, wlabels = O.explore_runs(seq, off, 0.5, 5, 12, 100, period_filter=False)
+    parts = []
+    for r0, r1 in ((0, 400), (400, 401), (401, 1100), (1100, 1500)):
+        lo = off[r0:r1 + 1] - off[r0]
+        got = ctx.explore_runs(seq[int(off[r0]):int(off[r1])], lo, 0.5, 5, 12, 100)
+        got["record"] += np.uint32(r0)
+        parts.append(got)
+    merged = np.concatenate(parts)
+    merged = merged[np.argsort(merged["k"], kind="stable")]
+    assert merged.size == want.size
+    for f in ("record", "slice", "k", "first", "start", "end"):
+        assert (merged[f] == want[f]).all(), f
+    labels = run_labels(seq, off, 0.5, merged)
+    assert labels == wlabels
+    keep = [i for i, l in enumerate(labels) if period(l) >= 3]
+    counts = [(int(merged[i]["end"]) - int(merged[i]["start"])) // int(merged[i]["k"]) for i in keep]
+    rows = estimates([labels[i] for i in keep], counts)
+    seqs = [seq[int(off[i]):int(off[i + 1])].tobytes() for i in range(len(ids))]
+    text = O.explore_text(seqs, 0.5, 5, 12, 100, literal=False).splitlines()[1:]
+    assert [f"{k.decode()}\t{c}" for k, c in rows] == text
+
+
 def test_explore_errors(ctx):
     import telomeric_identifier_b200 as T
     seq = np.frombuffer(b"ACGT" * 50, dtype=np.uint8)
