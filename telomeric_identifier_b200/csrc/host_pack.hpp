@@ -14,6 +14,7 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 
 namespace tidk {
@@ -162,11 +163,74 @@ __attribute__((target("avx2"))) inline void pack_words2_avx2(const uint8_t *src,
         pack_words2_scalar(src + full * 32, n_bytes - full * 32, n_words - full, lo + full, hi + full, word0 + full, exc, nonascii);
 }
 
+// AVX-512 (BW + VBMI) form: 64 bases per step.  A plane is ONE instruction -- vptestmb against the bit's mask
+// yields the 64 plane bits as a mask register -- and validity is a 64-entry table lookup on the low six bits of
+// the lower-cased byte (vpermb) plus one compare: about 8 uops per 64 bases against about 28 for the AVX2 form,
+// so a packer thread is bound by memory instead of the movemask port.
+template <class Vec>
+__attribute__((target("avx512f,avx512bw,avx512vbmi"))) inline void pack_words2_avx512(const uint8_t *src, size_t n_bytes,
+                                                                                     size_t n_words, uint32_t *lo, uint32_t *hi,
+                                                                                     uint64_t word0, Vec &exc, uint32_t *nonascii) {
+    const size_t full = n_bytes / 32 < n_words ? n_bytes / 32 : n_words;
+    alignas(64) uint8_t tab[64];
+    memset(tab, 0, sizeof tab); // 0 never equals a byte with bit 5 set
+    tab['a' & 63] = 'a'; tab['c' & 63] = 'c'; tab['g' & 63] = 'g'; tab['t' & 63] = 't';
+    const __m512i table = _mm512_load_si512(tab);
+    const __m512i c02 = _mm512_set1_epi8(0x02), c04 = _mm512_set1_epi8(0x04), c20 = _mm512_set1_epi8(0x20);
+    __m512i acc = _mm512_setzero_si512(); // OR of all bytes: bit 7 set somewhere <=> a non-ASCII byte
+    size_t w = 0;
+    // sixteen words (512 bases) per round: the eight 64-bit plane pieces of a round are gathered in a register and
+    // leave as ONE full-line non-temporal store per plane (8-byte streaming stores were tried: partially filled
+    // write-combining buffers get evicted and the memory controller serialises every thread at 6 GB/s)
+    if ((((uintptr_t)lo | (uintptr_t)hi) & 63) == 0) {
+        for (; w + 16 <= full; w += 16) {
+            __m512i gl = _mm512_setzero_si512(), gh = _mm512_setzero_si512();
+            uint64_t okall = ~0ull;
+            uint64_t oks[8];
+#define TIDK_PACK_STEP(I)                                                                                  \
+    do {                                                                                                   \
+        const __m512i v = _mm512_loadu_si512(src + (w + 2 * (I)) * 32);                                    \
+        const uint64_t l = _mm512_test_epi8_mask(v, c02), h = _mm512_test_epi8_mask(v, c04);               \
+        const __m512i u = _mm512_or_si512(v, c20);                                                         \
+        oks[I] = _mm512_cmpeq_epi8_mask(u, _mm512_permutexvar_epi8(u, table));                             \
+        okall &= oks[I];                                                                                   \
+        acc = _mm512_or_si512(acc, v);                                                                     \
+        gl = _mm512_mask_set1_epi64(gl, (__mmask8)(1u << (I)), (long long)l);                              \
+        gh = _mm512_mask_set1_epi64(gh, (__mmask8)(1u << (I)), (long long)h);                              \
+    } while (0)
+            TIDK_PACK_STEP(0); TIDK_PACK_STEP(1); TIDK_PACK_STEP(2); TIDK_PACK_STEP(3);
+            TIDK_PACK_STEP(4); TIDK_PACK_STEP(5); TIDK_PACK_STEP(6); TIDK_PACK_STEP(7);
+#undef TIDK_PACK_STEP
+#if TIDK_PACK_NT
+            _mm512_stream_si512((__m512i *)(lo + w), gl);
+            _mm512_stream_si512((__m512i *)(hi + w), gh);
+#else
+            _mm512_store_si512((__m512i *)(lo + w), gl);
+            _mm512_store_si512((__m512i *)(hi + w), gh);
+#endif
+            if (okall != ~0ull)
+                for (int i = 0; i < 8; i++) {
+                    const uint64_t ok = oks[i];
+                    if ((uint32_t)ok != 0xFFFFFFFFu) exc.push_back(((word0 + w + 2 * i) << 32) | (uint32_t)ok);
+                    if ((uint32_t)(ok >> 32) != 0xFFFFFFFFu) exc.push_back(((word0 + w + 2 * i + 1) << 32) | (uint32_t)(ok >> 32));
+                }
+        }
+        _mm_sfence();
+    }
+    if (_mm512_movepi8_mask(acc)) *nonascii = 1;
+    if (w < n_words)
+        pack_words2_scalar(src + w * 32, n_bytes - w * 32, n_words - w, lo + w, hi + w, word0 + w, exc, nonascii);
+}
+
 template <class Vec>
 inline void pack_words2(const uint8_t *src, size_t n_bytes, size_t n_words, uint32_t *lo, uint32_t *hi, uint64_t word0,
                         Vec &exc, uint32_t *nonascii) {
     static const bool avx2 = __builtin_cpu_supports("avx2");
-    if (avx2) pack_words2_avx2(src, n_bytes, n_words, lo, hi, word0, exc, nonascii);
+    // TIDK_PACK_ISA=avx2 keeps the AVX2 form on an AVX-512 machine (measurements)
+    static const bool avx512 = __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vbmi") &&
+                               !(getenv("TIDK_PACK_ISA") && strcmp(getenv("TIDK_PACK_ISA"), "avx2") == 0);
+    if (avx512) pack_words2_avx512(src, n_bytes, n_words, lo, hi, word0, exc, nonascii);
+    else if (avx2) pack_words2_avx2(src, n_bytes, n_words, lo, hi, word0, exc, nonascii);
     else pack_words2_scalar(src, n_bytes, n_words, lo, hi, word0, exc, nonascii);
 }
 

@@ -11,6 +11,8 @@
 #include <cstring>
 #include <new>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -43,6 +45,65 @@ struct tidk_seqbuf {
     uint64_t id = 0; // changes whenever the contents change (invalidates ctx-side caches)
 };
 
+// Packer threads of the host-packed upload, kept parked between calls: creating and joining 15 threads per call
+// cost a few hundred microseconds of a 5 ms call.  run(n, fn) executes fn(1) .. fn(n - 1) on the pool and fn(0)
+// on the caller, and returns when all are done.
+class PackPool {
+  public:
+    ~PackPool() {
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (std::thread &t : th_) t.join();
+    }
+    void run(int n, const std::function<void(int)> &fn) {
+        if (n <= 1) { fn(0); return; }
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            while ((int)th_.size() < n - 1) {
+                const int id = (int)th_.size() + 1;
+                th_.emplace_back([this, id] { loop(id); });
+            }
+            fn_ = &fn; active_ = n; pending_ = n - 1; gen_++;
+        }
+        cv_.notify_all();
+        fn(0);
+        std::unique_lock<std::mutex> g(mu_);
+        done_.wait(g, [this] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+
+  private:
+    void loop(int id) {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(int)> *fn = nullptr;
+            {
+                std::unique_lock<std::mutex> g(mu_);
+                cv_.wait(g, [&] { return stop_ || gen_ != seen; });
+                if (stop_) return;
+                seen = gen_;
+                if (id >= active_) continue; // this round uses fewer threads
+                fn = fn_;
+            }
+            (*fn)(id);
+            {
+                std::lock_guard<std::mutex> g(mu_);
+                if (--pending_ == 0) done_.notify_one();
+            }
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    std::vector<std::thread> th_;
+    const std::function<void(int)> *fn_ = nullptr;
+    uint64_t gen_ = 0;
+    int active_ = 0, pending_ = 0;
+    bool stop_ = false;
+};
+
 struct tidk_ctx {
     int device = 0;
     int sm_count = 148;
@@ -58,6 +119,7 @@ struct tidk_ctx {
     DevBuf packed;
     struct PackLane { cudaStream_t st = nullptr; cudaEvent_t ev[2] = {nullptr, nullptr}; uint32_t *pin = nullptr; };
     std::vector<PackLane> pack_lanes;
+    PackPool pack_pool;
     cudaStream_t dma_st = nullptr;  // hybrid upload: the ASCII share of the sequence
     static constexpr int kDmaDepth = 4;
     cudaEvent_t dma_ev[kDmaDepth] = {nullptr, nullptr, nullptr, nullptr};
@@ -769,10 +831,7 @@ static int upload_packed(tidk_ctx *ctx, const uint8_t *seq, uint64_t total, int 
         if (cudaStreamSynchronize(L.st) != cudaSuccess) cuda_err = 1;
         if (flag) nonascii = 1;
     };
-    std::vector<std::thread> th;
-    for (int t = 1; t < T; t++) th.emplace_back(worker, t);
-    worker(0);
-    for (auto &x : th) x.join();
+    ctx->pack_pool.run(T, worker);
     if (allow_ascii && cudaStreamSynchronize(ctx->dma_st) != cudaSuccess) cuda_err = 1;
     if (cuda_err) return fail(ctx, TIDK_ECUDA, "packed upload failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (nonascii)

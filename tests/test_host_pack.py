@@ -1,4 +1,4 @@
-"""The host packers of the two-ended upload (host_pack.hpp) against a numpy model: lo = ASCII bit 1,
+"""The host packers of the two-ended upload (host_pack.hpp; scalar, AVX2 and AVX-512 forms) against a numpy model: lo = ASCII bit 1,
 hi = ASCII bit 2, valid = byte is one of ACGTacgt, 32 bases per word, LSB first; the two-plane variant
 reports every word whose validity plane is not all ones as (global word index << 32 | va)."""
 import ctypes as C
@@ -41,7 +41,7 @@ def _aligned(n_words):
 
 
 @pytest.mark.parametrize("seed", range(6))
-@pytest.mark.parametrize("scalar", [0, 1])
+@pytest.mark.parametrize("scalar", [0, 1, 2])  # dispatch (AVX-512 if present) / scalar / AVX2
 def test_packers_match_model(shim, seed, scalar):
     rng = np.random.default_rng(seed)
     alphabet = [b"ACGT", b"ACGTacgt", b"ACGTN", b"ACGTNRYKMacgtn-*", b"ACGT\xc3", b"N"][seed]
@@ -55,7 +55,7 @@ def test_packers_match_model(shim, seed, scalar):
     # three planes
     l3, h3, v3 = _aligned(n_words), _aligned(n_words), _aligned(n_words)
     shim.shim_pack3(buf.ctypes.data, C.c_uint64(n), C.c_uint64(n_words), l3.ctypes.data, h3.ctypes.data, v3.ctypes.data,
-                    C.byref(flag), scalar)
+                    C.byref(flag), int(scalar == 1))
     assert (l3 == lo).all() and (h3 == hi).all() and (v3 == va).all()
     assert bool(flag.value) == bool((buf >= 0x80).any())
     # two planes + exceptions

@@ -21,6 +21,7 @@ int main() {
     struct V { uint32_t *p; uint32_t *data() { return p; } } lo{lo_b + mis}, hi{hi_b + mis}, va{va_b + mis};
     printf("avx2=%d avx512bw=%d hw_threads=%u\n", __builtin_cpu_supports("avx2"), __builtin_cpu_supports("avx512bw"),
            std::thread::hardware_concurrency());
+    const bool three = getenv("PACK_BENCH_PLANES") && atoi(getenv("PACK_BENCH_PLANES")) == 3;
     for (int T : {1, 2, 4, 8, 16, 32}) {
         double best = 1e9;
         for (int rep = 0; rep < 3; rep++) {
@@ -30,7 +31,13 @@ int main() {
                 th.emplace_back([&, t] {
                     uint32_t f = 0;
                     size_t w0 = nw * t / T, w1 = nw * (t + 1) / T;
-                    tidk::pack_words(s.data() + w0 * 32, (w1 - w0) * 32, w1 - w0, lo.data() + w0, hi.data() + w0, va.data() + w0, &f);
+                    // PACK_BENCH_PLANES=3: the three-plane form; default: two planes + validity exceptions (what the upload
+                    // uses; TIDK_PACK_ISA=avx2 keeps the AVX2 form on an AVX-512 machine)
+                    if (three) tidk::pack_words(s.data() + w0 * 32, (w1 - w0) * 32, w1 - w0, lo.data() + w0, hi.data() + w0, va.data() + w0, &f);
+                    else {
+                        std::vector<uint64_t> exc;
+                        tidk::pack_words2(s.data() + w0 * 32, (w1 - w0) * 32, w1 - w0, lo.data() + w0, hi.data() + w0, w0, exc, &f);
+                    }
                 });
             for (auto &q : th) q.join();
             double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
