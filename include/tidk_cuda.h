@@ -88,6 +88,10 @@ int tidk_cuda_window_counts(tidk_ctx *ctx, const uint8_t *seq, const uint64_t *o
  * (TIDK_HOST_PACK=0/1, TIDK_HYBRID_UPLOAD=0 and TIDK_PACK_THREADS override) -- or entirely as ASCII. */
 int tidk_cuda_last_transfer(const tidk_ctx *ctx, uint64_t *h2d_bytes, uint64_t *d2h_bytes, int *host_packed);
 
+/* Device time (CUDA events around the counting kernels, ms) and number of kernel launches of the last
+ * window-count call on ctx, host-pointer or resident (diagnostics: the drivers' --gpu-stats line). */
+int tidk_cuda_last_kernel_time(const tidk_ctx *ctx, float *kernel_ms, uint32_t *kernel_launches);
+
 /* Same computation on a sequence batch that is already resident in HBM
  * (uploaded once, queried many times: several clades, tsv + bedgraph, ...).
  * kernel_ms (nullable) receives the device time of the counting kernels of this

@@ -18,7 +18,7 @@ EXPORTS = [
     "tidk_cuda_host_alloc", "tidk_cuda_host_free", "tidk_cuda_window_counts",
     "tidk_cuda_seqbuf_upload", "tidk_cuda_seqbuf_free", "tidk_cuda_window_counts_resident",
     "tidk_cuda_explore_runs", "tidk_cuda_explore_runs_resident", "tidk_cuda_free_runs",
-    "tidk_cuda_last_explore_timings", "tidk_cuda_last_transfer",
+    "tidk_cuda_last_explore_timings", "tidk_cuda_last_transfer", "tidk_cuda_last_kernel_time",
 ]
 
 
@@ -86,6 +86,8 @@ def load_library():
     L.tidk_cuda_free_runs.restype = None
     L.tidk_cuda_last_transfer.argtypes = [vp, u64p, u64p, C.POINTER(C.c_int)]
     L.tidk_cuda_last_transfer.restype = C.c_int
+    L.tidk_cuda_last_kernel_time.argtypes = [vp, C.POINTER(C.c_float), u32p]
+    L.tidk_cuda_last_kernel_time.restype = C.c_int
     L.tidk_cuda_last_explore_timings.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
     L.tidk_cuda_last_explore_timings.restype = C.c_int
     _LIB = L
@@ -184,6 +186,9 @@ class Context:
         self._check(self._L.tidk_cuda_window_counts(self._h, seq.ctypes.data, offsets.ctypes.data,
                                                     len(offsets) - 1, window, qa, ql, nq,
                                                     fwd.ctypes.data, rev.ctypes.data))
+        ms, nl = C.c_float(0), C.c_uint32(0)
+        self._L.tidk_cuda_last_kernel_time(self._h, C.byref(ms), C.byref(nl))
+        self.last_kernel_ms, self.last_kernel_launches = ms.value, nl.value
         return fwd[:total], rev[:total]
 
     def last_transfer(self):

@@ -11,6 +11,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <functional>
@@ -20,10 +21,40 @@
 
 namespace tidk_host {
 
+// The concatenated sequence.  Not a std::vector: resize() would zero-fill (and page-fault) hundreds of megabytes on
+// one thread before the parser's workers overwrite them; here the pages are first touched by the workers, in parallel.
+class ByteBuf {
+  public:
+    ByteBuf() = default;
+    ByteBuf(const ByteBuf &) = delete;
+    ByteBuf &operator=(const ByteBuf &) = delete;
+    ByteBuf(ByteBuf &&o) noexcept : p_(o.p_), n_(o.n_) { o.p_ = nullptr; o.n_ = 0; }
+    ByteBuf &operator=(ByteBuf &&o) noexcept {
+        if (this != &o) { free(p_); p_ = o.p_; n_ = o.n_; o.p_ = nullptr; o.n_ = 0; }
+        return *this;
+    }
+    ~ByteBuf() { free(p_); }
+    void resize_uninitialized(size_t n) {
+        free(p_);
+        p_ = n ? (uint8_t *)malloc(n) : nullptr;
+        if (n && !p_) throw std::runtime_error("out of memory for the sequence");
+        n_ = n;
+    }
+    uint8_t *data() { return p_; }
+    const uint8_t *data() const { return p_; }
+    size_t size() const { return n_; }
+    const uint8_t *begin() const { return p_; }
+    const uint8_t *end() const { return p_ + n_; }
+
+  private:
+    uint8_t *p_ = nullptr;
+    size_t n_ = 0;
+};
+
 struct Fasta {
     std::vector<std::string> ids;
     std::vector<uint64_t> offsets{0};
-    std::vector<uint8_t> seq;
+    ByteBuf seq;
 };
 
 inline bool ends_with(const std::string &s, const char *suf) {
@@ -122,7 +153,7 @@ inline void parse_fasta_buffer(const char *data, size_t size, Fasta &fa, unsigne
         total += c.seq_total;
     }
     if (started) fa.offsets.push_back(total);
-    fa.seq.resize(total);
+    fa.seq.resize_uninitialized(total);
     auto pass2 = [&](const Chunk &c) {
         const char *p = data + c.beg, *end = data + c.end;
         uint8_t *out = fa.seq.data() + c.out;
@@ -162,14 +193,14 @@ inline Fasta read_fasta(const std::string &path, unsigned threads = 0) {
     struct stat st;
     if (fstat(fd, &st) != 0) { close(fd); throw std::runtime_error("cannot stat " + path); }
     if (st.st_size == 0) { close(fd); return fa; }
-    void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+    // (no MAP_POPULATE: it maps the whole file on this one thread; the workers' first reads fault their own parts in)
+    void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
     if (m == MAP_FAILED) { // pipes, odd filesystems: fall back to read()
         close(fd);
         const std::vector<char> data = slurp(path);
         parse_fasta_buffer(data.data(), data.size(), fa, threads);
         return fa;
     }
-    madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
     try {
         parse_fasta_buffer((const char *)m, (size_t)st.st_size, fa, threads);
     } catch (...) {

@@ -115,6 +115,8 @@ struct tidk_ctx {
     float explore_scan_ms = 0.f, explore_post_ms = 0.f, explore_host_ms[2] = {0.f, 0.f};
     uint64_t last_h2d = 0, last_d2h = 0; // bytes moved by the last host-pointer window-count call
     int last_packed = 0;
+    float last_kernel_ms = 0.f;     // device time / launches of the counting kernels of the last window-count call
+    uint32_t last_kernel_launches = 0;
     // host-packed upload path (tidk_cuda_window_counts): device planes + per-thread staging
     DevBuf packed;
     struct PackLane { cudaStream_t st = nullptr; cudaEvent_t ev[2] = {nullptr, nullptr}; uint32_t *pin = nullptr; };
@@ -693,7 +695,9 @@ static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint3
     ctx->counters_dirty = false;
     const uint32_t h_err = *(volatile uint32_t *)ctx->h_flags;
     if (h_err) ctx->h_flags[0] = 0; // flags are sticky: clear after reporting (the stream is idle here)
-    if (kernel_ms) CU(ctx, cudaEventElapsedTime(kernel_ms, ctx->ev0, ctx->ev1));
+    CU(ctx, cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev0, ctx->ev1));
+    ctx->last_kernel_launches = launches;
+    if (kernel_ms) *kernel_ms = ctx->last_kernel_ms;
     if (kernel_launches) *kernel_launches = launches;
     if (h_err & 1u)
         return fail(ctx, TIDK_ENONASCII, "sequence contains a byte >= 0x80 (the reference fails in str::from_utf8, search.rs:107)");
@@ -1000,6 +1004,13 @@ int tidk_cuda_last_transfer(const tidk_ctx *ctx, uint64_t *h2d_bytes, uint64_t *
     if (h2d_bytes) *h2d_bytes = ctx->last_h2d;
     if (d2h_bytes) *d2h_bytes = ctx->last_d2h;
     if (host_packed) *host_packed = ctx->last_packed;
+    return TIDK_OK;
+}
+
+int tidk_cuda_last_kernel_time(const tidk_ctx *ctx, float *kernel_ms, uint32_t *kernel_launches) {
+    if (!ctx) return TIDK_EARG;
+    if (kernel_ms) *kernel_ms = ctx->last_kernel_ms;
+    if (kernel_launches) *kernel_launches = ctx->last_kernel_launches;
     return TIDK_OK;
 }
 
