@@ -469,8 +469,11 @@ int cmd_explore(const Args &a) { // explore::explore, explore.rs:20-149
         for (long long k = a.minimum; k <= a.maximum; k++) fprintf(stderr, "[+]\t\tFinding telomeric repeat length: %lld\n", k);
         kmin = (uint32_t)a.minimum; kmax = (uint32_t)a.maximum;
     }
+    const auto t0 = std::chrono::steady_clock::now();
     Ctx ctx(a.device); // starts creating the CUDA context in the background
     Fasta fa = read_fasta(a.fasta, a.threads);
+    const auto t1 = std::chrono::steady_clock::now();
+    auto t_ready = t1, t_call = t1;
     std::vector<std::pair<std::string, long long>> rows;
     float ms = 0;
     uint32_t nl = 0;
@@ -478,6 +481,7 @@ int cmd_explore(const Args &a) { // explore::explore, explore.rs:20-149
     if (a.gpus < 1 || a.gpus > 64) die("--gpus must be between 1 and 64", 1);
     if (kmax >= kmin && kmin > 0) {
         ctx.ready();
+        t_ready = std::chrono::steady_clock::now();
         // `threshold as usize` (explore.rs:71,116): a negative i32 wraps to a huge usize
         const uint64_t thr = a.threshold < 0 ? (uint64_t)(int64_t)a.threshold : (uint64_t)a.threshold;
         std::vector<tidk_run> sharded;
@@ -496,6 +500,7 @@ int cmd_explore(const Args &a) { // explore::explore, explore.rs:20-149
             ms = tms[0] + tms[1];
             nl = 1;
         }
+        t_call = std::chrono::steady_clock::now();
         std::vector<std::string> labels;
         std::vector<long long> counts;
         for (uint64_t i = 0; i < n; i++) {
@@ -516,7 +521,13 @@ int cmd_explore(const Args &a) { // explore::explore, explore.rs:20-149
     fprintf(stderr, "[+]\tFinished searching genome\n[+]\tGenerating output\n");
     printf("canonical_repeat_unit\tcount_repeat_runs_gt_%lld\n", a.threshold); // explore.rs:140
     for (auto &r : rows) printf("%s\t%lld\n", r.first.c_str(), r.second);
-    if (a.stats) fprintf(stderr, "{\"runs\": %llu, \"kernel_ms\": %.4f, \"kernel_launches\": %u}\n", (unsigned long long)n, ms, nl);
+    if (a.stats) {
+        const auto t3 = std::chrono::steady_clock::now();
+        auto s = [](auto x, auto y) { return std::chrono::duration<double>(y - x).count(); };
+        fprintf(stderr, "{\"runs\": %llu, \"kernel_ms\": %.4f, \"kernel_launches\": %u, \"parse_s\": %.3f, \"wait_for_context_s\": %.3f, "
+                        "\"upload_and_scan_s\": %.3f, \"labels_and_estimator_s\": %.3f}\n",
+                (unsigned long long)n, ms, nl, s(t0, t1), s(t1, t_ready), s(t_ready, t_call), s(t_call, t3));
+    }
     if (a.log) // lib.rs:119-190: written to the current directory
         write_log_file("tidk-explore.log",
                        std::string("tidk version: ") + kTidkVersion + "\nLog information for output files: printed to STDOUT\nDate: " +

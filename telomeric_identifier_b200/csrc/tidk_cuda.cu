@@ -173,6 +173,79 @@ int ensure(tidk_ctx *ctx, DevBuf &b, size_t bytes) {
 
 constexpr size_t kSeqPad = 8192; // zeroed bytes behind the data: block loads never leave the buffer
 
+static int pack_threads() {
+    if (const char *e = getenv("TIDK_PACK_THREADS")) return atoi(e);
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw == 0) hw = 1;
+    unsigned share = 1; // ranks of one torchrun job share the host cores
+    if (const char *lws = getenv("LOCAL_WORLD_SIZE")) share = (unsigned)atoi(lws) > 0 ? (unsigned)atoi(lws) : 1;
+    unsigned t = hw / share;
+    return (int)(t > 32 ? 32 : t);
+}
+
+
+// one stream, two events and a two-slot pinned staging ring (2 x 1.5 MiB: the lo / hi planes of a 4 MiB chunk) per
+// host thread of the upload paths
+static int ensure_lanes(tidk_ctx *ctx, int T) {
+    const size_t ring_bytes = 2 * (3ull * kPackWords * 4);
+    if ((int)ctx->pack_lanes.size() < T) {
+        const size_t old = ctx->pack_lanes.size();
+        ctx->pack_lanes.resize(T);
+        for (size_t i = old; i < (size_t)T; i++) {
+            tidk_ctx::PackLane &L = ctx->pack_lanes[i];
+            CU(ctx, cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
+            CU(ctx, cudaEventCreateWithFlags(&L.ev[0], cudaEventDisableTiming));
+            CU(ctx, cudaEventCreateWithFlags(&L.ev[1], cudaEventDisableTiming));
+            CU(ctx, cudaHostAlloc((void **)&L.pin, ring_bytes, cudaHostAllocDefault));
+        }
+    }
+    return TIDK_OK;
+}
+
+// Host -> device copy of a sequence.  A pinned source goes by DMA straight from the caller's buffer.  From pageable
+// memory (a parsed FASTA in a malloc'ed buffer, a plain numpy array) one cudaMemcpy is staged by the driver on a single
+// thread at about 10 GB/s; here the host threads of the upload paths stage it themselves -- each copies 512 KiB pieces
+// into its own pinned ring and sends them on its own stream -- which runs at the rate of the bus.
+// Returns with the copy complete (pageable) or enqueued on ctx->stream (pinned / small).
+static int upload_bytes(tidk_ctx *ctx, uint8_t *dst, const uint8_t *src, uint64_t n) {
+    bool pageable = false;
+    static const bool allow = !(getenv("TIDK_STAGED_UPLOAD") && atoi(getenv("TIDK_STAGED_UPLOAD")) == 0);
+    const int T = pack_threads();
+    if (allow && T >= 4 && n >= (64ull << 20)) {
+        cudaPointerAttributes a{};
+        if (cudaPointerGetAttributes(&a, src) == cudaSuccess) pageable = a.type == cudaMemoryTypeUnregistered;
+        else cudaGetLastError();
+    }
+    if (!pageable) {
+        CU(ctx, cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, ctx->stream));
+        return TIDK_OK;
+    }
+    int rc;
+    if ((rc = ensure_lanes(ctx, T))) return rc;
+    constexpr uint64_t kPiece = 512u << 10;
+    const uint64_t n_pieces = (n + kPiece - 1) / kPiece;
+    std::atomic<uint64_t> next{0};
+    std::atomic<int> cuda_err{0};
+    auto worker = [&](int t) {
+        cudaSetDevice(ctx->device);
+        tidk_ctx::PackLane &L = ctx->pack_lanes[t];
+        for (int slot = 0;; slot ^= 1) {
+            const uint64_t c = next.fetch_add(1);
+            if (c >= n_pieces) break;
+            if (cudaEventSynchronize(L.ev[slot]) != cudaSuccess) { cuda_err = 1; break; } // the slot's previous copy is done
+            uint8_t *stage = (uint8_t *)L.pin + (size_t)slot * kPiece;
+            const uint64_t b0 = c * kPiece, len = n - b0 < kPiece ? n - b0 : kPiece;
+            memcpy(stage, src + b0, len);
+            if (cudaMemcpyAsync(dst + b0, stage, len, cudaMemcpyHostToDevice, L.st) != cudaSuccess ||
+                cudaEventRecord(L.ev[slot], L.st) != cudaSuccess) { cuda_err = 1; break; }
+        }
+        if (cudaStreamSynchronize(L.st) != cudaSuccess) cuda_err = 1;
+    };
+    ctx->pack_pool.run(T, worker);
+    if (cuda_err) return fail(ctx, TIDK_ECUDA, "staged upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return TIDK_OK;
+}
+
 // seq_mode 1: copy the sequence; 0: offsets only; 2: allocate the sequence buffer, copy nothing (the hybrid
 // upload fills the part of it that travels as ASCII)
 int seqbuf_fill(tidk_ctx *ctx, tidk_seqbuf *b, const uint8_t *seq, const uint64_t *offsets,
@@ -205,8 +278,9 @@ int seqbuf_fill(tidk_ctx *ctx, tidk_seqbuf *b, const uint8_t *seq, const uint64_
     b->n_records = n_records;
     b->total = total;
     b->id = ctx->next_buf_id++;
+    int rc_up = 0;
     if (copy_seq) {
-        if (total) CU(ctx, cudaMemcpyAsync(b->d_seq, seq, total, cudaMemcpyHostToDevice, ctx->stream));
+        if (total && (rc_up = upload_bytes(ctx, b->d_seq, seq, total))) return rc_up;
         CU(ctx, cudaMemsetAsync(b->d_seq + total, 0, kSeqPad, ctx->stream));
     }
     CU(ctx, cudaMemcpyAsync(b->d_off, b->h_off.data(), off_need, cudaMemcpyHostToDevice, ctx->stream));
@@ -728,16 +802,6 @@ __global__ void va_scatter_kernel(uint32_t *packed, const uint64_t *exc, uint64_
     packed[(word >> tidk::kPackShift) * (3ull * tidk::kPackWords) + 2ull * tidk::kPackWords + (word & (tidk::kPackWords - 1))] = (uint32_t)e;
 }
 
-static int pack_threads() {
-    if (const char *e = getenv("TIDK_PACK_THREADS")) return atoi(e);
-    unsigned hw = std::thread::hardware_concurrency();
-    if (hw == 0) hw = 1;
-    unsigned share = 1; // ranks of one torchrun job share the host cores
-    if (const char *lws = getenv("LOCAL_WORLD_SIZE")) share = (unsigned)atoi(lws) > 0 ? (unsigned)atoi(lws) : 1;
-    unsigned t = hw / share;
-    return (int)(t > 32 ? 32 : t);
-}
-
 //
 // Two-ended ("hybrid") upload.  The packers are bound by the host's memory bandwidth (about 76 GB/s of
 // sequence on 16 vCPUs) while the bus would still have room, and a plain DMA of ASCII needs no CPU at
@@ -759,17 +823,7 @@ static int upload_packed(tidk_ctx *ctx, const uint8_t *seq, uint64_t total, int 
     // the validity plane (third part of every chunk) is all ones except where the packers say otherwise
     CU(ctx, cudaMemset2DAsync((char *)ctx->packed.p + 2ull * kPackWords * 4, chunk_bytes, 0xFF, (size_t)kPackWords * 4, n_chunks, ctx->stream));
     std::vector<std::vector<uint64_t>> exc((size_t)T);
-    if ((int)ctx->pack_lanes.size() < T) {
-        const size_t old = ctx->pack_lanes.size();
-        ctx->pack_lanes.resize(T);
-        for (size_t i = old; i < (size_t)T; i++) {
-            tidk_ctx::PackLane &L = ctx->pack_lanes[i];
-            CU(ctx, cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
-            CU(ctx, cudaEventCreateWithFlags(&L.ev[0], cudaEventDisableTiming));
-            CU(ctx, cudaEventCreateWithFlags(&L.ev[1], cudaEventDisableTiming));
-            CU(ctx, cudaHostAlloc((void **)&L.pin, 2 * chunk_bytes, cudaHostAllocDefault));
-        }
-    }
+    if ((rc = ensure_lanes(ctx, T))) return rc;
     if (allow_ascii && !ctx->dma_st) {
         CU(ctx, cudaStreamCreateWithFlags(&ctx->dma_st, cudaStreamNonBlocking));
         for (int i = 0; i < tidk_ctx::kDmaDepth; i++)
