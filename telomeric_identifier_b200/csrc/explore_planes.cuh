@@ -116,7 +116,10 @@ struct ExJob {
 __device__ __forceinline__ void emit_event(const ExJob &job, uint32_t slice, uint32_t k, uint64_t chunk,
                                            bool start, bool joins) {
     const uint32_t type = start ? 0u : 1u, jn = joins ? 1u : 0u;
-    unsigned long long idx = atomicAdd(job.n_events, 1ull);
+    // a plain atom: one or two lanes of a warp get here together, the compiler's warp-aggregated atomicAdd (vote,
+    // leader election, popc, shuffle) costs more than the second atomic it saves
+    unsigned long long idx;
+    asm volatile("atom.global.add.u64 %0, [%1], 1;" : "=l"(idx) : "l"(job.n_events) : "memory");
     if (idx < job.cap_events) {
         if (job.packed) ((uint64_t *)job.events)[idx] = pack_event(job.fmt, slice, k, chunk, type, jn);
         else {
@@ -290,6 +293,13 @@ __device__ __forceinline__ uint32_t phase_byte(const uint32_t (&ph)[NREG]) {
     else
         return 0u;
 }
+
+// q / k for a q that IS a multiple of k (chunk end + 1), k <= 16, quotient < 2^32: shift out k's twos, multiply by the
+// inverse of its odd part modulo 2^32.  Two constant-bank reads, a shift and a multiply.
+__constant__ uint32_t kExactInv[17] = {0u, 1u, 1u, 0xAAAAAAABu, 1u, 0xCCCCCCCDu, 0xAAAAAAABu, 0xB6DB6DB7u, 1u,
+                                       0x38E38E39u, 0xCCCCCCCDu, 0xBA2E8BA3u, 0xAAAAAAABu, 0xC4EC4EC5u, 0xB6DB6DB7u, 0xEEEEEEEFu, 1u};
+__constant__ uint32_t kExactShift[17] = {0u, 0u, 1u, 0u, 2u, 0u, 1u, 0u, 3u, 0u, 1u, 0u, 2u, 0u, 1u, 0u, 4u};
+__device__ __forceinline__ uint32_t div_exact(uint32_t q, uint32_t k) { return (q >> kExactShift[k]) * kExactInv[k]; }
 
 // q / k for k <= 16 with the divisor known per case: a multiply and a shift instead of the generic division
 __device__ __forceinline__ uint32_t div_small(uint32_t q, uint32_t k) {
@@ -507,13 +517,17 @@ __global__ void __launch_bounds__(256, TIDK_EX_MINB) explore_planes_kernel(const
                         const int b = __ffs(ev) - 1;
                         ev &= ev - 1;
                         const uint64_t q1 = (uint64_t)(p + b) + 1; // chunk end + 1, a multiple of k
-                        const uint64_t j = (q1 >> 32 ? q1 / k : (uint64_t)div_small((uint32_t)q1, k)) - 2;
+                        const uint64_t j = (q1 >> 32 ? q1 / k : (uint64_t)div_exact((uint32_t)q1, k)) - 2;
                         // a run start in a uniform-case block never joins the previous chunk (they differ
                         // as bytes and share the case, so they differ after upper-casing too); with mixed
                         // case the two chunks are compared after upper-casing (explore.rs:212 vs :324)
-                        // the boundary says G[q] != G[q - k]; which of the two holds is read from the slice
-                        // (the planes' verdict and the bytes agree wherever the plane path emits)
-                        const bool start = g_bytes(t, m, (int)k, p + b);
+                        // The boundary says G[q] != G[q - k].  Which of the two holds is not needed here: the
+                        // boundaries of a (slice, k) alternate start / end from a start on (G is 0 before the first
+                        // full chunk pair and beyond the slice), so after the sort an event's type is the parity of
+                        // its rank and the run builder pairs (2i, 2i + 1).  Only `joins` needs it, in mixed-case
+                        // blocks, where it is read back from the slice (the planes' verdict and the bytes agree
+                        // wherever the plane path emits); elsewhere the type bit is left 0.
+                        const bool start = !need_cs || g_bytes(t, m, (int)k, p + b);
                         const bool joins = need_cs && start && j > 0 && chunks_equal_upper(t, (int)k, j);
                         emit_event(job, slice, k, j, start, joins);
                     }

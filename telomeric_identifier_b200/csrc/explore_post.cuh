@@ -3,7 +3,7 @@
 // calculate_indexes (explore.rs:289-347) + the count half of filter_by_frequency (explore.rs:265-274)
 // for millions of events: a radix sort of the 64-bit keys puts them into (k, record, slice, position)
 // order -- the reference's FASTA-order arrival order -- where they alternate start / end per
-// (slice, k); one thread per raw run decides whether it heads a (merged) run, walks the chain of
+// (slice, k), beginning with a start, so keys 2i and 2i + 1 are one raw run; one thread per raw run decides whether it heads a (merged) run, walks the chain of
 // raw runs that abut and agree after upper-casing, applies the first-run rule (start = 0,
 // explore.rs:297) and the threshold; an order-preserving compaction keeps the survivors.
 // The sort and the compaction are CUB device primitives (plumbing, not the hot path).
@@ -23,7 +23,8 @@ __global__ void __launch_bounds__(256) runs_from_keys_kernel(const uint64_t *key
     uint64_t s, e;
     unpack_event(fmt, keys[2 * i], sl, k, s, ty, jn);
     unpack_event(fmt, keys[2 * i + 1], sl2, k2, e, ty2, jn2);
-    if (ty != 0 || ty2 != 1 || sl != sl2 || k != k2 || e <= s) { atomicOr(err_flags, 4u); flags[i] = 0; return; }
+    // (the type bits are advisory: the plane kernel only fills them in mixed-case blocks; the pairing is by rank)
+    if (sl != sl2 || k != k2 || e <= s) { atomicOr(err_flags, 4u); flags[i] = 0; return; }
     bool first = true, head = true;
     if (i > 0) {
         uint32_t psl, pk, pty, pjn; uint64_t pe;
