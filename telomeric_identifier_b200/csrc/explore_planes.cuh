@@ -301,28 +301,6 @@ __constant__ uint32_t kExactInv[17] = {0u, 1u, 1u, 0xAAAAAAABu, 1u, 0xCCCCCCCDu,
 __constant__ uint32_t kExactShift[17] = {0u, 0u, 1u, 0u, 2u, 0u, 1u, 0u, 3u, 0u, 1u, 0u, 2u, 0u, 1u, 0u, 4u};
 __device__ __forceinline__ uint32_t div_exact(uint32_t q, uint32_t k) { return (q >> kExactShift[k]) * kExactInv[k]; }
 
-// q / k for k <= 16 with the divisor known per case: a multiply and a shift instead of the generic division
-__device__ __forceinline__ uint32_t div_small(uint32_t q, uint32_t k) {
-    switch (k) {
-    case 1: return q;
-    case 2: return q / 2u;
-    case 3: return q / 3u;
-    case 4: return q / 4u;
-    case 5: return q / 5u;
-    case 6: return q / 6u;
-    case 7: return q / 7u;
-    case 8: return q / 8u;
-    case 9: return q / 9u;
-    case 10: return q / 10u;
-    case 11: return q / 11u;
-    case 12: return q / 12u;
-    case 13: return q / 13u;
-    case 14: return q / 14u;
-    case 15: return q / 15u;
-    default: return q / 16u;
-    }
-}
-
 // KMIN > 0: the k range is a compile-time constant (default 5..12); KMIN == 0: run-time range.
 #ifndef TIDK_EX_MINB
 #define TIDK_EX_MINB 3
