@@ -18,14 +18,25 @@ def split_dist(n: int, d: float) -> int:  # explore.rs:156
 
 
 def run_labels(seq: np.ndarray, offsets: np.ndarray, distance: float, runs: np.ndarray) -> List[bytes]:
-    labels = []
-    for r in runs:
-        o, e = int(offsets[r["record"]]), int(offsets[r["record"] + 1])
-        dist = split_dist(e - o, distance)
-        base = o if r["slice"] == 0 else e - dist
-        p = base + int(r["label_pos"])
-        labels.append(seq[p:p + int(r["k"])].tobytes().upper())
-    return labels
+    """Upper-cased label of every run (slice[label_pos .. label_pos + k)), gathered per k in one indexing step:
+    a read set yields hundreds of thousands of runs, a per-run Python loop would dominate the call."""
+    if runs.size == 0:
+        return []
+    offsets = np.asarray(offsets)
+    rec = runs["record"].astype(np.int64)
+    o = offsets[rec].astype(np.int64)
+    e = offsets[rec + 1].astype(np.int64)
+    dist = np.maximum(np.ceil((e - o).astype(np.float64) * distance), 0).astype(np.int64)  # explore.rs:156
+    p = np.where(runs["slice"] == 0, o, e - dist) + runs["label_pos"].astype(np.int64)
+    out = np.empty(runs.size, dtype=object)
+    for k in np.unique(runs["k"]).tolist():
+        sel = np.flatnonzero(runs["k"] == k)
+        m = seq[p[sel][:, None] + np.arange(k, dtype=np.int64)[None, :]]
+        m = np.where((m >= 97) & (m <= 122), m - 32, m).astype(np.uint8)
+        out[sel] = np.ascontiguousarray(m).view(f"S{k}").ravel().tolist()
+    labels = out.tolist()
+    # numpy's S dtype strips trailing NULs; a label can only end in NUL if the sequence holds NUL bytes
+    return [l if len(l) == int(kk) else l + b"\x00" * (int(kk) - len(l)) for l, kk in zip(labels, runs["k"].tolist())]
 
 
 def explore_table(ctx: Context, seq: np.ndarray, offsets: np.ndarray, length: int = 0, minimum: int = 5,

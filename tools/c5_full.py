@@ -17,6 +17,7 @@ import numpy as np
 import torch
 import telomeric_identifier_b200 as T
 from telomeric_identifier_b200 import synth, hostlogic
+from telomeric_identifier_b200.explore import run_labels
 from oracle import oracle as O
 
 N_READS = int(os.environ.get("TIDK_C5_READS", "2000000"))
@@ -52,18 +53,7 @@ def make_batch(b: int, n_reads: int, host: np.ndarray, lut: torch.Tensor):
 
 
 def labels_of(seq, off, runs):
-    """Upper-cased labels of a run list, vectorised per k -> (list of bytes) aligned with runs."""
-    o = off[runs["record"]].astype(np.int64)
-    e = off[runs["record"].astype(np.int64) + 1].astype(np.int64)
-    dist = np.ceil((e - o).astype(np.float64) * D).astype(np.int64)  # explore.rs:156
-    p = np.where(runs["slice"] == 0, o, e - dist) + runs["label_pos"].astype(np.int64)
-    out = np.empty(runs.size, dtype=object)
-    for k in np.unique(runs["k"]).tolist():
-        sel = np.flatnonzero(runs["k"] == k)
-        m = seq[p[sel][:, None] + np.arange(k)[None, :]]
-        m = np.where((m >= 97) & (m <= 122), m - 32, m).astype(np.uint8)
-        out[sel] = np.ascontiguousarray(m).view(f"S{k}").ravel().tolist()
-    return out.tolist()
+    return run_labels(seq, off, D, runs)
 
 
 def same_runs(a, b, fields=("record", "slice", "k", "first", "start", "end", "label_pos")):
