@@ -46,9 +46,10 @@ def explore_table(ctx: Context, seq: np.ndarray, offsets: np.ndarray, length: in
     kmin, kmax = (length, length) if length > 0 else (minimum, maximum)  # explore.rs:50,83-88
     runs = ctx.explore_runs(seq, offsets, distance, kmin, kmax, threshold)
     labels = run_labels(seq, offsets, distance, runs)
-    keep = [i for i, l in enumerate(labels) if period(l) >= 3]  # filter_by_frequency, explore.rs:265-274
-    counts = [(int(runs[i]["end"]) - int(runs[i]["start"])) // int(runs[i]["k"]) for i in keep]
-    return estimates([labels[i] for i in keep], counts)
+    ok = {l: period(l) >= 3 for l in set(labels)}  # filter_by_frequency, explore.rs:265-274 (once per distinct label)
+    keep = [i for i, l in enumerate(labels) if ok[l]]
+    counts = ((runs["end"] - runs["start"]) // runs["k"]).tolist()
+    return estimates([labels[i] for i in keep], [counts[i] for i in keep])
 
 
 def explore(ctx: Context, fasta: str, length: int = 0, minimum: int = 5, maximum: int = 12, threshold: int = 100,
