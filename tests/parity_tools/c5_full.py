@@ -12,7 +12,7 @@ The random background of a batch is drawn on the GPU with torch (numpy needs ~15
 copied to host memory before anything is timed; lengths and planted arrays follow synth.config5.
 Writes gpurun_out/c5_full.json."""
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 import telomeric_identifier_b200 as T

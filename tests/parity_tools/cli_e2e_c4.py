@@ -1,12 +1,12 @@
 """End to end through the C++ driver on BASELINE config 4: a 3.1 Gb / 24-chromosome FASTA with N gaps (page-cache
 warm) -> `tidk search --string TTAGGG --window 10000` -> TSV.  The rows of two chromosomes are checked against the
-oracle's text.  usage: python tools/cli_e2e_c4.py [gpus ...]   (default: 1)"""
+oracle's text.  usage: python tests/parity_tools/cli_e2e_c4.py [gpus ...]   (default: 1)"""
 import os, subprocess, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from telomeric_identifier_b200 import synth
 from oracle import oracle as O
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 TIDK = os.path.join(ROOT, "telomeric_identifier_b200", "bin", "tidk")
 scale = float(os.environ.get("TIDK_BENCH_SCALE", "1.0"))
 d = "/tmp/tidk_cli_e2e_c4"; os.makedirs(d, exist_ok=True)

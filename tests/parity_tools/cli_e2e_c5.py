@@ -1,13 +1,13 @@
 """End to end through the C++ driver on a BASELINE config 5 read set (default 200 000 HiFi-like reads, ~3 Gb; the
-full 2 000 000 reads are covered batch-wise by tools/c5_full.py): FASTA (page-cache warm) ->
+full 2 000 000 reads are covered batch-wise by tests/parity_tools/c5_full.py): FASTA (page-cache warm) ->
 `tidk explore --minimum 5 --maximum 12 --threshold 100 --distance 0.5` -> STDOUT table, compared with the oracle's
-text (O(n) estimator, FASTA order).  usage: python tools/cli_e2e_c5.py [n_reads]"""
+text (O(n) estimator, FASTA order).  usage: python tests/parity_tools/cli_e2e_c5.py [n_reads]"""
 import os, subprocess, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from telomeric_identifier_b200 import synth
 from oracle import oracle as O
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 TIDK = os.path.join(ROOT, "telomeric_identifier_b200", "bin", "tidk")
 n_reads = int(sys.argv[1]) if len(sys.argv) > 1 else 200_000
 d = "/tmp/tidk_cli_e2e_c5"; os.makedirs(d, exist_ok=True)

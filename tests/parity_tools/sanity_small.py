@@ -1,6 +1,6 @@
 """Tiny end-to-end run for compute-sanitizer: one window-count call per kernel family and one explore call."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import telomeric_identifier_b200 as T
 from telomeric_identifier_b200 import synth

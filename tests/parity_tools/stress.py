@@ -1,8 +1,8 @@
 """One-off differential stress run (not part of the suite): many seeded random batches through the C ABI
 against the oracle -- window counts (all kernels, both upload paths) and explore (all block variants).
-usage: python tools/stress.py [first_seed] [n_seeds]"""
+usage: python tests/parity_tools/stress.py [first_seed] [n_seeds]"""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import telomeric_identifier_b200 as T
 from telomeric_identifier_b200 import synth
