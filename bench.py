@@ -285,6 +285,16 @@ def main():
                              "call_wall_ms": best[2] * 1e3, "runs": int(runs.size),
                              "scan_gbases_per_s": scanned / (best[0] * 1e-3) / 1e9,
                              "kernel": "explore_planes_kernel<5,12>", "k_range": [5, 12], "threshold": 100}
+            # the CPU port beside it: rayon's one-worker-per-record sharding (explore.rs:97-100) as
+            # min(host cores, records) threads, one pass over the same genome, same arguments
+            from oracle import oracle as O
+            cpu_threads = max(1, min(os.cpu_count() or 1, len(off) - 1))
+            t4 = time.perf_counter()
+            cpu_runs, _ = O.explore_runs(seq, off, d, 5, 12, 100, False, cpu_threads)
+            cpu_dt = time.perf_counter() - t4
+            explore[name]["cpu_baseline"] = {"value": scanned / cpu_dt / 1e9, "unit": UNIT, "cores": cpu_threads,
+                                             "kind": "port", "sample": "whole genome, one pass, records sharded over threads",
+                                             "runs_equal_to_gpu": bool(len(cpu_runs) == int(runs.size))}
 
     if dist is not None:
         t = torch.tensor([dt, dt_e2e, kernel_ms], device="cuda", dtype=torch.float64)

@@ -92,7 +92,9 @@ inline void pack_words(const uint8_t *src, size_t n_bytes, size_t n_words, uint3
 // (every base one of ACGTacgt), so only the words where it is not are reported, as (global word index << 32 |
 // va) records appended to `exc`.  The device fills its va plane with ones and scatters the exceptions.
 // 2 bits per base cross the bus instead of 3, and the host writes a third less.
-template <class Vec>
+// STRICT (the explore upload): a base is valid only if it is one of A C G T in UPPER case, so that the planes of an
+// exception-free word determine its bytes exactly (explore compares raw bytes, explore.rs:208).
+template <bool STRICT = false, class Vec>
 inline void pack_words2_scalar(const uint8_t *src, size_t n_bytes, size_t n_words, uint32_t *lo, uint32_t *hi,
                                uint64_t word0, Vec &exc, uint32_t *nonascii) {
     uint32_t na = 0;
@@ -102,7 +104,7 @@ inline void pack_words2_scalar(const uint8_t *src, size_t n_bytes, size_t n_word
         const size_t m = base >= n_bytes ? 0 : (n_bytes - base < 32 ? n_bytes - base : 32);
         for (size_t b = 0; b < m; b++) {
             const uint8_t c = src[base + b];
-            const uint8_t u = c | 0x20;
+            const uint8_t u = STRICT ? (uint8_t)(c ^ 0x20) : (uint8_t)(c | 0x20); // STRICT: only 'A' maps to 'a', ...
             l |= (uint32_t)((c >> 1) & 1u) << b;
             h |= (uint32_t)((c >> 2) & 1u) << b;
             v |= (uint32_t)(u == 'a' || u == 'c' || u == 'g' || u == 't') << b;
@@ -114,7 +116,7 @@ inline void pack_words2_scalar(const uint8_t *src, size_t n_bytes, size_t n_word
     if (na) *nonascii = 1;
 }
 
-template <class Vec>
+template <bool STRICT = false, class Vec>
 __attribute__((target("avx2"))) inline void pack_words2_avx2(const uint8_t *src, size_t n_bytes, size_t n_words,
                                                              uint32_t *lo, uint32_t *hi, uint64_t word0, Vec &exc,
                                                              uint32_t *nonascii) {
@@ -127,7 +129,7 @@ __attribute__((target("avx2"))) inline void pack_words2_avx2(const uint8_t *src,
         const __m256i v = _mm256_loadu_si256((const __m256i *)(src + (W) * 32));                         \
         (L) = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 6));                                   \
         (H) = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 5));                                   \
-        const __m256i u = _mm256_or_si256(v, c20);                                                       \
+        const __m256i u = STRICT ? _mm256_xor_si256(v, c20) : _mm256_or_si256(v, c20);                                                       \
         const __m256i ok = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(u, ca), _mm256_cmpeq_epi8(u, cc)), \
                                            _mm256_or_si256(_mm256_cmpeq_epi8(u, cg), _mm256_cmpeq_epi8(u, ct))); \
         (V) = (uint32_t)_mm256_movemask_epi8(ok);                                                        \
@@ -160,20 +162,21 @@ __attribute__((target("avx2"))) inline void pack_words2_avx2(const uint8_t *src,
 #undef TIDK_PACK_ONE
     if (na) *nonascii = 1;
     if (full < n_words)
-        pack_words2_scalar(src + full * 32, n_bytes - full * 32, n_words - full, lo + full, hi + full, word0 + full, exc, nonascii);
+        pack_words2_scalar<STRICT>(src + full * 32, n_bytes - full * 32, n_words - full, lo + full, hi + full, word0 + full, exc, nonascii);
 }
 
 // AVX-512 (BW + VBMI) form: 64 bases per step.  A plane is ONE instruction -- vptestmb against the bit's mask
 // yields the 64 plane bits as a mask register -- and validity is a 64-entry table lookup on the low six bits of
 // the lower-cased byte (vpermb) plus one compare: about 8 uops per 64 bases against about 28 for the AVX2 form,
 // so a packer thread is bound by memory instead of the movemask port.
-template <class Vec>
+template <bool STRICT = false, class Vec>
 __attribute__((target("avx512f,avx512bw,avx512vbmi"))) inline void pack_words2_avx512(const uint8_t *src, size_t n_bytes,
                                                                                      size_t n_words, uint32_t *lo, uint32_t *hi,
                                                                                      uint64_t word0, Vec &exc, uint32_t *nonascii) {
     const size_t full = n_bytes / 32 < n_words ? n_bytes / 32 : n_words;
     alignas(64) uint8_t tab[64];
     memset(tab, 0, sizeof tab); // 0 never equals a byte with bit 5 set
+    tab[0] = 0xFF;              // STRICT: u = v ^ 0x20 is 0 for a space; 0xFF equals none of 0x00 / 0x40 / 0x80 / 0xC0
     tab['a' & 63] = 'a'; tab['c' & 63] = 'c'; tab['g' & 63] = 'g'; tab['t' & 63] = 't';
     const __m512i table = _mm512_load_si512(tab);
     const __m512i c02 = _mm512_set1_epi8(0x02), c04 = _mm512_set1_epi8(0x04), c20 = _mm512_set1_epi8(0x20);
@@ -191,7 +194,7 @@ __attribute__((target("avx512f,avx512bw,avx512vbmi"))) inline void pack_words2_a
     do {                                                                                                   \
         const __m512i v = _mm512_loadu_si512(src + (w + 2 * (I)) * 32);                                    \
         const uint64_t l = _mm512_test_epi8_mask(v, c02), h = _mm512_test_epi8_mask(v, c04);               \
-        const __m512i u = _mm512_or_si512(v, c20);                                                         \
+        const __m512i u = STRICT ? _mm512_xor_si512(v, c20) : _mm512_or_si512(v, c20);                     \
         oks[I] = _mm512_cmpeq_epi8_mask(u, _mm512_permutexvar_epi8(u, table));                             \
         okall &= oks[I];                                                                                   \
         acc = _mm512_or_si512(acc, v);                                                                     \
@@ -219,19 +222,19 @@ __attribute__((target("avx512f,avx512bw,avx512vbmi"))) inline void pack_words2_a
     }
     if (_mm512_movepi8_mask(acc)) *nonascii = 1;
     if (w < n_words)
-        pack_words2_scalar(src + w * 32, n_bytes - w * 32, n_words - w, lo + w, hi + w, word0 + w, exc, nonascii);
+        pack_words2_scalar<STRICT>(src + w * 32, n_bytes - w * 32, n_words - w, lo + w, hi + w, word0 + w, exc, nonascii);
 }
 
-template <class Vec>
+template <bool STRICT = false, class Vec>
 inline void pack_words2(const uint8_t *src, size_t n_bytes, size_t n_words, uint32_t *lo, uint32_t *hi, uint64_t word0,
                         Vec &exc, uint32_t *nonascii) {
     static const bool avx2 = __builtin_cpu_supports("avx2");
     // TIDK_PACK_ISA=avx2 keeps the AVX2 form on an AVX-512 machine (measurements)
     static const bool avx512 = __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vbmi") &&
                                !(getenv("TIDK_PACK_ISA") && strcmp(getenv("TIDK_PACK_ISA"), "avx2") == 0);
-    if (avx512) pack_words2_avx512(src, n_bytes, n_words, lo, hi, word0, exc, nonascii);
-    else if (avx2) pack_words2_avx2(src, n_bytes, n_words, lo, hi, word0, exc, nonascii);
-    else pack_words2_scalar(src, n_bytes, n_words, lo, hi, word0, exc, nonascii);
+    if (avx512) pack_words2_avx512<STRICT>(src, n_bytes, n_words, lo, hi, word0, exc, nonascii);
+    else if (avx2) pack_words2_avx2<STRICT>(src, n_bytes, n_words, lo, hi, word0, exc, nonascii);
+    else pack_words2_scalar<STRICT>(src, n_bytes, n_words, lo, hi, word0, exc, nonascii);
 }
 
 } // namespace tidk

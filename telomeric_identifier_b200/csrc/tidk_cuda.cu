@@ -111,7 +111,7 @@ struct tidk_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
     tidk_seqbuf scratch; // staging for the host-pointer entry points
-    DevBuf win_base, out_fwd, out_rev, misc, qbytes, runs, items, exc;
+    DevBuf win_base, out_fwd, out_rev, misc, qbytes, runs, items, exc, exc_raw, chunk_state;
     float explore_scan_ms = 0.f, explore_post_ms = 0.f, explore_host_ms[2] = {0.f, 0.f};
     uint64_t last_h2d = 0, last_d2h = 0; // bytes moved by the last host-pointer window-count call
     int last_packed = 0;
@@ -471,7 +471,7 @@ void tidk_cuda_destroy(tidk_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     seqbuf_release(&ctx->scratch);
-    for (DevBuf *b : {&ctx->win_base, &ctx->out_fwd, &ctx->out_rev, &ctx->misc, &ctx->qbytes, &ctx->runs, &ctx->items, &ctx->exc})
+    for (DevBuf *b : {&ctx->win_base, &ctx->out_fwd, &ctx->out_rev, &ctx->misc, &ctx->qbytes, &ctx->runs, &ctx->items, &ctx->exc, &ctx->exc_raw, &ctx->chunk_state})
         if (b->p) cudaFree(b->p);
     explore_scratch_release(ctx->ex);
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
@@ -802,6 +802,53 @@ __global__ void va_scatter_kernel(uint32_t *packed, const uint64_t *exc, uint64_
     packed[(word >> tidk::kPackShift) * (3ull * tidk::kPackWords) + 2ull * tidk::kPackWords + (word & (tidk::kPackWords - 1))] = (uint32_t)e;
 }
 
+// ---- explore: planes back to ASCII ------------------------------------------------------------
+// The explore scan compares raw bytes (explore.rs:208), so its host-pointer entry point uses the packers in
+// STRICT form (valid = upper-case A C G T): an exception-free word is exactly the bytes its lo / hi planes say,
+// and the words with anything else in them (lower case, N, IUPAC codes, the tail behind the last base) travel
+// as raw 32-byte records.  On the device the packed chunks are expanded into the ordinary ASCII sequence buffer
+// (one 16-byte store per thread, write-bound: 1.5 GB in about 0.3 ms) and the raw words patched over them; the
+// scan then runs unchanged.  The bus carries 0.25 B per base instead of 1.
+__global__ void __launch_bounds__(256) unpack_planes_kernel(const uint32_t *packed, const uint8_t *chunk_state, uint8_t *seq,
+                                                            uint64_t half0, uint64_t n_half_words, uint64_t total) {
+    __shared__ uint32_t lut[256]; // (hi nibble << 4 | lo nibble) -> four ASCII bases; (hi, lo): 00 A, 01 C, 11 G, 10 T
+    {
+        const uint32_t t = threadIdx.x, l4 = t & 15u, h4 = t >> 4;
+        uint32_t v = 0;
+        for (int b = 0; b < 4; b++) {
+            const uint32_t code = ((h4 >> b) & 1u) * 2u + ((l4 >> b) & 1u);
+            v |= (uint32_t)("ACTG"[code]) << (8 * b);
+        }
+        lut[t] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; r++) { // 16 bases per thread and round, 16 KiB of sequence per CTA
+        const uint64_t i = half0 + ((uint64_t)blockIdx.x * 4 + r) * 256 + threadIdx.x;
+        if (i >= n_half_words) return;
+        const uint64_t word = i >> 1;
+        const uint64_t chunk = word >> tidk::kPackShift;
+        if (chunk_state[chunk] != 1 || word * 32 >= total) continue; // the chunk went up as ASCII
+        const uint32_t *pc = packed + chunk * (3ull * tidk::kPackWords) + (word & (tidk::kPackWords - 1));
+        const uint32_t sh = (uint32_t)(i & 1) * 16u;
+        const uint32_t lo = __ldg(pc) >> sh, hi = __ldg(pc + tidk::kPackWords) >> sh;
+        uint4 o;
+        o.x = lut[((hi & 0xFu) << 4) | (lo & 0xFu)];
+        o.y = lut[(((hi >> 4) & 0xFu) << 4) | ((lo >> 4) & 0xFu)];
+        o.z = lut[(((hi >> 8) & 0xFu) << 4) | ((lo >> 8) & 0xFu)];
+        o.w = lut[(((hi >> 12) & 0xFu) << 4) | ((lo >> 12) & 0xFu)];
+        *reinterpret_cast<uint4 *>(seq + i * 16) = o; // the buffer is 256-byte aligned and padded behind `total`
+    }
+}
+
+// exception words: exc[i] >> 32 = global word index, raw[i] = its 32 bytes as the caller has them
+__global__ void __launch_bounds__(256) patch_words_kernel(uint8_t *seq, const uint64_t *exc, const uint4 *raw, uint64_t n_halves) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; // one thread per 16 bytes
+    if (i >= n_halves) return;
+    const uint64_t word = exc[i >> 1] >> 32;
+    *reinterpret_cast<uint4 *>(seq + word * 32 + (i & 1) * 16) = raw[i];
+}
+
 //
 // Two-ended ("hybrid") upload.  The packers are bound by the host's memory bandwidth (about 76 GB/s of
 // sequence on 16 vCPUs) while the bus would still have room, and a plain DMA of ASCII needs no CPU at
@@ -810,7 +857,11 @@ __global__ void va_scatter_kernel(uint32_t *packed, const uint64_t *exc, uint64_
 // passes by), the packers take chunks from the back, and they meet wherever the machine's pack rate and
 // bus rate put the balance.  *split receives the first packed byte; the windows below it are counted
 // from ASCII, the rest from planes.
-static int upload_packed(tidk_ctx *ctx, const uint8_t *seq, uint64_t total, int T, bool allow_ascii, uint64_t *split) {
+// explore_mode: STRICT packing, chunks with many exception words sent as ASCII by their packer, and the packed
+// chunks expanded into the sequence buffer afterwards (see unpack_planes_kernel): on return (stream order) the
+// buffer holds the caller's bytes exactly.
+static int upload_packed(tidk_ctx *ctx, const uint8_t *seq, uint64_t total, int T, bool allow_ascii, uint64_t *split,
+                         bool explore_mode = false) {
     const uint64_t n_words = (total + 31) / 32;
     const uint64_t n_chunks = (n_words + kPackWords - 1) / kPackWords;
     const size_t chunk_bytes = 3ull * kPackWords * 4;
@@ -819,10 +870,13 @@ static int upload_packed(tidk_ctx *ctx, const uint8_t *seq, uint64_t total, int 
     *split = 0;
     int rc;
     if ((rc = ensure(ctx, ctx->packed, (n_chunks + 1) * chunk_bytes))) return rc; // + one zero chunk: blocks read past the end
-    CU(ctx, cudaMemsetAsync((char *)ctx->packed.p + n_chunks * chunk_bytes, 0, chunk_bytes, ctx->stream));
-    // the validity plane (third part of every chunk) is all ones except where the packers say otherwise
-    CU(ctx, cudaMemset2DAsync((char *)ctx->packed.p + 2ull * kPackWords * 4, chunk_bytes, 0xFF, (size_t)kPackWords * 4, n_chunks, ctx->stream));
+    if (!explore_mode) {
+        CU(ctx, cudaMemsetAsync((char *)ctx->packed.p + n_chunks * chunk_bytes, 0, chunk_bytes, ctx->stream));
+        // the validity plane (third part of every chunk) is all ones except where the packers say otherwise
+        CU(ctx, cudaMemset2DAsync((char *)ctx->packed.p + 2ull * kPackWords * 4, chunk_bytes, 0xFF, (size_t)kPackWords * 4, n_chunks, ctx->stream));
+    }
     std::vector<std::vector<uint64_t>> exc((size_t)T);
+    std::vector<uint8_t> chunk_state((size_t)n_chunks, 0); // 0: ASCII by DMA from the front, 1: packed, 2: ASCII sent by a packer
     if ((rc = ensure_lanes(ctx, T))) return rc;
     if (allow_ascii && !ctx->dma_st) {
         CU(ctx, cudaStreamCreateWithFlags(&ctx->dma_st, cudaStreamNonBlocking));
@@ -876,13 +930,30 @@ static int upload_packed(tidk_ctx *ctx, const uint8_t *seq, uint64_t total, int 
             const uint64_t byte0 = (uint64_t)c * chunk_seq;
             const uint64_t have = total - byte0 < chunk_seq ? total - byte0 : chunk_seq;
             constexpr uint32_t kSub = 8; // packed in eighths, looking after the ASCII copy queue in between
+            const size_t exc_before = exc[(size_t)t].size();
             for (uint32_t s8 = 0; s8 < kSub; s8++) {
                 const uint32_t w0 = s8 * (kPackWords / kSub);
                 const uint64_t b0 = (uint64_t)w0 * 32;
-                pack_words2(seq + byte0 + b0, (size_t)(have > b0 ? have - b0 : 0), kPackWords / kSub, buf + w0,
-                            buf + kPackWords + w0, (uint64_t)c * kPackWords + w0, exc[(size_t)t], &flag);
+                if (explore_mode)
+                    pack_words2<true>(seq + byte0 + b0, (size_t)(have > b0 ? have - b0 : 0), kPackWords / kSub, buf + w0,
+                                      buf + kPackWords + w0, (uint64_t)c * kPackWords + w0, exc[(size_t)t], &flag);
+                else
+                    pack_words2(seq + byte0 + b0, (size_t)(have > b0 ? have - b0 : 0), kPackWords / kSub, buf + w0,
+                                buf + kPackWords + w0, (uint64_t)c * kPackWords + w0, exc[(size_t)t], &flag);
                 pump();
             }
+            // explore: an exception word costs 40 bytes on the bus, a packed word saves 24 -- a chunk with more than
+            // one exception word in sixteen (soft-masked stretches, N gaps) goes up as ASCII instead
+            if (explore_mode) // words wholly behind the last base pack as invalid: nothing to reproduce there
+                while (exc[(size_t)t].size() > exc_before && (exc[(size_t)t].back() >> 32) * 32 >= total) exc[(size_t)t].pop_back();
+            if (explore_mode && exc[(size_t)t].size() - exc_before > kPackWords / 16) {
+                exc[(size_t)t].resize(exc_before);
+                chunk_state[(size_t)c] = 2;
+                if (cudaMemcpyAsync(ctx->scratch.d_seq + byte0, seq + byte0, have, cudaMemcpyHostToDevice, L.st) != cudaSuccess ||
+                    cudaEventRecord(L.ev[slot], L.st) != cudaSuccess) { cuda_err = 1; break; }
+                continue;
+            }
+            chunk_state[(size_t)c] = 1;
             if (cudaMemcpyAsync((char *)ctx->packed.p + (uint64_t)c * chunk_bytes, buf, plane2_bytes, cudaMemcpyHostToDevice, L.st) != cudaSuccess ||
                 cudaEventRecord(L.ev[slot], L.st) != cudaSuccess) { cuda_err = 1; break; }
         }
@@ -897,6 +968,46 @@ static int upload_packed(tidk_ctx *ctx, const uint8_t *seq, uint64_t total, int 
     const uint64_t n_ascii = (uint64_t)front.load() < n_chunks ? (uint64_t)front.load() : n_chunks; // chunks [0, n_ascii) went as ASCII
     uint64_t sp = n_ascii * chunk_seq;
     if (sp > total) sp = total;
+    if (explore_mode) {
+        uint64_t n_packed = 0, ascii_bytes = 0;
+        for (uint64_t c = 0; c < n_chunks; c++) {
+            if (chunk_state[(size_t)c] == 1) n_packed++;
+            else ascii_bytes += total - c * chunk_seq < chunk_seq ? total - c * chunk_seq : chunk_seq;
+        }
+        size_t n_exc = 0;
+        for (const auto &v : exc) n_exc += v.size();
+        ctx->last_h2d += ascii_bytes + n_packed * plane2_bytes + n_exc * 40 + n_chunks;
+        if (n_packed) {
+            if ((rc = ensure(ctx, ctx->chunk_state, (size_t)n_chunks))) return rc;
+            CU(ctx, cudaMemcpyAsync(ctx->chunk_state.p, chunk_state.data(), (size_t)n_chunks, cudaMemcpyHostToDevice, ctx->stream));
+            const uint64_t n_half = n_chunks * (uint64_t)kPackWords * 2, half0 = n_ascii * (uint64_t)kPackWords * 2;
+            unpack_planes_kernel<<<(unsigned)((n_half - half0 + 1023) / 1024), 256, 0, ctx->stream>>>(
+                (const uint32_t *)ctx->packed.p, (const uint8_t *)ctx->chunk_state.p, ctx->scratch.d_seq, half0, n_half, total);
+            CU(ctx, cudaGetLastError());
+        }
+        std::vector<uint64_t> all;
+        std::vector<uint8_t> raw;
+        if (n_exc) {
+            all.reserve(n_exc);
+            for (const auto &v : exc) all.insert(all.end(), v.begin(), v.end());
+            raw.assign(n_exc * 32, 0);
+            for (size_t i = 0; i < n_exc; i++) {
+                const uint64_t b0 = (all[i] >> 32) * 32;
+                if (b0 < total) memcpy(raw.data() + i * 32, seq + b0, (size_t)(total - b0 < 32 ? total - b0 : 32));
+            }
+            if ((rc = ensure(ctx, ctx->exc, n_exc * 8))) return rc;
+            if ((rc = ensure(ctx, ctx->exc_raw, n_exc * 32))) return rc;
+            CU(ctx, cudaMemcpyAsync(ctx->exc.p, all.data(), n_exc * 8, cudaMemcpyHostToDevice, ctx->stream));
+            CU(ctx, cudaMemcpyAsync(ctx->exc_raw.p, raw.data(), n_exc * 32, cudaMemcpyHostToDevice, ctx->stream));
+            patch_words_kernel<<<(unsigned)((2 * n_exc + 255) / 256), 256, 0, ctx->stream>>>(
+                ctx->scratch.d_seq, (const uint64_t *)ctx->exc.p, (const uint4 *)ctx->exc_raw.p, 2 * (uint64_t)n_exc);
+            CU(ctx, cudaGetLastError());
+        }
+        CU(ctx, cudaMemsetAsync(ctx->scratch.d_seq + total, 0, kSeqPad, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream)); // the pageable staging vectors go out of scope
+        *split = sp;
+        return TIDK_OK;
+    }
     if (n_ascii > 0) {
         // the last window below the split may reach up to a window (<= 32 KiB here) plus a block beyond it
         const uint64_t extra = total - sp < (64u << 10) ? total - sp : (64u << 10);
@@ -1045,8 +1156,38 @@ int tidk_cuda_explore_runs(tidk_ctx *ctx, const uint8_t *seq, const uint64_t *of
         if (rc) return fail(ctx, rc, "%s", err.c_str());
         return TIDK_OK;
     }
+    // Whole-batch upload (read sets, --distance near 0.5).  With enough host cores the sequence goes up two-ended
+    // like the window counter's (ASCII chunks by DMA from the front, STRICT-packed planes from the back) and the
+    // packed part is expanded back to ASCII on the device: the scan is unchanged, the bus carries a quarter.
+    {
+        const uint64_t total = (n_records && offsets) ? offsets[n_records] : 0;
+        const char *env = getenv("TIDK_EXPLORE_PACK");
+        const int T = pack_threads();
+        const bool forced = env && atoi(env) != 0;
+        if (seq && total > 0 && T >= 1 && (env ? forced : (T >= 12 && total >= (32u << 20)))) {
+            int rc = seqbuf_fill(ctx, &ctx->scratch, seq, offsets, n_records, /*seq_mode=*/2);
+            if (rc) return rc;
+            cudaPointerAttributes a;
+            bool pageable = true;
+            if (cudaPointerGetAttributes(&a, seq) == cudaSuccess) pageable = a.type == cudaMemoryTypeUnregistered;
+            else (void)cudaGetLastError();
+            const char *eh = getenv("TIDK_HYBRID_UPLOAD");
+            const bool hybrid = !pageable && (eh ? atoi(eh) != 0 : true); // DMA straight from the caller's buffer needs it pinned
+            ctx->last_h2d = ((uint64_t)n_records + 1) * 8;
+            ctx->last_packed = 1;
+            uint64_t split = 0;
+            if ((rc = upload_packed(ctx, seq, total, T, hybrid, &split, /*explore_mode=*/true))) {
+                ctx->scratch.id = ctx->next_buf_id++;
+                return rc;
+            }
+            return tidk_cuda_explore_runs_resident(ctx, &ctx->scratch, distance, kmin, kmax, threshold,
+                                                   out_runs, n_runs, nullptr, nullptr);
+        }
+    }
     int rc = seqbuf_fill(ctx, &ctx->scratch, seq, offsets, n_records);
     if (rc) return rc;
+    ctx->last_packed = 0;
+    ctx->last_h2d = ((uint64_t)n_records + 1) * 8 + ((n_records && offsets) ? offsets[n_records] : 0);
     return tidk_cuda_explore_runs_resident(ctx, &ctx->scratch, distance, kmin, kmax, threshold,
                                            out_runs, n_runs, nullptr, nullptr);
 }

@@ -25,4 +25,15 @@ uint64_t shim_pack2(const uint8_t *src, uint64_t n_bytes, uint64_t n_words, uint
     for (uint64_t i = 0; i < v.size() && i < cap; i++) exc[i] = v[i];
     return v.size();
 }
+
+// the explore upload's STRICT form: valid = upper-case A C G T only (exception-free words determine their bytes)
+uint64_t shim_pack2_strict(const uint8_t *src, uint64_t n_bytes, uint64_t n_words, uint32_t *lo, uint32_t *hi, uint64_t word0,
+                           uint64_t *exc, uint64_t cap, uint32_t *nonascii, int force_scalar) {
+    std::vector<uint64_t> v;
+    if (force_scalar == 1) tidk::pack_words2_scalar<true>(src, n_bytes, n_words, lo, hi, word0, v, nonascii);
+    else if (force_scalar == 2 && __builtin_cpu_supports("avx2")) tidk::pack_words2_avx2<true>(src, n_bytes, n_words, lo, hi, word0, v, nonascii);
+    else tidk::pack_words2<true>(src, n_bytes, n_words, lo, hi, word0, v, nonascii);
+    for (uint64_t i = 0; i < v.size() && i < cap; i++) exc[i] = v[i];
+    return v.size();
+}
 }

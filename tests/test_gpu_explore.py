@@ -257,3 +257,96 @@ def test_slice_ends_around_block_and_tile_edges(ctx, case):
     _runs_equal(ctx, seq, off, 0.5, 5, 12, 0)
     _runs_equal(ctx, seq, off, 0.5, 1, 16, 2)
     _runs_equal(ctx, seq, off, 0.5, 5, 12, 100)
+
+
+# ---- two-ended (host-packed) upload of the explore entry point ---------------------------------------
+def _packed_case(ctx, monkeypatch, seq, off, d, pinned, hybrid):
+    """The host-pointer call with the STRICT-packed upload forced on must return the run list of the resident
+    call (plain ASCII upload) and of the oracle."""
+    monkeypatch.setenv("TIDK_EXPLORE_PACK", "1")
+    monkeypatch.setenv("TIDK_PACK_THREADS", "4")
+    monkeypatch.setenv("TIDK_HYBRID_UPLOAD", "1" if hybrid else "0")
+    src = seq
+    if pinned:
+        src = ctx.pinned_empty(seq.size)
+        src[:] = seq
+    got = ctx.explore_runs(src, off, d, 5, 12, 3)
+    h2d, _, packed = ctx.last_transfer()
+    assert packed == 1
+    monkeypatch.setenv("TIDK_EXPLORE_PACK", "0")
+    plain = ctx.explore_runs(seq, off, d, 5, 12, 3)
+    assert ctx.last_transfer()[2] == 0
+    assert got.size == plain.size and (got == plain).all()
+    want, _ = O.explore_runs(seq, off, d, 5, 12, 3, period_filter=False)
+    assert got.size == want.size
+    for f in ("record", "slice", "k", "first", "start", "end"):
+        assert (got[f] == want[f]).all(), f
+    return h2d
+
+
+def _reads(rng, n_reads, alphabet, mean=6000):
+    parts, off = [], [0]
+    lut = np.frombuffer(alphabet, dtype=np.uint8)
+    for _ in range(n_reads):
+        n = int(rng.integers(mean // 2, mean * 2))
+        r = lut[rng.integers(0, lut.size, n)].copy()
+        if rng.random() < 0.3:  # a planted array at one end
+            unit = np.frombuffer([b"TTAGGG", b"AACCT", b"TTAGGCATG"][int(rng.integers(0, 3))], dtype=np.uint8)
+            m = int(rng.integers(50, 600))
+            arr = np.tile(unit, m // unit.size + 1)[:m]
+            if rng.random() < 0.5: r[:m] = arr
+            else: r[n - m:] = arr
+        parts.append(r)
+        off.append(off[-1] + n)
+    return np.concatenate(parts), np.array(off, dtype=np.uint64)
+
+
+@pytest.mark.parametrize("pinned,hybrid", [(False, False), (True, True), (True, False)])
+def test_packed_upload_clean_reads(ctx, monkeypatch, pinned, hybrid):
+    """Upper-case A/C/G/T reads over several 4 MiB chunks (the last one partial): everything packs; the bus
+    carries about a quarter of the bases when nothing goes up as ASCII."""
+    rng = np.random.default_rng(11)
+    seq, off = _reads(rng, 1500, b"ACGT")
+    assert seq.size > 2 * (4 << 20)
+    h2d = _packed_case(ctx, monkeypatch, seq, off, 0.5, pinned, hybrid)
+    if not hybrid:
+        assert h2d < 0.5 * seq.size
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_packed_upload_exceptions_and_fallback_chunks(ctx, monkeypatch, seed):
+    """Sparse exceptions (N, lower case, IUPAC codes, a space) travel as raw words; chunks dense in them go up as
+    ASCII; slices straddle chunk borders."""
+    rng = np.random.default_rng(200 + seed)
+    seq, off = _reads(rng, 900, b"ACGT", mean=8000)
+    n = seq.size
+    # sparse single-byte exceptions in the first part
+    for ch in b"NnacgtRY -":
+        pos = rng.integers(0, n // 2, 200)
+        seq[pos] = ch
+    # a soft-masked stretch and an N gap across the second chunk border
+    b = 2 * (4 << 20)
+    if n > b + 300000:
+        seq[b - 200000:b + 100000] |= 0x20
+        seq[b + 150000:b + 250000] = ord("N")
+    if seed % 2:  # mixed-case tandem array over a chunk border
+        unit = np.frombuffer(b"TTAGGGttagggTTAGGG", dtype=np.uint8)
+        b1 = 4 << 20
+        seq[b1 - 3000:b1 + 3000] = np.tile(unit, 6000 // unit.size + 1)[:6000]
+    _packed_case(ctx, monkeypatch, seq, off, [0.5, 0.45, 0.5, 0.41][seed], bool(seed & 1), bool(seed & 2))
+
+
+def test_packed_upload_small_and_nonascii(ctx, monkeypatch):
+    import telomeric_identifier_b200 as T
+    seq = np.frombuffer(GENOME * 3, dtype=np.uint8).copy()
+    off = np.array([0, 60, 180], dtype=np.uint64)
+    monkeypatch.setenv("TIDK_EXPLORE_PACK", "1")
+    monkeypatch.setenv("TIDK_PACK_THREADS", "2")
+    got = ctx.explore_runs(seq, off, 0.5, 5, 6, 0)
+    want, _ = O.explore_runs(seq, off, 0.5, 5, 6, 0, period_filter=False)
+    assert got.size == want.size and (got["start"] == want["start"]).all() and (got["end"] == want["end"]).all()
+    bad = seq.copy()
+    bad[70] = 0xC3
+    with pytest.raises(T.TidkCudaError) as e:
+        ctx.explore_runs(bad, off, 0.5, 5, 6, 0)
+    assert e.value.code == -4  # TIDK_ENONASCII

@@ -17,6 +17,7 @@ def shim(tmp_path_factory):
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, os.path.join(HERE, "host_pack_shim.cpp")])
     L = C.CDLL(so)
     L.shim_pack2.restype = C.c_uint64
+    L.shim_pack2_strict.restype = C.c_uint64
     return L
 
 
@@ -34,9 +35,9 @@ def model(buf: np.ndarray, n_words: int):
     return lo.astype(np.uint32), hi.astype(np.uint32), va.astype(np.uint32)
 
 
-def _aligned(n_words):
-    raw = np.zeros(n_words + 16, dtype=np.uint32)
-    shift = (-raw.ctypes.data // 4) % 8
+def _aligned(n_words):  # 64-byte aligned, like the pinned staging buffers (the AVX-512 form needs it)
+    raw = np.zeros(n_words + 32, dtype=np.uint32)
+    shift = (-raw.ctypes.data // 4) % 16
     return raw[shift: shift + n_words]
 
 
@@ -88,3 +89,41 @@ def test_empty_and_exact_multiples(shim):
                              C.c_uint64(0), exc.ctypes.data, C.c_uint64(exc.size), C.byref(flag), 0)
         assert (l2 == lo).all() and (h2 == hi).all()
         assert ne == int((va != 0xFFFFFFFF).sum())
+
+
+@pytest.mark.parametrize("seed", range(5))
+@pytest.mark.parametrize("scalar", [0, 1, 2])
+def test_strict_packers_for_the_explore_upload(shim, seed, scalar):
+    """STRICT validity (explore upload): only upper-case A C G T are valid, so an exception-free word is
+    reproduced exactly from its lo / hi planes; every other word is reported."""
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.integers(600, 6000))
+    if seed == 0:
+        buf = rng.integers(0, 128, n).astype(np.uint8)             # every ASCII byte, spaces and NUL included
+    else:
+        alphabet = [b"", b"ACGT", b"ACGTacgt", b"ACGTN", b"ACGT -@`\x00\x7f"][seed]
+        buf = np.frombuffer(alphabet, dtype=np.uint8)[rng.integers(0, len(alphabet), n)].copy()
+    buf[64:64 + 512] = np.frombuffer(b"ACGT" * 128, dtype=np.uint8)  # a clean stretch: words without exceptions
+    n_words = (n + 31) // 32 + 3
+    lo, hi, _ = model(buf, n_words)
+    pad = np.zeros(n_words * 32, dtype=np.uint8); pad[:n] = buf
+    ok = np.isin(pad, np.frombuffer(b"ACGT", dtype=np.uint8)); ok[n:] = False
+    w = (np.uint64(1) << np.arange(32, dtype=np.uint64))
+    va = (ok.astype(np.uint64).reshape(n_words, 32) @ w).astype(np.uint32)
+    l2, h2 = _aligned(n_words), _aligned(n_words)
+    exc = np.zeros(n_words + 1, dtype=np.uint64)
+    flag = C.c_uint32(0)
+    ne = shim.shim_pack2_strict(buf.ctypes.data, C.c_uint64(n), C.c_uint64(n_words), l2.ctypes.data, h2.ctypes.data, C.c_uint64(7),
+                                exc.ctypes.data, C.c_uint64(exc.size), C.byref(flag), scalar)
+    assert (l2 == lo).all() and (h2 == hi).all()
+    want = [((7 + i) << 32) | int(v) for i, v in enumerate(va) if v != 0xFFFFFFFF]
+    assert ne == len(want) and exc[:ne].tolist() == want
+    # what the device does with it: unpack (hi, lo) -> A C T G and overwrite the exception words with the raw bytes
+    lut = np.frombuffer(b"ACTG", dtype=np.uint8)
+    bits_lo = ((l2[:, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(-1)
+    bits_hi = ((h2[:, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(-1)
+    out = lut[bits_hi * 2 + bits_lo]
+    for e in exc[:ne].tolist():
+        i = (e >> 32) - 7
+        out[i * 32:(i + 1) * 32] = pad[i * 32:(i + 1) * 32]
+    assert (out[:n] == buf).all()
