@@ -81,7 +81,9 @@ int tidk_cuda_window_counts(tidk_ctx *ctx, const uint8_t *seq, const uint64_t *o
                             const uint32_t *qlens, uint32_t nq, uint64_t *out_fwd,
                             uint64_t *out_rev);
 
-/* Bytes that crossed PCIe in the last tidk_cuda_window_counts call on ctx, and whether the sequence
+/* Bytes that crossed PCIe in the last tidk_cuda_window_counts call on ctx (or the last tidk_cuda_explore_runs call
+ * that uploaded the whole batch: there the planes are STRICT -- upper-case A C G T only -- words with anything else
+ * travel as raw bytes, and the device expands the planes back to ASCII before the scan), and whether the sequence
  * went up (at least in part) as host-packed bit-planes -- 2 bits per base plus validity exceptions for
  * the chunks packed from the back, ASCII by DMA for the chunks taken from the front; taken when every
  * query has a compile-time plane kernel, the batch is >= 32 MiB and >= 12 host threads are available
