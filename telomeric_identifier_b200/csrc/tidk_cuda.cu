@@ -111,7 +111,8 @@ struct tidk_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
     tidk_seqbuf scratch; // staging for the host-pointer entry points
-    DevBuf win_base, out_fwd, out_rev, misc, qbytes, runs, items, exc, exc_raw, chunk_state;
+    DevBuf win_base, out_fwd, out_rev, misc, qbytes, runs, items, exc, chunk_state;
+    std::vector<uint32_t> h_chunk_state; // explore upload: per 4 MiB chunk, 0 = went up as ASCII, else 1 + number of raw-word records
     float explore_scan_ms = 0.f, explore_post_ms = 0.f, explore_host_ms[2] = {0.f, 0.f};
     uint64_t last_h2d = 0, last_d2h = 0; // bytes moved by the last host-pointer window-count call
     int last_packed = 0;
@@ -471,7 +472,7 @@ void tidk_cuda_destroy(tidk_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     seqbuf_release(&ctx->scratch);
-    for (DevBuf *b : {&ctx->win_base, &ctx->out_fwd, &ctx->out_rev, &ctx->misc, &ctx->qbytes, &ctx->runs, &ctx->items, &ctx->exc, &ctx->exc_raw, &ctx->chunk_state})
+    for (DevBuf *b : {&ctx->win_base, &ctx->out_fwd, &ctx->out_rev, &ctx->misc, &ctx->qbytes, &ctx->runs, &ctx->items, &ctx->exc, &ctx->chunk_state})
         if (b->p) cudaFree(b->p);
     explore_scratch_release(ctx->ex);
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
@@ -806,10 +807,14 @@ __global__ void va_scatter_kernel(uint32_t *packed, const uint64_t *exc, uint64_
 // The explore scan compares raw bytes (explore.rs:208), so its host-pointer entry point uses the packers in
 // STRICT form (valid = upper-case A C G T): an exception-free word is exactly the bytes its lo / hi planes say,
 // and the words with anything else in them (lower case, N, IUPAC codes, the tail behind the last base) travel
-// as raw 32-byte records.  On the device the packed chunks are expanded into the ordinary ASCII sequence buffer
-// (one 16-byte store per thread, write-bound: 1.5 GB in about 0.3 ms) and the raw words patched over them; the
-// scan then runs unchanged.  The bus carries 0.25 B per base instead of 1.
-__global__ void __launch_bounds__(256) unpack_planes_kernel(const uint32_t *packed, const uint8_t *chunk_state, uint8_t *seq,
+// as records -- chunk-local word index + the 32 raw bytes -- in the third (validity) part of their chunk, written
+// by the packer that found them and carried by the same copy as the planes.  On the device the packed chunks are
+// expanded into the ordinary ASCII sequence buffer (one 16-byte store per thread, write-bound: 1.5 GB in about
+// 0.3 ms) and the raw words laid over them; the scan then runs unchanged.  The bus carries 0.25 B per base
+// instead of 1.
+constexpr uint32_t kExcPerChunk = tidk::kPackWords / 16; // more exception words than this: the chunk goes up as ASCII
+
+__global__ void __launch_bounds__(256) unpack_planes_kernel(const uint32_t *packed, const uint32_t *chunk_state, uint8_t *seq,
                                                             uint64_t half0, uint64_t n_half_words, uint64_t total) {
     __shared__ uint32_t lut[256]; // (hi nibble << 4 | lo nibble) -> four ASCII bases; (hi, lo): 00 A, 01 C, 11 G, 10 T
     {
@@ -828,7 +833,7 @@ __global__ void __launch_bounds__(256) unpack_planes_kernel(const uint32_t *pack
         if (i >= n_half_words) return;
         const uint64_t word = i >> 1;
         const uint64_t chunk = word >> tidk::kPackShift;
-        if (chunk_state[chunk] != 1 || word * 32 >= total) continue; // the chunk went up as ASCII
+        if (chunk_state[chunk] == 0 || word * 32 >= total) continue; // the chunk went up as ASCII
         const uint32_t *pc = packed + chunk * (3ull * tidk::kPackWords) + (word & (tidk::kPackWords - 1));
         const uint32_t sh = (uint32_t)(i & 1) * 16u;
         const uint32_t lo = __ldg(pc) >> sh, hi = __ldg(pc + tidk::kPackWords) >> sh;
@@ -841,12 +846,18 @@ __global__ void __launch_bounds__(256) unpack_planes_kernel(const uint32_t *pack
     }
 }
 
-// exception words: exc[i] >> 32 = global word index, raw[i] = its 32 bytes as the caller has them
-__global__ void __launch_bounds__(256) patch_words_kernel(uint8_t *seq, const uint64_t *exc, const uint4 *raw, uint64_t n_halves) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; // one thread per 16 bytes
-    if (i >= n_halves) return;
-    const uint64_t word = exc[i >> 1] >> 32;
-    *reinterpret_cast<uint4 *>(seq + word * 32 + (i & 1) * 16) = raw[i];
+// raw-word records of a packed chunk, in its validity third: [kExcPerChunk x u32 chunk-local word][n x 32 raw bytes].
+// grid = (chunks from chunk0 on) x (2 * kExcPerChunk / 256); one thread per 16 bytes.
+__global__ void __launch_bounds__(256) patch_words_kernel(const uint32_t *packed, const uint32_t *chunk_state, uint8_t *seq, uint64_t chunk0) {
+    constexpr uint32_t kGroups = 2 * kExcPerChunk / 256;
+    const uint64_t chunk = chunk0 + blockIdx.x / kGroups;
+    const uint32_t st = chunk_state[chunk];
+    if (st <= 1) return;
+    const uint32_t i = (blockIdx.x % kGroups) * 256 + threadIdx.x, rec = i >> 1;
+    if (rec >= st - 1) return;
+    const uint32_t *third = packed + chunk * (3ull * tidk::kPackWords) + 2ull * tidk::kPackWords;
+    const uint64_t word = chunk * (uint64_t)tidk::kPackWords + third[rec];
+    *reinterpret_cast<uint4 *>(seq + word * 32 + (i & 1) * 16) = reinterpret_cast<const uint4 *>(third + kExcPerChunk)[i];
 }
 
 //
@@ -876,7 +887,9 @@ static int upload_packed(tidk_ctx *ctx, const uint8_t *seq, uint64_t total, int 
         CU(ctx, cudaMemset2DAsync((char *)ctx->packed.p + 2ull * kPackWords * 4, chunk_bytes, 0xFF, (size_t)kPackWords * 4, n_chunks, ctx->stream));
     }
     std::vector<std::vector<uint64_t>> exc((size_t)T);
-    std::vector<uint8_t> chunk_state((size_t)n_chunks, 0); // 0: ASCII by DMA from the front, 1: packed, 2: ASCII sent by a packer
+    std::vector<uint32_t> &chunk_state = ctx->h_chunk_state; // explore: 0 = the chunk went up as ASCII, else 1 + raw-word records
+    chunk_state.assign((size_t)n_chunks, 0);
+    std::vector<uint64_t> lane_bytes((size_t)T, 0);          // bytes each packer put on the bus
     if ((rc = ensure_lanes(ctx, T))) return rc;
     if (allow_ascii && !ctx->dma_st) {
         CU(ctx, cudaStreamCreateWithFlags(&ctx->dma_st, cudaStreamNonBlocking));
@@ -942,19 +955,37 @@ static int upload_packed(tidk_ctx *ctx, const uint8_t *seq, uint64_t total, int 
                                 buf + kPackWords + w0, (uint64_t)c * kPackWords + w0, exc[(size_t)t], &flag);
                 pump();
             }
-            // explore: an exception word costs 40 bytes on the bus, a packed word saves 24 -- a chunk with more than
+            // explore: an exception word costs 36 bytes on the bus, a packed word saves 24 -- a chunk with more than
             // one exception word in sixteen (soft-masked stretches, N gaps) goes up as ASCII instead
             if (explore_mode) // words wholly behind the last base pack as invalid: nothing to reproduce there
                 while (exc[(size_t)t].size() > exc_before && (exc[(size_t)t].back() >> 32) * 32 >= total) exc[(size_t)t].pop_back();
-            if (explore_mode && exc[(size_t)t].size() - exc_before > kPackWords / 16) {
-                exc[(size_t)t].resize(exc_before);
-                chunk_state[(size_t)c] = 2;
-                if (cudaMemcpyAsync(ctx->scratch.d_seq + byte0, seq + byte0, have, cudaMemcpyHostToDevice, L.st) != cudaSuccess ||
-                    cudaEventRecord(L.ev[slot], L.st) != cudaSuccess) { cuda_err = 1; break; }
-                continue;
+            size_t copy_bytes = plane2_bytes;
+            if (explore_mode) {
+                std::vector<uint64_t> &ev = exc[(size_t)t];
+                const size_t n_new = ev.size() - exc_before;
+                if (n_new > kExcPerChunk) {
+                    ev.resize(exc_before);
+                    if (cudaMemcpyAsync(ctx->scratch.d_seq + byte0, seq + byte0, have, cudaMemcpyHostToDevice, L.st) != cudaSuccess ||
+                        cudaEventRecord(L.ev[slot], L.st) != cudaSuccess) { cuda_err = 1; break; }
+                    lane_bytes[(size_t)t] += have;
+                    continue; // chunk_state stays 0: ASCII
+                }
+                // the records ride in the validity third of the staging slot, behind the planes: one copy
+                uint32_t *idx = buf + 2 * kPackWords;
+                uint8_t *rawp = reinterpret_cast<uint8_t *>(idx + kExcPerChunk);
+                for (size_t i = 0; i < n_new; i++) {
+                    const uint64_t word = ev[exc_before + i] >> 32, w0b = word * 32;
+                    const size_t nb = (size_t)(total - w0b < 32 ? total - w0b : 32);
+                    idx[i] = (uint32_t)(word - (uint64_t)c * kPackWords);
+                    memcpy(rawp + i * 32, seq + w0b, nb);
+                    if (nb < 32) memset(rawp + i * 32 + nb, 0, 32 - nb);
+                }
+                ev.resize(exc_before);
+                chunk_state[(size_t)c] = 1u + (uint32_t)n_new;
+                if (n_new) copy_bytes += (size_t)kExcPerChunk * 4 + n_new * 32;
             }
-            chunk_state[(size_t)c] = 1;
-            if (cudaMemcpyAsync((char *)ctx->packed.p + (uint64_t)c * chunk_bytes, buf, plane2_bytes, cudaMemcpyHostToDevice, L.st) != cudaSuccess ||
+            lane_bytes[(size_t)t] += copy_bytes;
+            if (cudaMemcpyAsync((char *)ctx->packed.p + (uint64_t)c * chunk_bytes, buf, copy_bytes, cudaMemcpyHostToDevice, L.st) != cudaSuccess ||
                 cudaEventRecord(L.ev[slot], L.st) != cudaSuccess) { cuda_err = 1; break; }
         }
         if (cudaStreamSynchronize(L.st) != cudaSuccess) cuda_err = 1;
@@ -969,42 +1000,27 @@ static int upload_packed(tidk_ctx *ctx, const uint8_t *seq, uint64_t total, int 
     uint64_t sp = n_ascii * chunk_seq;
     if (sp > total) sp = total;
     if (explore_mode) {
-        uint64_t n_packed = 0, ascii_bytes = 0;
-        for (uint64_t c = 0; c < n_chunks; c++) {
-            if (chunk_state[(size_t)c] == 1) n_packed++;
-            else ascii_bytes += total - c * chunk_seq < chunk_seq ? total - c * chunk_seq : chunk_seq;
-        }
-        size_t n_exc = 0;
-        for (const auto &v : exc) n_exc += v.size();
-        ctx->last_h2d += ascii_bytes + n_packed * plane2_bytes + n_exc * 40 + n_chunks;
+        uint64_t n_packed = 0;
+        for (uint64_t c = 0; c < n_chunks; c++) n_packed += chunk_state[(size_t)c] != 0;
+        ctx->last_h2d += sp + n_chunks * 4; // the front chunks by DMA + the chunk table
+        for (uint64_t b : lane_bytes) ctx->last_h2d += b;
         if (n_packed) {
-            if ((rc = ensure(ctx, ctx->chunk_state, (size_t)n_chunks))) return rc;
-            CU(ctx, cudaMemcpyAsync(ctx->chunk_state.p, chunk_state.data(), (size_t)n_chunks, cudaMemcpyHostToDevice, ctx->stream));
+            if ((rc = ensure(ctx, ctx->chunk_state, (size_t)n_chunks * 4))) return rc;
+            // (the host table is a ctx member: it outlives this copy; the next upload starts after a stream sync)
+            CU(ctx, cudaMemcpyAsync(ctx->chunk_state.p, chunk_state.data(), (size_t)n_chunks * 4, cudaMemcpyHostToDevice, ctx->stream));
             const uint64_t n_half = n_chunks * (uint64_t)kPackWords * 2, half0 = n_ascii * (uint64_t)kPackWords * 2;
             unpack_planes_kernel<<<(unsigned)((n_half - half0 + 1023) / 1024), 256, 0, ctx->stream>>>(
-                (const uint32_t *)ctx->packed.p, (const uint8_t *)ctx->chunk_state.p, ctx->scratch.d_seq, half0, n_half, total);
+                (const uint32_t *)ctx->packed.p, (const uint32_t *)ctx->chunk_state.p, ctx->scratch.d_seq, half0, n_half, total);
             CU(ctx, cudaGetLastError());
-        }
-        std::vector<uint64_t> all;
-        std::vector<uint8_t> raw;
-        if (n_exc) {
-            all.reserve(n_exc);
-            for (const auto &v : exc) all.insert(all.end(), v.begin(), v.end());
-            raw.assign(n_exc * 32, 0);
-            for (size_t i = 0; i < n_exc; i++) {
-                const uint64_t b0 = (all[i] >> 32) * 32;
-                if (b0 < total) memcpy(raw.data() + i * 32, seq + b0, (size_t)(total - b0 < 32 ? total - b0 : 32));
+            bool any_rec = false;
+            for (uint64_t c = n_ascii; c < n_chunks && !any_rec; c++) any_rec = chunk_state[(size_t)c] > 1;
+            if (any_rec) {
+                patch_words_kernel<<<(unsigned)((n_chunks - n_ascii) * (2 * kExcPerChunk / 256)), 256, 0, ctx->stream>>>(
+                    (const uint32_t *)ctx->packed.p, (const uint32_t *)ctx->chunk_state.p, ctx->scratch.d_seq, n_ascii);
+                CU(ctx, cudaGetLastError());
             }
-            if ((rc = ensure(ctx, ctx->exc, n_exc * 8))) return rc;
-            if ((rc = ensure(ctx, ctx->exc_raw, n_exc * 32))) return rc;
-            CU(ctx, cudaMemcpyAsync(ctx->exc.p, all.data(), n_exc * 8, cudaMemcpyHostToDevice, ctx->stream));
-            CU(ctx, cudaMemcpyAsync(ctx->exc_raw.p, raw.data(), n_exc * 32, cudaMemcpyHostToDevice, ctx->stream));
-            patch_words_kernel<<<(unsigned)((2 * n_exc + 255) / 256), 256, 0, ctx->stream>>>(
-                ctx->scratch.d_seq, (const uint64_t *)ctx->exc.p, (const uint4 *)ctx->exc_raw.p, 2 * (uint64_t)n_exc);
-            CU(ctx, cudaGetLastError());
         }
         CU(ctx, cudaMemsetAsync(ctx->scratch.d_seq + total, 0, kSeqPad, ctx->stream));
-        CU(ctx, cudaStreamSynchronize(ctx->stream)); // the pageable staging vectors go out of scope
         *split = sp;
         return TIDK_OK;
     }
