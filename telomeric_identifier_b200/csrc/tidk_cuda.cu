@@ -813,6 +813,7 @@ __global__ void va_scatter_kernel(uint32_t *packed, const uint64_t *exc, uint64_
 // 0.3 ms) and the raw words laid over them; the scan then runs unchanged.  The bus carries 0.25 B per base
 // instead of 1.
 constexpr uint32_t kExcPerChunk = tidk::kPackWords / 16; // more exception words than this: the chunk goes up as ASCII
+constexpr int kUnpackRounds = 16;
 
 __global__ void __launch_bounds__(256) unpack_planes_kernel(const uint32_t *packed, const uint32_t *chunk_state, uint8_t *seq,
                                                             uint64_t half0, uint64_t n_half_words, uint64_t total) {
@@ -827,9 +828,9 @@ __global__ void __launch_bounds__(256) unpack_planes_kernel(const uint32_t *pack
         lut[t] = v;
     }
     __syncthreads();
-#pragma unroll
-    for (int r = 0; r < 4; r++) { // 16 bases per thread and round, 16 KiB of sequence per CTA
-        const uint64_t i = half0 + ((uint64_t)blockIdx.x * 4 + r) * 256 + threadIdx.x;
+#pragma unroll 4
+    for (int r = 0; r < kUnpackRounds; r++) { // 16 bases per thread and round, 64 KiB of sequence per CTA (the table is built once)
+        const uint64_t i = half0 + ((uint64_t)blockIdx.x * kUnpackRounds + r) * 256 + threadIdx.x;
         if (i >= n_half_words) return;
         const uint64_t word = i >> 1;
         const uint64_t chunk = word >> tidk::kPackShift;
@@ -1009,7 +1010,7 @@ static int upload_packed(tidk_ctx *ctx, const uint8_t *seq, uint64_t total, int 
             // (the host table is a ctx member: it outlives this copy; the next upload starts after a stream sync)
             CU(ctx, cudaMemcpyAsync(ctx->chunk_state.p, chunk_state.data(), (size_t)n_chunks * 4, cudaMemcpyHostToDevice, ctx->stream));
             const uint64_t n_half = n_chunks * (uint64_t)kPackWords * 2, half0 = n_ascii * (uint64_t)kPackWords * 2;
-            unpack_planes_kernel<<<(unsigned)((n_half - half0 + 1023) / 1024), 256, 0, ctx->stream>>>(
+            unpack_planes_kernel<<<(unsigned)((n_half - half0 + 256 * kUnpackRounds - 1) / (256 * kUnpackRounds)), 256, 0, ctx->stream>>>(
                 (const uint32_t *)ctx->packed.p, (const uint32_t *)ctx->chunk_state.p, ctx->scratch.d_seq, half0, n_half, total);
             CU(ctx, cudaGetLastError());
             bool any_rec = false;
