@@ -61,25 +61,26 @@ inline int explore_runs_device(ExploreScratch &sc, cudaStream_t st, cudaEvent_t 
     if (n_records > 0x7FFFFFFFu) { err = "too many records"; return TIDK_EARG; }
     const bool planes = kmax <= (uint32_t)kPlaneMaxK; // bit-plane kernel; byte-wise kernel otherwise
     const uint32_t n_slices = n_records * 2;
-    uint64_t tile = kExploreTile;
-    if (planes) { // smaller items when the big ones would leave most of the GPU idle (C3: 60 slices)
-        uint64_t total = 0;
-        for (uint32_t r = 0; r < n_records; r++) total += 2 * split_dist(h_off[r + 1] - h_off[r], distance);
-        tile = total / kExTile < (uint64_t)sm_count * 32 ? kExTileSmall : kExTile;
-    }
     // The slice table (explore.rs:151-160) and the tile prefix sums are built on the device from the
-    // resident offsets; the host only needs the totals, which one pass over its copy of the offsets gives.
-    uint64_t scanned = 0, n_tiles = 0, max_dist = 0;
+    // resident offsets; the host only needs the totals, which ONE pass over its copy of the offsets gives
+    // (tiles counted for both item sizes: which one is used depends on the total).
+    uint64_t scanned = 0, max_dist = 0, nt_main = 0, nt_small = 0;
     const uint32_t extra = planes ? kmax : 0; // the plane kernel also evaluates the kmax positions behind the slice end
+    const uint64_t tile_main = planes ? kExTile : kExploreTile;
     for (uint32_t r = 0; r < n_records; r++) {
         const uint64_t len = h_off[r + 1] - h_off[r];
         const uint64_t dist = split_dist(len, distance);
         if (dist > len) { err = "slice longer than record"; return TIDK_EARG; }
         const uint64_t span = dist == 0 ? 0 : dist + extra;
-        n_tiles += 2 * ((span + tile - 1) / tile);
+        nt_main += 2 * ((span + tile_main - 1) / tile_main);
+        nt_small += 2 * ((span + kExTileSmall - 1) / kExTileSmall);
         scanned += 2 * dist;
         max_dist = std::max(max_dist, dist);
     }
+    // smaller items when the big ones would leave most of the GPU idle (C3: 60 slices)
+    const bool small_items = planes && scanned / kExTile < (uint64_t)sm_count * 32;
+    const uint64_t tile = small_items ? kExTileSmall : tile_main;
+    const uint64_t n_tiles = small_items ? nt_small : nt_main;
     // events as sortable 64-bit keys + device-side run building when the batch fits the key layout
     const uint64_t max_chunks = max_dist / kmin + 2;
     // TIDK_EXPLORE_HOST_POST=1 forces the struct events + host stitching path (tests exercise both)

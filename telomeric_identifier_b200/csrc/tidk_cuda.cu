@@ -1209,7 +1209,10 @@ int tidk_cuda_explore_runs(tidk_ctx *ctx, const uint8_t *seq, const uint64_t *of
                                            out_runs, n_runs, nullptr, nullptr);
 }
 
-void tidk_cuda_free_runs(tidk_run *runs) { free(runs); }
+void tidk_cuda_free_runs(tidk_run *runs) {
+    if (!runs) return;
+    if (!tidk::RunBlockPool::get().give_back(runs)) free(runs); // large lists live in pooled pinned blocks (explore_post.cuh)
+}
 
 int tidk_cuda_last_transfer(const tidk_ctx *ctx, uint64_t *h2d_bytes, uint64_t *d2h_bytes, int *host_packed) {
     if (!ctx) return TIDK_EARG;
