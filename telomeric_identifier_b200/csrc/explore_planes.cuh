@@ -30,6 +30,10 @@
 #include "explore.cuh"
 #include "planes.cuh"
 
+#ifndef TIDK_EX_LDS_PRMT
+#define TIDK_EX_LDS_PRMT 1 // chunk-end masks: table address and phase folded by one PRMT (see phase_addr)
+#endif
+
 namespace tidk {
 
 constexpr int kPlaneMaxK = 16;
@@ -230,8 +234,16 @@ __device__ __forceinline__ void explore_k(Stash &stash, const HTable &htab, uint
     const uint32_t nd_lo = __shfl_sync(0xFFFFFFFFu, bitsel(m31, carry_nd, nd_hi), src_lane);
     carry_nd = nd_hi;
     if (!EMIT) return; // special block: only the carries are kept consistent
+#if TIDK_EX_LDS_PRMT
+    // s8 already IS the shared-window address of the entry's row start + 8 * s (phase_addr): one LDS with an immediate
+    uint32_t nh_lo, nh_hi;
+    asm("ld.shared.v2.u32 {%0,%1}, [%2+%3];" : "=r"(nh_lo), "=r"(nh_hi) : "r"(s8), "n"((K - 1) * 128));
+    const unsigned long long nh = ((unsigned long long)nh_hi << 32) | nh_lo;
+    (void)htab;
+#else
     const unsigned long long nh = *reinterpret_cast<const unsigned long long *>(reinterpret_cast<const char *>(&htab.nh[K - 1][0]) + s8);
     const uint32_t nh_lo = (uint32_t)nh, nh_hi = (uint32_t)(nh >> 32);
+#endif
     // one 64-bit add: IADD3 + IMAD.X (issuing the low word as mad.wide to reach the fma pipe was tried: ptxas
     // splits it into IMAD.WIDE + IADD3 + IADD3.X, one instruction more)
     const unsigned long long sum = (((unsigned long long)(nd_hi & nh_hi) << 32) | (nd_lo & nh_lo)) + nh;
@@ -285,6 +297,17 @@ __device__ __forceinline__ void phase_step_all(uint32_t (&ph)[NREG]) {
     }
 }
 
+// TIDK_EX_LDS_PRMT: the chunk-end table sits 256-byte aligned in shared memory, so "table address + 8 * s_K" is ONE
+// PRMT (byte 0 from the phase register, bytes 1-3 from the table's shared-window address) and the row of K is the
+// load's immediate -- no address add per k, and no generic-to-shared conversion inside the block loop.
+template <int KBASE, int NREG, int K>
+__device__ __forceinline__ uint32_t phase_addr(const uint32_t (&ph)[NREG], uint32_t htab_s) {
+    if constexpr (K >= KBASE && K < KBASE + 4 * NREG)
+        return __byte_perm(ph[(K - KBASE) / 4], htab_s, 0x7650u + (uint32_t)((K - KBASE) % 4));
+    else
+        return htab_s;
+}
+
 // 8 * s_K out of the packed phase registers (one PRMT); K outside the registers' range never runs
 template <int KBASE, int NREG, int K>
 __device__ __forceinline__ uint32_t phase_byte(const uint32_t (&ph)[NREG]) {
@@ -308,11 +331,12 @@ __device__ __forceinline__ uint32_t div_exact(uint32_t q, uint32_t k) { return (
 template <int KMIN, int KMAX>
 __global__ void __launch_bounds__(256, TIDK_EX_MINB) explore_planes_kernel(const ExJob job) {
     __shared__ EvStash<(KMIN > 0 ? KMAX - KMIN + 1 : kPlaneMaxK)> stash;
-    __shared__ HTable htab;
+    __shared__ __align__(256) HTable htab;
     constexpr int KBASE = KMIN > 0 ? KMIN : 1;                         // first k of the packed phase registers
     constexpr int NREG = KMIN > 0 ? (KMAX - KMIN) / 4 + 1 : kPlaneMaxK / 4;
     fill_htable(htab);
     __syncthreads();
+    const uint32_t htab_s = (uint32_t)__cvta_generic_to_shared(&htab); // low byte 0 (256-byte aligned)
     const int lane = threadIdx.x & 31;
     const uint32_t m31 = lane == 31 ? 0xFFFFFFFFu : 0u; // look-behind: lane 31 sends its previous-block value
     const int src_lane = (lane + 31) & 31;
@@ -466,7 +490,7 @@ __global__ void __launch_bounds__(256, TIDK_EX_MINB) explore_planes_kernel(const
 #define TIDK_EXK(K, VA, CS, EM)                                                                   \
     if ((KMIN > 0) ? (K >= KMIN && K <= KMAX) : (job.kmin <= K && K <= job.kmax)) {              \
         explore_k<K, (K >= KBASE ? K - KBASE : 0), VA, CS, EM>(stash, htab, any_ev, cur, prv, carry_nd[K - 1], m31, src_lane,  \
-                                 phase_byte<KBASE, NREG, K>(ph), own);                             \
+                                 TIDK_EX_LDS_PRMT ? phase_addr<KBASE, NREG, K>(ph, htab_s) : phase_byte<KBASE, NREG, K>(ph), own); \
     }
 #define TIDK_EXALL(VA, CS, EM)                                                                    \
     TIDK_EXK(1, VA, CS, EM) TIDK_EXK(2, VA, CS, EM) TIDK_EXK(3, VA, CS, EM) TIDK_EXK(4, VA, CS, EM)     \
