@@ -336,7 +336,8 @@ __global__ void __launch_bounds__(256, TIDK_EX_MINB) explore_planes_kernel(const
     constexpr int NREG = KMIN > 0 ? (KMAX - KMIN) / 4 + 1 : kPlaneMaxK / 4;
     fill_htable(htab);
     __syncthreads();
-    const uint32_t htab_s = (uint32_t)__cvta_generic_to_shared(&htab); // low byte 0 (256-byte aligned)
+    uint32_t htab_s; // shared-window address of the table, low byte 0 (256-byte aligned); volatile: computed once, not per block
+    asm volatile("{\n\t.reg .u64 t;\n\tcvta.to.shared.u64 t, %1;\n\tcvt.u32.u64 %0, t;\n\t}" : "=r"(htab_s) : "l"(&htab));
     const int lane = threadIdx.x & 31;
     const uint32_t m31 = lane == 31 ? 0xFFFFFFFFu : 0u; // look-behind: lane 31 sends its previous-block value
     const int src_lane = (lane + 31) & 31;
@@ -430,12 +431,29 @@ __global__ void __launch_bounds__(256, TIDK_EX_MINB) explore_planes_kernel(const
             const bool edge_plain = edge && all_plain && calm && (blk == 0 || (prev_last_plain && case_prev == 0));
             uint32_t inslice = 0xFFFFFFFFu;
             cur.lo = core.lo; cur.hi = core.hi;
+            const uint32_t xoff = (uint32_t)prel; // < 2^15
+#define TIDK_EXK(K, VA, CS, EM)                                                                   \
+    if ((KMIN > 0) ? (K >= KMIN && K <= KMAX) : (job.kmin <= K && K <= job.kmax)) {              \
+        explore_k<K, (K >= KBASE ? K - KBASE : 0), VA, CS, EM>(stash, htab, any_ev, cur, prv, carry_nd[K - 1], m31, src_lane,  \
+                                 TIDK_EX_LDS_PRMT ? phase_addr<KBASE, NREG, K>(ph, htab_s) : phase_byte<KBASE, NREG, K>(ph), own); \
+    }
+#define TIDK_EXALL(VA, CS, EM)                                                                    \
+    TIDK_EXK(1, VA, CS, EM) TIDK_EXK(2, VA, CS, EM) TIDK_EXK(3, VA, CS, EM) TIDK_EXK(4, VA, CS, EM)     \
+    TIDK_EXK(5, VA, CS, EM) TIDK_EXK(6, VA, CS, EM) TIDK_EXK(7, VA, CS, EM) TIDK_EXK(8, VA, CS, EM)     \
+    TIDK_EXK(9, VA, CS, EM) TIDK_EXK(10, VA, CS, EM) TIDK_EXK(11, VA, CS, EM) TIDK_EXK(12, VA, CS, EM)  \
+    TIDK_EXK(13, VA, CS, EM) TIDK_EXK(14, VA, CS, EM) TIDK_EXK(15, VA, CS, EM) TIDK_EXK(16, VA, CS, EM)
             if (fast) {
+                // self-contained: nothing of the case / N / validity state is touched.  Only lane 31's own_prev is ever
+                // read (lane_lookbehind), and its va / cs / nn already are ~0 / 0 / 0 here: prev_last_plain says the
+                // word was in the slice and A/C/G/T, case_prev == 0 that it was upper case; both stay as they are.
                 cur.va = 0xFFFFFFFFu; cur.cs = 0u; cur.nn = 0u;
                 prv.lo = lane_lookbehind(cur.lo, own_prev.lo, lane);
                 prv.hi = lane_lookbehind(cur.hi, own_prev.hi, lane);
                 prv.va = 0xFFFFFFFFu; prv.cs = 0u; prv.nn = 0u;
-            } else if (edge_plain) {
+                own_prev.lo = cur.lo; own_prev.hi = cur.hi;
+                TIDK_EXALL(false, false, true)
+            } else {
+            if (edge_plain) {
                 inslice = range_mask32(v_lo - prel, v_hi - prel);
                 own = range_mask32(own_lo - prel, own_hi - prel);
                 cur.va = inslice; cur.cs = 0u; cur.nn = 0u;
@@ -486,29 +504,19 @@ __global__ void __launch_bounds__(256, TIDK_EX_MINB) explore_planes_kernel(const
             }
             own_prev = cur;
             prev_last_plain = (plain_lanes >> 31) != 0u && (!edge || __shfl_sync(0xFFFFFFFFu, inslice, 31) == 0xFFFFFFFFu);
-            const uint32_t xoff = (uint32_t)prel; // < 2^15
-#define TIDK_EXK(K, VA, CS, EM)                                                                   \
-    if ((KMIN > 0) ? (K >= KMIN && K <= KMAX) : (job.kmin <= K && K <= job.kmax)) {              \
-        explore_k<K, (K >= KBASE ? K - KBASE : 0), VA, CS, EM>(stash, htab, any_ev, cur, prv, carry_nd[K - 1], m31, src_lane,  \
-                                 TIDK_EX_LDS_PRMT ? phase_addr<KBASE, NREG, K>(ph, htab_s) : phase_byte<KBASE, NREG, K>(ph), own); \
-    }
-#define TIDK_EXALL(VA, CS, EM)                                                                    \
-    TIDK_EXK(1, VA, CS, EM) TIDK_EXK(2, VA, CS, EM) TIDK_EXK(3, VA, CS, EM) TIDK_EXK(4, VA, CS, EM)     \
-    TIDK_EXK(5, VA, CS, EM) TIDK_EXK(6, VA, CS, EM) TIDK_EXK(7, VA, CS, EM) TIDK_EXK(8, VA, CS, EM)     \
-    TIDK_EXK(9, VA, CS, EM) TIDK_EXK(10, VA, CS, EM) TIDK_EXK(11, VA, CS, EM) TIDK_EXK(12, VA, CS, EM)  \
-    TIDK_EXK(13, VA, CS, EM) TIDK_EXK(14, VA, CS, EM) TIDK_EXK(15, VA, CS, EM) TIDK_EXK(16, VA, CS, EM)
             // four straight-line variants, chosen per block (warp-uniform):
             //   interior of a clean stretch (every base of both words valid, uniform case) -> lo/hi only
             //   clean block at a slice edge                                                -> + va plane
             //   mixed letter case / case change / N present                                -> + va + case + N planes
             //   special block (bytes other than A C G T N)                                 -> carries only + byte-wise
-            bool lohi_only = fast;
-            if (!fast && !special && !need_cs && !edge) // (edge blocks own only part of their positions: VA variant)
+            bool lohi_only = false;
+            if (!special && !need_cs && !edge) // (edge blocks own only part of their positions: VA variant)
                 lohi_only = __all_sync(0xFFFFFFFFu, (cur.va & prv.va) == 0xFFFFFFFFu);
             if (lohi_only) { TIDK_EXALL(false, false, true) }
             else if (special) { TIDK_EXALL(true, false, false) }
             else if (need_cs) { TIDK_EXALL(true, true, true) }
             else { TIDK_EXALL(true, false, true) }
+            } // !fast
 #undef TIDK_EXALL
 #undef TIDK_EXK
             if (any_ev) { // rare: this lane found run boundaries in this block
