@@ -188,8 +188,14 @@ __device__ __forceinline__ void fill_htable(HTable &tab) {
 // all four bytes at once (no byte overflows: 16k - 16 + 128 - 8k < 256 for k <= 16).
 template <int KBASE, int REG>
 struct PhaseConst {
-    __host__ __device__ static constexpr uint32_t byte_of(int k, int what) { // what 0: 8 * ((k - 1024 % k) % k), 1: 0x80 - 8k, 2: 8k
-        return k > kPlaneMaxK ? 0u : what == 0 ? 8u * (uint32_t)((k - 1024 % k) % k) : what == 1 ? 0x80u - 8u * (uint32_t)k : 8u * (uint32_t)k;
+    __host__ __device__ static constexpr uint32_t byte_of(int k, int what) { // what 0: 8 * ((k - 1024 % k) % k), 1: 0x80 - 8k, 2: 8k,
+        return k > kPlaneMaxK ? 0u                                                  //      3: 0x80 - k, 4: k, 5: k - 1
+               : what == 0 ? 8u * (uint32_t)((k - 1024 % k) % k)
+               : what == 1 ? 0x80u - 8u * (uint32_t)k
+               : what == 2 ? 8u * (uint32_t)k
+               : what == 3 ? 0x80u - (uint32_t)k
+               : what == 4 ? (uint32_t)k
+                           : (uint32_t)(k - 1);
     }
     __host__ __device__ static constexpr uint32_t word(int what) {
         return byte_of(KBASE + 4 * REG, what) | byte_of(KBASE + 4 * REG + 1, what) << 8 |
@@ -204,6 +210,20 @@ __device__ __forceinline__ uint32_t phase_step(uint32_t p) {
     p += INC;
     const uint32_t ge = ((p + CMP) >> 7) & 0x01010101u; // byte >= 8k
     return p - ((ge * 0xFFu) & MOD);
+}
+
+// Phases of an item's block 0 for this lane, four k at once.  r = the item's (rel0 mod k) bytes, c = this lane's
+// (32 * lane + 32 * (k - 1)) mod k bytes (computed once per thread): x = (r + c) mod k is the offset of the lane's
+// bit 0 inside its chunk (of the PREVIOUS word), s = k - 1 - x the bit of the first chunk end there; returns 8 * s.
+// Byte-parallel like phase_step: r + c < 2k <= 32, so no byte overflows.
+template <int KBASE, int REG>
+__device__ __forceinline__ uint32_t phase_init(uint32_t r, uint32_t c) {
+    constexpr uint32_t CMP = PhaseConst<KBASE, REG>::word(3), MOD = PhaseConst<KBASE, REG>::word(4),
+                       KM1 = PhaseConst<KBASE, REG>::word(5);
+    uint32_t x = r + c;
+    const uint32_t ge = ((x + CMP) >> 7) & 0x01010101u; // byte >= k
+    x -= (ge * 0xFFu) & MOD;
+    return (KM1 - x) << 3;
 }
 
 // One k for one 32-base word.  WITH_VA: honour the validity plane (edge blocks); interior blocks of
@@ -308,6 +328,14 @@ __device__ __forceinline__ uint32_t phase_addr(const uint32_t (&ph)[NREG], uint3
         return htab_s;
 }
 
+template <int KBASE, int NREG, int G = 0>
+__device__ __forceinline__ void phase_init_all(uint32_t (&ph)[NREG], const uint32_t (&rw)[4], const uint32_t (&lane_c)[NREG]) {
+    if constexpr (G < NREG) {
+        ph[G] = phase_init<KBASE, G>(rw[(KBASE - 1) / 4 + G], lane_c[G]);
+        phase_init_all<KBASE, NREG, G + 1>(ph, rw, lane_c);
+    }
+}
+
 // 8 * s_K out of the packed phase registers (one PRMT); K outside the registers' range never runs
 template <int KBASE, int NREG, int K>
 __device__ __forceinline__ uint32_t phase_byte(const uint32_t (&ph)[NREG]) {
@@ -341,6 +369,16 @@ __global__ void __launch_bounds__(256, TIDK_EX_MINB) explore_planes_kernel(const
     const int lane = threadIdx.x & 31;
     const uint32_t m31 = lane == 31 ? 0xFFFFFFFFu : 0u; // look-behind: lane 31 sends its previous-block value
     const int src_lane = (lane + 31) & 31;
+    uint32_t lane_c[NREG]; // byte b of lane_c[g]: (32 * lane + 32 * (k - 1)) mod k for k = KBASE + 4g + b (see phase_init)
+#pragma unroll
+    for (int g = 0; g < NREG; g++) {
+        lane_c[g] = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int k = KBASE + 4 * g + b;
+            if (k <= kPlaneMaxK) lane_c[g] |= ((32u * (uint32_t)lane + 32u * (uint32_t)(k - 1)) % (uint32_t)k) << (8 * b);
+        }
+    }
     uint32_t nonascii = 0;
     // Work queue, pipelined like the window counter's: the ticket of the item after next is drawn while
     // an item is scanned, the next item's block 0 address is fetched at the start of the current item,
@@ -378,17 +416,10 @@ __global__ void __launch_bounds__(256, TIDK_EX_MINB) explore_planes_kernel(const
         for (int i = 0; i < kPlaneMaxK; i++) carry_nd[i] = 0xFFFFFFFFu;
         // chunk phases of block 0 for this lane: s_k = (k-1) - (rel0 + 32 * lane - 32) mod k, kept as 8 * s_k
         uint32_t ph[NREG];
-#pragma unroll
-        for (int g = 0; g < NREG; g++) {
-            ph[g] = 0;
-#pragma unroll
-            for (int b = 0; b < 4; b++) {
-                const int k = KBASE + 4 * g + b;
-                if (k <= kPlaneMaxK) {
-                    const uint32_t x = (r0_of(rq0, k - 1) + (uint32_t)lane * 32u + 32u * (uint32_t)(k - 1)) % (uint32_t)k;
-                    ph[g] |= (8u * ((uint32_t)(k - 1) - x)) << (8 * b);
-                }
-            }
+        static_assert((KBASE - 1) % 4 == 0, "the r0 bytes of a phase register are one word of the descriptor's r0 vector");
+        {
+            const uint32_t rw[4] = {rq0.x, rq0.y, rq0.z, rq0.w}; // r0[k - 1], k = 1..16
+            phase_init_all<KBASE, NREG>(ph, rw, lane_c);
         }
         bool dirty_prev = false;
         int case_prev = -1; // -1 unknown (first block), 0 all upper, 1 all lower, 2 mixed
