@@ -399,7 +399,9 @@ __global__ void __launch_bounds__(256, TIDK_EX_MINB) explore_planes_kernel(const
         uint64_t scan0_next = 0;
         if (have_next) scan0_next = job.items[item_next].scan0;
         unsigned long long t2 = 0;
-        if (lane == 0) t2 = atomicAdd(job.work_counter, 1ull);
+        // (a plain atom: only lane 0 gets here, the compiler's warp-aggregated atomicAdd would add a vote, a leader
+        // election and two shuffles per item)
+        if (lane == 0) asm volatile("atom.global.add.u64 %0, [%1], 1;" : "=l"(t2) : "l"(job.work_counter) : "memory");
         const uint64_t scan0 = ip->scan0;
         const int64_t rel0 = ip->rel0;
         const int64_t m = (int64_t)ip->slice_len;
@@ -483,8 +485,10 @@ __global__ void __launch_bounds__(256, TIDK_EX_MINB) explore_planes_kernel(const
                 prv.va = 0xFFFFFFFFu; prv.cs = 0u; prv.nn = 0u;
                 own_prev.lo = cur.lo; own_prev.hi = cur.hi;
                 TIDK_EXALL(false, false, true)
-            } else {
-            if (edge_plain) {
+            } else if (edge_plain) {
+                // self-contained like the plain path, plus the slice masks.  Lane 31's case / N planes of the block
+                // before are 0 already (block 0: the item's initial state; later: prev_last_plain && case_prev == 0)
+                // and stay 0, the N / dirty state stays calm.
                 inslice = range_mask32(v_lo - prel, v_hi - prel);
                 own = range_mask32(own_lo - prel, own_hi - prel);
                 cur.va = inslice; cur.cs = 0u; cur.nn = 0u;
@@ -492,8 +496,12 @@ __global__ void __launch_bounds__(256, TIDK_EX_MINB) explore_planes_kernel(const
                 prv.hi = lane_lookbehind(cur.hi, own_prev.hi, lane);
                 prv.va = lane_lookbehind(cur.va, own_prev.va, lane);
                 prv.cs = 0u; prv.nn = 0u;
-                case_prev = 0; // all upper case (the other state stays calm)
+                case_prev = 0; // all upper case
+                own_prev.lo = cur.lo; own_prev.hi = cur.hi; own_prev.va = cur.va;
+                prev_last_plain = __shfl_sync(0xFFFFFFFFu, inslice, 31) == 0xFFFFFFFFu; // (all 32 lanes are plain here)
+                TIDK_EXALL(true, false, true)
             } else {
+            {
                 uint32_t na = 0;
                 const Planes P = finish_planes(nib, core, __any_sync(0xFFFFFFFFu, core.bad != 0u), na);
                 if (edge) {
