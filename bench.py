@@ -180,6 +180,9 @@ def main():
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        # NCCL writes its banner ("NCCL version ...") and any NCCL_DEBUG output to stdout by default; stdout is
+        # reserved for the one JSON line, so route NCCL's log to stderr unless the caller chose a file
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
