@@ -139,6 +139,15 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line.  Libraries write there too (NCCL prints its "NCCL version ..." banner to
+    # stdout with printf when NCCL_DEBUG=VERSION, whatever NCCL_DEBUG_FILE says), so file descriptor 1 is pointed at
+    # stderr for the whole run and the line goes out through a private duplicate of the original stdout.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -170,7 +179,7 @@ def main():
                 "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -180,9 +189,6 @@ def main():
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
-        # NCCL writes its banner ("NCCL version ...") and any NCCL_DEBUG output to stdout by default; stdout is
-        # reserved for the one JSON line, so route NCCL's log to stderr unless the caller chose a file
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
@@ -344,7 +350,7 @@ def main():
             for v in explore.values():
                 v["frac_of_hbm_peak"] = v["scan_gbases_per_s"] / peak
             line["explore"] = explore
-        print(json.dumps(line))
+        emit(line)
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
