@@ -1,23 +1,34 @@
 #!/usr/bin/env python
-"""bench.py -- the hot path of tidk on B200, measured the way BASELINE.json names it.
+"""bench.py -- the hot path of tidk on B200, measured on the configuration BASELINE.json's target
+sentence is written on: config 4, `tidk search --string TTAGGG --window 10000` on the synthetic
+human-scale 3.1 Gb / 24-chromosome genome with N gaps.
 
-Workload (N = 1): BASELINE config[1] -- `tidk find --clade Lepidoptera` (one repeat,
-AACCT) with --window 10000 on a synthetic 500 Mb / 30-chromosome genome.
-A "step" is one pass of the window counter over the whole genome.
+  N = 1   the whole genome resident on one GPU.
+  N > 1   (torchrun, one rank per GPU) the SAME genome cut into N contiguous window ranges
+          (sharding.plan_shards: whole chromosomes where possible, long ones split at multiples of
+          W, so no halo and no data-path collective): "scaling": "strong".  Every rank generates
+          only the chromosomes its range touches.
 
-  value     Gbases/s, genome already resident in HBM, K steps, wall clock between
-            synchronisations, max over ranks (the per-step device time of the counting
-            kernel, from CUDA events on the library's stream, feeds `roofline`)
-  e2e       Gbases/s through the C ABI with HOST (pinned) buffers: H2D of the genome,
+A "step" is PASSES (32) passes of the window counter over the resident genome, issued through the
+asynchronous entry point (tidk_cuda_window_counts_resident_async: the counts of pass i leave the device
+while pass i + 1 counts) and collected with tidk_cuda_wait at the end of the step, so the counts of every
+pass are in host memory when its step ends.  Passes are what makes the timed region long enough (>= 0.3 s
+at N = 1) for a wall-clock number; `value` counts every pass.
+
+  value     Gbases/s, genome resident in HBM, wall clock between barriers, max over ranks
+  roofline  algorithmic bytes (1 B per scanned base) / device time of the counting kernel (CUDA events on
+            the library's stream, summed by tidk_cuda_wait) vs the measured HBM peak
+  e2e       Gbases/s through the C ABI with HOST (pinned) buffers: H2D of the (shard of the) genome,
             kernel, D2H of the counts inside the timed region, every step
-  roofline  algorithmic bytes (1 B per scanned base) / kernel time vs the measured HBM peak
-  cpu_baseline  the CPU oracle (a port of the reference's algorithm; the Rust reference
-            cannot be built in this image) on the same workload, 1 thread as in the reference
+  e2e_fasta FASTA file (page cache warm) -> TSV file through the C++ `tidk` driver in a fresh process:
+            parse, CUDA context, upload, count, format, write (N = 1: one device; N > 1: rank 0 runs
+            `--gpus N` in one process while the other ranks wait)
+  roofline_explore  the other half of the path (explore) on config-5-shaped reads
+            (100 000 HiFi-like reads, 1.5 Gb, --distance 0.5, k = 5..12), N = 1 only
+  cpu_baseline  the CPU oracle (a port of the reference's algorithm; the Rust reference cannot be
+            built in this image) on the same genome, all host cores, window ranges over threads
 
-N > 1 (torchrun, one rank per GPU): every rank holds its own 30-chromosome genome
-(seed + rank) -- records shard across ranks with no data-path collective ("weak").
-
-`--impl reference` times the CPU oracle instead (rank 0 only).
+`--impl reference` times the CPU oracle instead (rank 0 only), all host cores.
 """
 from __future__ import annotations
 
@@ -28,6 +39,7 @@ import subprocess
 import sys
 import tempfile
 import time
+from concurrent.futures import ThreadPoolExecutor
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -35,9 +47,11 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 WINDOW = 10000
-REPEATS = [b"AACCT"]  # clades/curated.csv: every Lepidoptera row is AACCT
-METRIC = "find_window_count_throughput"
+QUERY = [b"TTAGGG"]
+PASSES = int(os.environ.get("TIDK_BENCH_PASSES", "32"))
+METRIC = "search_window_count_throughput"
 UNIT = "Gbases/s"
+SCALE = float(os.environ.get("TIDK_BENCH_SCALE", "1.0"))
 
 
 def measured_peak():
@@ -99,36 +113,204 @@ class ClockSampler:
         return out
 
 
-def make_workload(seed: int):
+# ------------------------------------------------------------------------------- workload
+def c4_offsets():
     from telomeric_identifier_b200 import synth
-    scale = float(os.environ.get("TIDK_BENCH_SCALE", "1.0"))
-    ids, seq, off = synth.config2(scale=scale, seed=seed)
-    return ids, seq, off, scale
+    lens = synth.config4_lengths(SCALE)
+    off = np.zeros(len(lens) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(lens)
+    return off
 
 
-def cpu_leg(seq, off, steps, warmup, budget_s=150.0):
-    """Time the CPU oracle (1 thread: search.rs:57 / finder.rs:85 are sequential loops)."""
+def c4_shard(rank: int, world: int, threads: int):
+    """This rank's contiguous window range of the C4 genome as a local batch (one sub-record per
+    piece of a chromosome).  Returns (plan pieces, local sequence, local offsets, global offsets)."""
+    from telomeric_identifier_b200 import sharding, synth
+    off = c4_offsets()
+    pieces = sharding.plan_shards(off, WINDOW, world)[rank]
+    recs = sorted({p[0] for p in pieces})
+    with ThreadPoolExecutor(max(1, min(threads, len(recs) or 1))) as ex:  # Philox streams keyed by chromosome: any subset, any order
+        chrom = dict(zip(recs, ex.map(lambda i: synth.config4_contig(i, SCALE)[1], recs)))
+    lens = []
+    for rec, first, n in pieces:
+        lo = first * WINDOW
+        hi = min((first + n) * WINDOW, chrom[rec].size)
+        lens.append(hi - lo)
+    loff = np.zeros(len(pieces) + 1, dtype=np.uint64)
+    if lens:
+        loff[1:] = np.cumsum(np.asarray(lens, dtype=np.uint64))
+    return pieces, chrom, loff, off
+
+
+def fill_shard(dst: np.ndarray, pieces, chrom, loff):
+    for i, (rec, first, n) in enumerate(pieces):
+        lo = first * WINDOW
+        a, b = int(loff[i]), int(loff[i + 1])
+        dst[a:b] = chrom[rec][lo:lo + (b - a)]
+
+
+def split_for_threads(off: np.ndarray, threads: int):
+    """Window ranges as sub-records so that the record-sharded oracle keeps every core busy (windows are
+    independent, search.rs:98: cutting a record at a multiple of W changes no count)."""
+    from telomeric_identifier_b200 import sharding
+    plans = sharding.plan_shards(off, WINDOW, max(1, threads * 4))
+    sub = [0]
+    for pieces in plans:
+        for rec, first, n in pieces:
+            o, e = int(off[rec]), int(off[rec + 1])
+            sub.append(min(o + (first + n) * WINDOW, e))
+    return np.asarray(sub, dtype=np.uint64)
+
+
+def cpu_counts(seq, off, threads):
     from oracle import oracle as O
-    # bounded sample: whole chromosomes from the front until the whole run fits the budget
-    probe_n = min(int(off[1]), seq.size)
-    t0 = time.perf_counter()
-    O.window_counts(seq[:min(probe_n, 4_000_000)], np.array([0, min(probe_n, 4_000_000)], dtype=np.uint64), WINDOW, REPEATS, False)
-    rate = min(probe_n, 4_000_000) / max(time.perf_counter() - t0, 1e-6)
-    max_bases = rate * budget_s / max(steps + warmup, 1)
-    nrec = 1
-    while nrec < len(off) - 1 and int(off[nrec + 1]) <= max_bases:
-        nrec += 1
-    sub_off = off[:nrec + 1].copy()
-    sub = seq[:int(sub_off[-1])]
+    sub = split_for_threads(off, threads) if threads > 1 else off
+    return O.window_counts(seq, sub, WINDOW, QUERY, True, threads=threads)
+
+
+def write_fasta(path, ids, seq, off):
+    with open(path, "wb") as fh:
+        for i, rid in enumerate(ids):
+            s = seq[int(off[i]):int(off[i + 1])]
+            fh.write(f">{rid}\n".encode())
+            full = (s.size // 60) * 60
+            body = np.empty((full // 60, 61), dtype=np.uint8)
+            body[:, :60] = s[:full].reshape(-1, 60)
+            body[:, 60] = 10
+            fh.write(body.tobytes())
+            if full < s.size:
+                fh.write(s[full:].tobytes() + b"\n")
+
+
+def reference_arm(args, emit, config, steps, warmup):
+    """The CPU oracle on a bounded sample of the same genome (three whole chromosomes), every host core."""
+    from telomeric_identifier_b200 import synth
+    ncpu = os.cpu_count() or 1
+    recs = [19, 20, 21]
+    with ThreadPoolExecutor(3) as ex:
+        parts = list(ex.map(lambda i: synth.config4_contig(i, SCALE)[1], recs))
+    off = np.zeros(len(parts) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([p.size for p in parts])
+    seq = np.concatenate(parts)
     for _ in range(warmup):
-        O.window_counts(sub, sub_off, WINDOW, REPEATS, False)
+        cpu_counts(seq, off, ncpu)
     t0 = time.perf_counter()
     for _ in range(steps):
-        f, r = O.window_counts(sub, sub_off, WINDOW, REPEATS, False)
+        cpu_counts(seq, off, ncpu)
     dt = time.perf_counter() - t0
-    return dict(value=sub.size * steps / dt / 1e9, unit=UNIT, cores=1, kind="port",
-                sample=f"first {nrec} of {len(off) - 1} chromosomes ({sub.size} bases) x {steps} passes; "
-                       f"oracle/tidk_oracle.c restates tidk 0.2.7 (the Rust reference cannot be built here)"), dt / steps
+    t1 = time.perf_counter()
+    cpu_counts(seq, off, 1)
+    dt1 = time.perf_counter() - t1
+    value = seq.size * steps / dt / 1e9
+    cb = {"value": value, "unit": UNIT, "cores": ncpu, "kind": "port",
+          "sample": f"chromosomes 20, 21, 22 of the C4 genome ({seq.size} bases), one pass per step, window ranges sharded "
+                    f"over {ncpu} threads; oracle/tidk_oracle.c restates tidk 0.2.7 (the Rust reference cannot be built here)",
+          "single_thread_as_the_reference_runs": {"value": seq.size / dt1 / 1e9, "unit": UNIT, "cores": 1,
+                                                  "note": "search.rs:57 is one sequential loop; one pass over the same sample"}}
+    emit({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+          "steps": steps, "warmup": warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+          "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
+          "cpu_baseline": cb,
+          "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+          "gpu_launches": 0})
+
+
+def explore_block(ctx, peak):
+    """explore on config-5-shaped reads: 100 000 reads ~N(15 kb, 2 kb), --distance 0.5, k = 5..12, threshold 100."""
+    from telomeric_identifier_b200 import synth
+    from oracle import oracle as O
+    n_reads = max(1000, int(100_000 * SCALE))
+    ids, seq, off = synth.config5(n_reads)
+    lens = (off[1:] - off[:-1]).astype(np.int64)
+    scanned = int((2 * ((lens + 1) // 2)).sum())  # 2 * ceil(len / 2)
+    pseq = ctx.pinned_empty(seq.size)
+    pseq[:] = seq
+    batch = ctx.upload(pseq, off)
+    out = {"workload": f"C5-shaped: {n_reads} reads, {seq.size} bases, explore --minimum 5 --maximum 12 --threshold 100 --distance 0.5",
+           "scanned_bases": scanned, "k_range": [5, 12], "threshold": 100}
+    runs = None
+    for name, kmin, kmax in (("k5_12", 5, 12), ("k6_single", 6, 6)):
+        best = None
+        for _ in range(7):
+            t0 = time.perf_counter()
+            r = ctx.explore_runs_resident(batch, 0.5, kmin, kmax, 100)
+            wall = time.perf_counter() - t0
+            sm, pm = ctx.explore_timings()
+            if best is None or sm < best[0]:
+                best = (sm, pm, wall)
+        if name == "k5_12":
+            runs = r
+        ach = scanned / (best[0] * 1e-3) / 1e9
+        out[name] = {"scan_kernel_ms": best[0], "post_ms": best[1], "resident_call_wall_ms": best[2] * 1e3, "runs": int(r.size),
+                     "scan_gbases_per_s": ach,
+                     "roofline": {"bound": "alu pipe (instruction issue), not hbm: see DESIGN.md 3.3", "achieved": ach, "peak": peak,
+                                  "unit": "GB/s", "frac": ach / peak, "algorithmic_bytes_per_launch": scanned}}
+    # the same call through the host-pointer entry point (upload inside)
+    e2e_ms = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        r2 = ctx.explore_runs(pseq, off, 0.5, 5, 12, 100)
+        w = (time.perf_counter() - t0) * 1e3
+        e2e_ms = w if e2e_ms is None else min(e2e_ms, w)
+    h2d, _, packed = ctx.last_transfer()
+    out["e2e_host_pointer"] = {"ms_per_call": e2e_ms, "value": seq.size / (e2e_ms * 1e-3) / 1e9, "unit": UNIT,
+                               "h2d_bytes": h2d, "host_packed": packed, "runs_equal_resident": bool(np.array_equal(r2, runs))}
+    # CPU port beside it: rayon's one-worker-per-record sharding (explore.rs:97-100) as one thread per core, on a
+    # bounded sample (the first tenth of the reads), full run lists compared field by field
+    nsub = max(100, n_reads // 10)
+    sub_off = off[:nsub + 1]
+    ncpu = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    cpu_runs, _ = O.explore_runs(seq[:int(sub_off[-1])], sub_off, 0.5, 5, 12, 100, False, ncpu)
+    cdt = time.perf_counter() - t0
+    mine = runs[runs["record"] < nsub]
+    mine = mine[np.lexsort((mine["start"], mine["slice"], mine["record"], mine["k"]))]
+    same = mine.size == cpu_runs.size and all(np.array_equal(mine[f], cpu_runs[f]) for f in ("record", "slice", "k", "start", "end"))
+    out["cpu_baseline"] = {"value": int(2 * ((lens[:nsub] + 1) // 2).sum()) / cdt / 1e9, "unit": UNIT, "cores": ncpu, "kind": "port",
+                           "sample": f"first {nsub} reads, one pass, records sharded over threads",
+                           "run_lists_equal_to_gpu": bool(same)}
+    batch.free()
+    return out
+
+
+def fasta_e2e(pieces_all, world, local):
+    """FASTA file -> TSV file through the C++ driver in a fresh process (context creation included)."""
+    from telomeric_identifier_b200 import synth
+    tidk = os.path.join(ROOT, "telomeric_identifier_b200", "bin", "tidk")
+    if not os.path.exists(tidk):
+        return {"unavailable": "bin/tidk not built"}
+    d = tempfile.mkdtemp(prefix="tidk_bench_")
+    fa = os.path.join(d, "c4.fa")
+    ids, seq, off = pieces_all
+    t0 = time.perf_counter()
+    write_fasta(fa, ids, seq, off)
+    wrote_s = time.perf_counter() - t0
+    best = None
+    for rep in range(2):
+        t0 = time.perf_counter()
+        r = subprocess.run([tidk, "search", fa, "-s", "TTAGGG", "-w", str(WINDOW), "-o", "c4", "-d", d, "--gpu-stats",
+                            "--device", str(local), "--gpus", str(world)], capture_output=True, text=True)
+        dt = time.perf_counter() - t0
+        stats = [l for l in r.stderr.splitlines() if l.startswith("{")]
+        if r.returncode != 0:
+            return {"unavailable": f"tidk search failed rc={r.returncode}: {r.stderr[-300:]}"}
+        if best is None or dt < best[0]:
+            best = (dt, json.loads(stats[-1]) if stats else {})
+    tsv = os.path.join(d, "c4_telomeric_repeat_windows.tsv")
+    out = {"value": int(seq.size) / best[0] / 1e9, "unit": UNIT, "wall_s": best[0], "fasta_bytes": os.path.getsize(fa),
+           "tsv_bytes": os.path.getsize(tsv), "devices": world,
+           "what": "fresh `tidk search` process: FASTA parse (mmap, multi-threaded) + CUDA context creation + upload + count + format + "
+                   "write; page cache warm; best of 2", "breakdown": best[1], "fasta_write_s_untimed": wrote_s}
+    for f in (fa, tsv):
+        try:
+            os.unlink(f)
+        except OSError:
+            pass
+    try:
+        os.rmdir(d)
+    except OSError:
+        pass
+    return out
 
 
 def main():
@@ -138,6 +320,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
+    ap.add_argument("--skip-extras", action="store_true", help="no explore / FASTA / CPU legs (profiling runs)")
     args = ap.parse_args()
     # stdout carries exactly one JSON line.  Libraries write there too (NCCL prints its "NCCL version ..." banner to
     # stdout with printf when NCCL_DEBUG=VERSION, whatever NCCL_DEBUG_FILE says), so file descriptor 1 is pointed at
@@ -152,34 +335,19 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     steps, warmup = max(1, args.steps), max(0, args.warmup)
+    ncpu = os.cpu_count() or 1
 
-    config = {"workload": "C2: tidk find --clade Lepidoptera (AACCT) --window 10000, synthetic 500 Mb / 30 chromosomes",
-              "window": WINDOW, "queries": [q.decode() for q in REPEATS], "records_per_gpu": 30,
-              "l2": "inputs (500 MB per GPU) larger than the 126 MB L2; no flush needed",
-              "sharding": "records across ranks, no collective"}
+    config = {"workload": "C4: tidk search --string TTAGGG --window 10000, synthetic 3.1 Gb / 24 chromosomes with N gaps",
+              "window": WINDOW, "queries": [q.decode() for q in QUERY], "passes_per_step": PASSES,
+              "l2": "inputs (3.1 GB at N = 1, 386 MB per GPU at N = 8) larger than the 126 MB L2; no flush needed",
+              "sharding": "contiguous window ranges of the one genome across ranks (long chromosomes cut at multiples of W), no collective"}
+    if SCALE != 1.0:
+        config["scale"] = SCALE
 
     if args.impl == "reference":
         if rank != 0:
             return
-        ids, seq, off, scale = make_workload(2)
-        if scale != 1.0:
-            config["scale"] = scale
-        cb, per_step = cpu_leg(seq, off, steps, warmup)
-        # for information: the same port sharded by record over every host core -- the
-        # reference itself never does this (search.rs:57 / finder.rs:85 are sequential loops)
-        from oracle import oracle as O
-        ncpu = os.cpu_count() or 1
-        t0 = time.perf_counter()
-        O.window_counts(seq, off, WINDOW, REPEATS, False, threads=ncpu)
-        cb["all_cores_for_information"] = {"value": seq.size / (time.perf_counter() - t0) / 1e9, "unit": UNIT, "cores": ncpu,
-                                           "sample": "whole genome, records sharded over threads, 1 pass"}
-        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-                "steps": steps, "warmup": warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
-                "cpu_baseline": cb,
-                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
-        emit(line)
+        reference_arm(args, emit, config, steps, warmup)
         return
 
     import torch
@@ -199,56 +367,86 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    ids, seq, off, scale = make_workload(2 + rank)
-    if scale != 1.0:
-        config["scale"] = scale
-    bases = int(seq.size)
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    pieces, chrom, off, goff = c4_shard(rank, world, max(1, ncpu // max(1, local_world)))
+    bases = int(off[-1])
     ctx = T.Context(local)
-    nwin = int(T.api.n_windows(off, WINDOW).sum()) * len(REPEATS)
+    nwin = int(T.api.n_windows(off, WINDOW).sum()) * len(QUERY)
     # pinned host copies: what a host reader parsing straight into tidk_cuda_host_alloc memory holds
-    pseq = ctx.pinned_empty(bases); pseq[:] = seq
-    pout = ctx.pinned_empty(2 * nwin * 8).view(np.uint64)  # forward and reverse counts back to back: one D2H copy
-    pf, pr = pout[:nwin], pout[nwin:]
+    pseq = ctx.pinned_empty(bases)
+    fill_shard(pseq, pieces, chrom, off)
+    chrom = None
+    outs = []
+    for _ in range(2):  # two sets of pinned output arrays, used alternately by the asynchronous calls
+        po = ctx.pinned_empty(2 * nwin * 8).view(np.uint64)  # forward and reverse counts back to back: one D2H copy
+        outs.append((po[:nwin], po[nwin:]))
     batch = ctx.upload(pseq, off)
 
-    # correctness spot check against the oracle before timing anything (rank 0, first 2 Mb)
-    f, r = ctx.window_counts_resident(batch, WINDOW, REPEATS, out=(pf, pr))
+    # correctness before timing anything: blocking call vs the oracle on the first 2 Mb of rank 0's range,
+    # and asynchronous calls vs the blocking one on every rank
+    f, r = ctx.window_counts_resident(batch, WINDOW, QUERY)
+    f, r = f.copy(), r.copy()
     if rank == 0:
         from oracle import oracle as O
         nchk = min(int(off[1]), 2_000_000) // WINDOW * WINDOW
-        of, orr = O.window_counts(seq[:nchk], np.array([0, nchk], dtype=np.uint64), WINDOW, REPEATS, False)
+        of, orr = O.window_counts(pseq[:nchk], np.array([0, nchk], dtype=np.uint64), WINDOW, QUERY, False)
         assert (f[:of.size] == of).all() and (r[:orr.size] == orr).all(), "GPU counts differ from the oracle"
+    for o in outs:
+        o[0][:] = 0xFFFFFFFF
+        ctx.window_counts_resident_async(batch, WINDOW, QUERY, o)
+    ctx.wait()
+    for o in outs:
+        assert np.array_equal(o[0], f) and np.array_equal(o[1], r), "asynchronous counts differ from the blocking call"
+
+    def step():
+        for p in range(PASSES):
+            ctx.window_counts_resident_async(batch, WINDOW, QUERY, outs[p & 1])
+        return ctx.wait()
 
     sampler = ClockSampler(local)
     sampler.start()
     t_s = time.perf_counter()
     for _ in range(warmup):
-        ctx.window_counts_resident(batch, WINDOW, REPEATS, out=(pf, pr))
+        step()
     kernel_ms, launches = 0.0, 0
     barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
-        ctx.window_counts_resident(batch, WINDOW, REPEATS, out=(pf, pr))
-        kernel_ms += ctx.last_kernel_ms
-        launches += ctx.last_kernel_launches
+        ms, nl = step()
+        kernel_ms += ms
+        launches += nl
+        if os.environ.get("TIDK_BENCH_VERBOSE"):
+            print(f"step kernel ms per pass {ms / PASSES:.4f}", file=sys.stderr)
     barrier()
     dt = time.perf_counter() - t0
     # nvidia-smi samples every 100 ms: keep the same step running (untimed) until the sampler has
     # seen at least ~1.5 s of this load, so the clocks line describes the kernel that was timed
     while time.perf_counter() - t_s < 1.5:
-        ctx.window_counts_resident(batch, WINDOW, REPEATS, out=(pf, pr))
+        step()
     clocks = sampler.stop()
     clocks["note"] = "sampled over warm-up + timed steps + identical untimed steps (>= 1.5 s of the same kernel)"
+    assert np.array_equal(outs[0][0], f) and np.array_equal(outs[1][1], r), "counts changed during the timed steps"
+
+    # blocking calls, for the per-call fixed cost (wall per call vs kernel time)
+    barrier()
+    t_b = time.perf_counter()
+    kb = 0.0
+    nb = 8
+    for _ in range(nb):
+        ctx.window_counts_resident(batch, WINDOW, QUERY, out=outs[0])
+        kb += ctx.last_kernel_ms
+    blocking = {"wall_ms_per_call": (time.perf_counter() - t_b) / nb * 1e3, "kernel_ms_per_call": kb / nb}
 
     # end to end through the C ABI with host buffers
     e2e_steps = args.e2e_steps or min(steps, 5)
-    ctx.window_counts(pseq, off, WINDOW, REPEATS)
+    ctx.window_counts(pseq, off, WINDOW, QUERY)
     barrier()
     t1 = time.perf_counter()
     for _ in range(e2e_steps):
-        ctx.window_counts(pseq, off, WINDOW, REPEATS)
+        ef, er = ctx.window_counts(pseq, off, WINDOW, QUERY)
     barrier()
     dt_e2e = time.perf_counter() - t1
+    assert np.array_equal(ef, f) and np.array_equal(er, r), "host-pointer counts differ from the resident ones"
     h2d_bytes, d2h_bytes, host_packed = ctx.last_transfer()
 
     # the bound for e2e: a bare pinned host -> device copy of the same buffer (PCIe Gen5 x16)
@@ -263,93 +461,101 @@ def main():
     ev[1].record()
     torch.cuda.synchronize()
     h2d_gbs = bases * 3 / (ev[0].elapsed_time(ev[1]) * 1e-3) / 1e9
-    del dst
-
-    # the other half of the hot path (explore) on the same resident genome:
-    # C3 (--distance 0.01, 60 slices) and --distance 0.5 (every base scanned once, 8 k's per pass)
-    explore = None
-    if world == 1:
-        explore = {}
-        lens = (off[1:] - off[:-1]).astype(np.float64)
-        for name, d in (("c3_distance_0.01", 0.01), ("distance_0.5", 0.5)):
-            scanned = int(sum(2 * int(np.ceil(l * d)) for l in lens.tolist()))
-            best = None
-            for _ in range(5):
-                t2 = time.perf_counter()
-                runs = ctx.explore_runs_resident(batch, d, 5, 12, 100)
-                wall = time.perf_counter() - t2
-                sm, pm = ctx.explore_timings()
-                if best is None or sm < best[0]:
-                    best = (sm, pm, wall)
-            # the same call through the host-pointer entry point (pinned buffer): with d = 0.01 only the
-            # slices are uploaded, with d = 0.5 the whole genome is
-            e2e_ms = None
-            for _ in range(3):
-                t3 = time.perf_counter()
-                ctx.explore_runs(pseq, off, d, 5, 12, 100)
-                w3 = (time.perf_counter() - t3) * 1e3
-                e2e_ms = w3 if e2e_ms is None else min(e2e_ms, w3)
-            explore[name] = {"scanned_bases": scanned, "scan_kernel_ms": best[0], "post_ms": best[1],
-                             "e2e_host_pointer_call_ms": e2e_ms,
-                             "call_wall_ms": best[2] * 1e3, "runs": int(runs.size),
-                             "scan_gbases_per_s": scanned / (best[0] * 1e-3) / 1e9,
-                             "kernel": "explore_planes_kernel<5,12>", "k_range": [5, 12], "threshold": 100}
-            # the CPU port beside it: rayon's one-worker-per-record sharding (explore.rs:97-100) as
-            # min(host cores, records) threads, one pass over the same genome, same arguments
-            from oracle import oracle as O
-            cpu_threads = max(1, min(os.cpu_count() or 1, len(off) - 1))
-            t4 = time.perf_counter()
-            cpu_runs, _ = O.explore_runs(seq, off, d, 5, 12, 100, False, cpu_threads)
-            cpu_dt = time.perf_counter() - t4
-            explore[name]["cpu_baseline"] = {"value": scanned / cpu_dt / 1e9, "unit": UNIT, "cores": cpu_threads,
-                                             "kind": "port", "sample": "whole genome, one pass, records sharded over threads",
-                                             "runs_equal_to_gpu": bool(len(cpu_runs) == int(runs.size))}
+    del dst, src
 
     if dist is not None:
         t = torch.tensor([dt, dt_e2e, kernel_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt, dt_e2e, kernel_ms = (float(x) for x in t.tolist())
-        tot = torch.tensor([float(bases), float(launches)], device="cuda", dtype=torch.float64)
+        tot = torch.tensor([float(bases), float(launches), float(f.sum()), float(r.sum()), float(h2d_bytes), float(d2h_bytes)],
+                           device="cuda", dtype=torch.float64)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
         total_bases, launches = float(tot[0]), int(tot[1])
+        fwd_total, rev_total, h2d_bytes, d2h_bytes = int(tot[2]), int(tot[3]), int(tot[4]), int(tot[5])
     else:
         total_bases = float(bases)
+        fwd_total, rev_total = int(f.sum()), int(r.sum())
+
+    peak, peak_src = measured_peak()
+    extras = {}
+    if not args.skip_extras:
+        if world == 1:
+            extras["roofline_explore"] = explore_block(ctx, peak)
+            # explore --distance 0.01 on the resident genome (48 slices, 1 % of each chromosome end: launch-bound)
+            lens = (off[1:] - off[:-1]).astype(np.float64)
+            scanned = int(sum(2 * int(np.ceil(l * 0.01)) for l in lens.tolist()))
+            best = None
+            for _ in range(5):
+                t2 = time.perf_counter()
+                runs = ctx.explore_runs_resident(batch, 0.01, 5, 12, 100)
+                wall = time.perf_counter() - t2
+                sm, pm = ctx.explore_timings()
+                if best is None or sm < best[0]:
+                    best = (sm, pm, wall)
+            extras["explore_c4_distance_0.01"] = {"scanned_bases": scanned, "scan_kernel_ms": best[0], "post_ms": best[1],
+                                                  "resident_call_wall_ms": best[2] * 1e3, "runs": int(runs.size)}
+        # FASTA in -> TSV out, fresh process (rank 0 drives `--gpus world`; the other ranks idle at the barrier)
+        barrier()
+        if rank == 0:
+            try:
+                if world == 1:
+                    from telomeric_identifier_b200 import synth
+                    ids = [f"chr{n}" for n in synth._HG38_NAMES]
+                    extras["e2e_fasta"] = fasta_e2e((ids, pseq, goff), world, local)
+                else:
+                    from telomeric_identifier_b200 import synth
+                    with ThreadPoolExecutor(max(1, ncpu // 2)) as ex:
+                        parts = list(ex.map(lambda i: synth.config4_contig(i, SCALE)[1], range(len(goff) - 1)))
+                    ids = [f"chr{n}" for n in synth._HG38_NAMES]
+                    extras["e2e_fasta"] = fasta_e2e((ids, np.concatenate(parts), goff), world, local)
+                    del parts
+            except Exception as exc:  # never lose the bench line to the extra leg
+                extras["e2e_fasta"] = {"unavailable": repr(exc)[:300]}
+        barrier()
 
     if rank == 0:
-        peak, peak_src = measured_peak()
-        k_ms = kernel_ms / steps
-        achieved = bases / (k_ms * 1e-3) / 1e9  # GB/s per GPU at 1 B per scanned base
+        k_ms = kernel_ms / (steps * PASSES)  # max over ranks of the mean device time per pass
+        per_gpu = total_bases / world
+        achieved = per_gpu / (k_ms * 1e-3) / 1e9  # GB/s per GPU at 1 B per scanned base
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "window_counts_kernel<StaticMatcher<5,AACCT>>", "kernel_ms": k_ms,
-                "algorithmic_bytes_per_launch": bases, "peak_source": peak_src}
+                "traffic": None, "kernel": "window_counts_kernel<StaticMatcher<6,TTAGGG>,4,AsciiSource>", "kernel_ms": k_ms,
+                "algorithmic_bytes_per_launch": per_gpu, "peak_source": peak_src,
+                "note": "per GPU: bases of one rank's range / slowest rank's mean kernel time per pass"}
         tr = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tr):
+        if os.path.exists(tr) and world == 1 and SCALE == 1.0:
             try:
-                roof["traffic"] = json.load(open(tr)).get("window_counts_kernel_dram_bytes_per_launch")
+                roof["traffic"] = json.load(open(tr)).get("window_counts_kernel_c4_dram_bytes_per_launch")
             except Exception:
                 pass
         cb = None
-        if world == 1:  # the CPU baseline is reported at N = 1 only
-            cb, _ = cpu_leg(seq, off, 1, 0, budget_s=25.0)
-        line = {"metric": METRIC, "value": total_bases * steps / dt / 1e9, "unit": UNIT, "n_gpus": world,
+        if world == 1 and not args.skip_extras:  # the CPU baseline is reported at N = 1 only
+            t3 = time.perf_counter()
+            cf, cr = cpu_counts(pseq, off, ncpu)
+            cdt = time.perf_counter() - t3
+            cb = {"value": bases / cdt / 1e9, "unit": UNIT, "cores": ncpu, "kind": "port",
+                  "sample": f"the whole genome ({bases} bases), one pass, window ranges sharded over {ncpu} threads; oracle/tidk_oracle.c "
+                            "restates tidk 0.2.7 (the Rust reference cannot be built here; the reference itself is single-threaded, search.rs:57)",
+                  "all_windows_equal_to_gpu": bool(np.array_equal(cf, f) and np.array_equal(cr, r))}
+        e2e_val = total_bases * e2e_steps / dt_e2e / 1e9
+        line = {"metric": METRIC, "value": total_bases * PASSES * steps / dt / 1e9, "unit": UNIT, "n_gpus": world,
                 "steps": steps, "warmup": warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
-                "kernel_ms_per_step": k_ms, "clocks": clocks,
-                "e2e": {"value": total_bases * e2e_steps / dt_e2e / 1e9, "unit": UNIT,
+                "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
+                "kernel_ms_per_pass": k_ms, "wall_ms_per_pass": dt / steps / PASSES * 1e3,
+                "wall_over_kernel": dt / steps / PASSES * 1e3 / k_ms,
+                "kernel_only_value": total_bases / (k_ms * 1e-3) / 1e9,
+                "counts": {"fwd_total": fwd_total, "rev_total": rev_total}, "blocking_call": blocking, "clocks": clocks,
+                "e2e": {"value": e2e_val, "unit": UNIT,
                         "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
-                        "host_bytes_per_step": bases,
+                        "host_bytes_per_step": int(total_bases),
                         "upload": ("two-ended: ASCII chunks by DMA from the front, host-packed lo/hi bit-planes (2 bits per base + validity "
-                                   "exceptions) from the back, packed by %d host threads inside the timed region"
-                                   % min(32, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
+                                   "exceptions) from the back, packed by %d host threads per rank inside the timed region"
+                                   % min(32, ncpu // max(1, local_world))
                                    if host_packed else "ASCII, straight DMA from the caller's pinned buffer"),
                         "ms_per_step": dt_e2e / e2e_steps * 1e3,
                         "h2d_bound_gbs_rank0": h2d_gbs,
                         "frac_of_h2d_bound_rank0": (bases * e2e_steps / dt_e2e / 1e9) / h2d_gbs},
                 "gpu_launches": launches, "roofline": roof, "cpu_baseline": cb}
-        if explore is not None:
-            for v in explore.values():
-                v["frac_of_hbm_peak"] = v["scan_gbases_per_s"] / peak
-            line["explore"] = explore
+        line.update(extras)
         emit(line)
     ctx.close()
     if dist is not None:

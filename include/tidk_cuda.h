@@ -107,6 +107,20 @@ int tidk_cuda_window_counts_resident(tidk_ctx *ctx, const tidk_seqbuf *buf, uint
                                      uint32_t nq, uint64_t *out_fwd, uint64_t *out_rev,
                                      float *kernel_ms, uint32_t *kernel_launches);
 
+/* Asynchronous form of tidk_cuda_window_counts_resident: the kernels are enqueued and the call returns; the counts
+ * leave the device on a second stream while the next call's kernels run (two output buffers are used alternately, so
+ * up to two calls are in flight and a third first waits for the oldest).  out_fwd / out_rev must stay valid -- and
+ * should be tidk_cuda_host_alloc memory, or the copy is staged -- until tidk_cuda_wait returns.  A single-threaded
+ * host (search.rs:57 is one sequential loop) keeps the device busy this way: the per-call cost of a blocking call
+ * (copy of the counts + wake-up of the waiting thread, 40-80 us) is as long as a whole launch on a sharded genome. */
+int tidk_cuda_window_counts_resident_async(tidk_ctx *ctx, const tidk_seqbuf *buf, uint64_t window,
+                                           const char *const *queries, const uint32_t *qlens,
+                                           uint32_t nq, uint64_t *out_fwd, uint64_t *out_rev);
+/* Blocks until every asynchronous call on ctx has delivered its counts.  kernel_ms / kernel_launches (nullable):
+ * device time of the counting kernels (CUDA events on the ctx stream) and launches summed over the calls collected
+ * since the previous wait.  Returns the first deferred error (TIDK_ENONASCII: some call saw a byte >= 0x80). */
+int tidk_cuda_wait(tidk_ctx *ctx, float *kernel_ms, uint32_t *kernel_launches);
+
 /* ---------------------------------------------------------------------- explore
  * Replaces split_seq_by_distance + chunk_fasta + calculate_indexes for every
  * record, slice and k (explore.rs:151-160, 178-233, 289-347; call sites

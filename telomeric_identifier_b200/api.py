@@ -19,6 +19,7 @@ EXPORTS = [
     "tidk_cuda_seqbuf_upload", "tidk_cuda_seqbuf_free", "tidk_cuda_window_counts_resident",
     "tidk_cuda_explore_runs", "tidk_cuda_explore_runs_resident", "tidk_cuda_free_runs",
     "tidk_cuda_last_explore_timings", "tidk_cuda_last_transfer", "tidk_cuda_last_kernel_time",
+    "tidk_cuda_window_counts_resident_async", "tidk_cuda_wait",
 ]
 
 
@@ -76,6 +77,10 @@ def load_library():
     L.tidk_cuda_window_counts_resident.argtypes = [vp, vp, C.c_uint64, C.POINTER(C.c_char_p), u32p, C.c_uint32,
                                                    vp, vp, C.POINTER(C.c_float), u32p]
     L.tidk_cuda_window_counts_resident.restype = C.c_int
+    L.tidk_cuda_window_counts_resident_async.argtypes = [vp, vp, C.c_uint64, C.POINTER(C.c_char_p), u32p, C.c_uint32, vp, vp]
+    L.tidk_cuda_window_counts_resident_async.restype = C.c_int
+    L.tidk_cuda_wait.argtypes = [vp, C.POINTER(C.c_float), u32p]
+    L.tidk_cuda_wait.restype = C.c_int
     L.tidk_cuda_explore_runs.argtypes = [vp, vp, vp, C.c_uint32, C.c_double, C.c_uint32, C.c_uint32, C.c_uint64,
                                          C.POINTER(C.POINTER(Run)), u64p]
     L.tidk_cuda_explore_runs.restype = C.c_int
@@ -219,6 +224,25 @@ class Context:
                                                              C.byref(ms), C.byref(nl)))
         self.last_kernel_ms, self.last_kernel_launches = ms.value, nl.value
         return fwd[:total], rev[:total]
+
+    def window_counts_resident_async(self, batch: SeqBatch, window: int, queries: Sequence[bytes],
+                                     out: Tuple[np.ndarray, np.ndarray]) -> None:
+        """Enqueue one counting pass; `out` (pinned arrays from pinned_empty) is filled by the time wait() returns."""
+        key = tuple(queries)
+        cached = getattr(self, "_qcache", None)
+        if cached is None or cached[0] != key:
+            self._qcache = cached = (key, _qargs(queries))
+        qa, ql, nq = cached[1]
+        fwd, rev = out
+        self._check(self._L.tidk_cuda_window_counts_resident_async(self._h, batch._h, window, qa, ql, nq,
+                                                                   fwd.ctypes.data, rev.ctypes.data))
+
+    def wait(self) -> Tuple[float, int]:
+        """Collect every asynchronous call: (summed kernel ms, launches) since the previous wait."""
+        ms, nl = C.c_float(0), C.c_uint32(0)
+        self._check(self._L.tidk_cuda_wait(self._h, C.byref(ms), C.byref(nl)))
+        self.last_kernel_ms, self.last_kernel_launches = ms.value, nl.value
+        return ms.value, nl.value
 
     # -- explore ------------------------------------------------------------
     def _runs_out(self, runs, n) -> np.ndarray:

@@ -16,6 +16,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "explore_host.cuh"
@@ -131,7 +132,20 @@ struct tidk_ctx {
     uint32_t *h_flags = nullptr;    // pinned + mapped: the window kernels store the (rare) error flag straight into host memory
     uint32_t *d_flags = nullptr;    // device view of h_flags
     ExploreScratch ex;
+    // window counts, asynchronous form: two device output buffers used alternately; the counts of call i leave on
+    // the copy stream while the kernel of call i + 1 runs
+    struct WinSlot { cudaEvent_t k0 = nullptr, k1 = nullptr, done = nullptr; bool busy = false; uint32_t launches = 0; };
+    WinSlot wslot[2];
+    DevBuf out_dev[2];
+    cudaStream_t copy_st = nullptr;
+    uint32_t wslot_next = 0;
+    float pending_kernel_ms = 0.f;     // device time / launches of the calls retired since the last tidk_cuda_wait
+    uint32_t pending_launches = 0;
+    int pending_err = 0;               // first deferred failure (reported by tidk_cuda_wait)
+    std::unordered_map<const void *, int> occupancy; // resident CTAs per SM, per kernel instantiation, on THIS device
     uint64_t next_buf_id = 1;
+    // multi-device context: one single-device context per device, this one holds no device state of its own
+    std::vector<tidk_ctx *> subs;
     // work items cached for (sequence batch, window, query count): several clades or output
     // formats over one uploaded genome reuse them
     uint64_t items_buf_id = 0, items_window = 0, items_n = 0, items_nwin = 0;
@@ -339,27 +353,34 @@ constexpr uint64_t cx_enc(const char *s) {
 }
 
 // persistent launch: the grid is the number of CTAs that are resident at once (the kernels assign
-// the first items statically and rely on every CTA running from the start)
+// the first items statically and rely on every CTA running from the start).  Occupancy is looked up once
+// per kernel instantiation and CONTEXT (= device): contexts of different devices run on different threads.
+struct LaunchEnv {
+    int sm_count;
+    std::unordered_map<const void *, int> *occupancy;
+    cudaStream_t st;
+};
+
 template <class K>
-int resident_grid(K kernel, int sm_count, uint64_t n_items) {
-    static int per_sm = 0; // one static per kernel instantiation
+int resident_grid(K kernel, const LaunchEnv &env, uint64_t n_items) {
+    int &per_sm = (*env.occupancy)[(const void *)kernel];
     if (per_sm == 0) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWarpsPerBlock * 32, 0) != cudaSuccess || per_sm < 1)
             per_sm = 1;
     }
     const uint64_t want = (n_items + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    const uint64_t cap = (uint64_t)sm_count * per_sm;
+    const uint64_t cap = (uint64_t)env.sm_count * per_sm;
     const uint64_t g = want < cap ? want : cap;
     return g < 1 ? 1 : (int)g;
 }
 
-using LaunchFn = void (*)(const WindowJob &, int, cudaStream_t);
+using LaunchFn = void (*)(const WindowJob &, const LaunchEnv &);
 template <int L, uint64_t F, class Src>
-void launch_static(const WindowJob &job, int sm_count, cudaStream_t st) {
+void launch_static(const WindowJob &job, const LaunchEnv &env) {
     using M = StaticMatcher<L, F>;
     typename M::Params mp{0};
-    const int grid = resident_grid(window_counts_kernel<M, 4, Src>, sm_count, job.n_items);
-    window_counts_kernel<M, 4, Src><<<grid, kWarpsPerBlock * 32, 0, st>>>(job, mp);
+    const int grid = resident_grid(window_counts_kernel<M, 4, Src>, env, job.n_items);
+    window_counts_kernel<M, 4, Src><<<grid, kWarpsPerBlock * 32, 0, env.st>>>(job, mp);
 }
 struct StaticEntry { int L; uint64_t F; LaunchFn fn, fn_packed; };
 #define X_(s) {cx_len(s), cx_enc(s), &launch_static<cx_len(s), cx_enc(s), AsciiSource>, &launch_static<cx_len(s), cx_enc(s), PackedSource>},
@@ -388,10 +409,10 @@ using Hymenoptera = StaticMultiMatcher<MOTIF_("AACCCAGACCT"), MOTIF_("AACCCCAACC
 #undef MOTIF_
 
 template <class M, int MINB, class Src>
-void launch_multi(const WindowJob &job, int sm_count, cudaStream_t st) {
+void launch_multi(const WindowJob &job, const LaunchEnv &env) {
     typename M::Params mp{0};
-    const int grid = resident_grid(window_counts_kernel<M, MINB, Src>, sm_count, job.n_items);
-    window_counts_kernel<M, MINB, Src><<<grid, kWarpsPerBlock * 32, 0, st>>>(job, mp);
+    const int grid = resident_grid(window_counts_kernel<M, MINB, Src>, env, job.n_items);
+    window_counts_kernel<M, MINB, Src><<<grid, kWarpsPerBlock * 32, 0, env.st>>>(job, mp);
 }
 
 struct CladeSet { std::vector<const char *> motifs; LaunchFn fn, fn_packed; };
@@ -415,19 +436,19 @@ LaunchFn find_clade_set(const char *const *queries, const uint32_t *qlens, uint3
 }
 
 template <int L>
-void launch_runtime(const WindowJob &job, const RuntimeQueries &rq, int sm_count, cudaStream_t st) {
-    const int grid = resident_grid(window_counts_kernel<RuntimeMatcher<L>, 3>, sm_count, job.n_items);
-    window_counts_kernel<RuntimeMatcher<L>, 3><<<grid, kWarpsPerBlock * 32, 0, st>>>(job, rq);
+void launch_runtime(const WindowJob &job, const RuntimeQueries &rq, const LaunchEnv &env) {
+    const int grid = resident_grid(window_counts_kernel<RuntimeMatcher<L>, 3>, env, job.n_items);
+    window_counts_kernel<RuntimeMatcher<L>, 3><<<grid, kWarpsPerBlock * 32, 0, env.st>>>(job, rq);
 }
 
-void launch_planes(int L, const WindowJob &job, const RuntimeQueries &rq, int sm_count, cudaStream_t st) {
+void launch_planes(int L, const WindowJob &job, const RuntimeQueries &rq, const LaunchEnv &env) {
     switch (L) {
-#define C_(n) case n: launch_runtime<n>(job, rq, sm_count, st); break;
+#define C_(n) case n: launch_runtime<n>(job, rq, env); break;
         C_(1) C_(2) C_(3) C_(4) C_(5) C_(6) C_(7) C_(8) C_(9) C_(10) C_(11) C_(12) C_(13) C_(14)
         C_(15) C_(16) C_(17) C_(18) C_(19) C_(20) C_(21) C_(22) C_(23) C_(24) C_(25) C_(26) C_(27)
         C_(28) C_(29) C_(30) C_(31) C_(32)
 #undef C_
-    default: launch_runtime<0>(job, rq, sm_count, st); break;
+    default: launch_runtime<0>(job, rq, env); break;
     }
 }
 
@@ -483,6 +504,13 @@ void tidk_cuda_destroy(tidk_ctx *ctx) {
         if (L.ev[1]) cudaEventDestroy(L.ev[1]);
         if (L.st) cudaStreamDestroy(L.st);
     }
+    for (int s = 0; s < 2; s++) {
+        if (ctx->wslot[s].busy) cudaEventSynchronize(ctx->wslot[s].done);
+        for (cudaEvent_t e : {ctx->wslot[s].k0, ctx->wslot[s].k1, ctx->wslot[s].done})
+            if (e) cudaEventDestroy(e);
+        if (ctx->out_dev[s].p) cudaFree(ctx->out_dev[s].p);
+    }
+    if (ctx->copy_st) cudaStreamDestroy(ctx->copy_st);
     for (cudaEvent_t e : ctx->dma_ev)
         if (e) cudaEventDestroy(e);
     if (ctx->dma_st) cudaStreamDestroy(ctx->dma_st);
@@ -538,10 +566,38 @@ void tidk_cuda_seqbuf_free(tidk_ctx *ctx, tidk_seqbuf *buf) {
 
 // packed != nullptr: the host-packed planes are the source for the sequence from byte `split` on; the bytes
 // below `split` (a multiple of 32, 0 = none) are resident as ASCII in buf->d_seq (hybrid upload).
+// The call that used window slot `s` has finished on the device: fold its kernel time into the pending totals.
+static int retire_slot(tidk_ctx *ctx, int s) {
+    tidk_ctx::WinSlot &S = ctx->wslot[s];
+    if (!S.busy) return TIDK_OK;
+    S.busy = false;
+    cudaError_t e = cudaEventSynchronize(S.done);
+    if (e != cudaSuccess) {
+        if (!ctx->pending_err) ctx->pending_err = TIDK_ECUDA;
+        return fail(ctx, TIDK_ECUDA, "asynchronous window count failed: %s", cudaGetErrorString(e));
+    }
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, S.k0, S.k1) == cudaSuccess) ctx->pending_kernel_ms += ms;
+    else (void)cudaGetLastError();
+    ctx->pending_launches += S.launches;
+    return TIDK_OK;
+}
+
+static int drain_slots(tidk_ctx *ctx) {
+    int rc = TIDK_OK;
+    for (int s = 0; s < 2; s++) {
+        const int r = retire_slot(ctx, s);
+        if (r && !rc) rc = r;
+    }
+    return rc;
+}
+
+// async: the counts leave on the copy stream behind the kernels and the call returns at once (tidk_cuda_wait collects);
+// otherwise the call returns with the counts in place.
 static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint32_t *packed, uint64_t window,
                               const char *const *queries, const uint32_t *qlens,
                               uint32_t nq, uint64_t *out_fwd, uint64_t *out_rev,
-                              float *kernel_ms, uint32_t *kernel_launches, uint64_t split = 0) {
+                              float *kernel_ms, uint32_t *kernel_launches, uint64_t split = 0, bool async = false) {
     if (!ctx) return TIDK_EARG;
     if (kernel_ms) *kernel_ms = 0.f;
     if (kernel_launches) *kernel_launches = 0;
@@ -577,14 +633,29 @@ static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint3
     if (spw64 > 0xFFFFFFFFull) spw64 = 0xFFFFFFFFull; // records are < 2^64 bytes: never reached in practice
     const uint32_t spw = (uint32_t)spw64;
     const uint64_t n_items = n_windows * spw;
+    if (n_items >= (1ull << 34)) return fail(ctx, TIDK_EARG, "more than 2^34 work items (windows x 32 KiB segments) in one call");
 
     int rc;
-    // one allocation, forward counts then reverse counts, so that a caller whose two output arrays are
-    // adjacent in memory gets both with a single copy
-    if ((rc = ensure(ctx, ctx->out_fwd, 2 * n_out * 8))) return rc;
-    if (!ctx->misc.p) { // two queue counters (each launch zeroes the other one) + error flags
-        if ((rc = ensure(ctx, ctx->misc, 256))) return rc;
-        CU(ctx, cudaMemsetAsync(ctx->misc.p, 0, 256, ctx->stream));
+    // Two output buffers used alternately (the counts of call i leave the device while call i + 1 counts).  One
+    // allocation each, forward counts then reverse counts, so that a caller whose two output arrays are adjacent
+    // in memory gets both with a single copy.
+    if (!async && (rc = drain_slots(ctx))) return rc; // a blocking call behind asynchronous ones: collect those first
+    const int slot = (int)(ctx->wslot_next & 1u);
+    tidk_ctx::WinSlot &S = ctx->wslot[slot];
+    if ((rc = retire_slot(ctx, slot))) return rc;
+    if (!S.k0) {
+        CU(ctx, cudaEventCreate(&S.k0));
+        CU(ctx, cudaEventCreate(&S.k1));
+        CU(ctx, cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming));
+    }
+    if (async && !ctx->copy_st) CU(ctx, cudaStreamCreateWithFlags(&ctx->copy_st, cudaStreamNonBlocking));
+    if (2 * n_out * 8 > ctx->out_dev[slot].cap) { // (re)allocation: nothing of this slot is in flight (retired above)
+        if ((rc = ensure(ctx, ctx->out_dev[slot], 2 * n_out * 8))) return rc;
+    }
+    constexpr size_t kCounterBytes = 2 * (size_t)kQueues * kQueueStride * 8; // two sets of queue counters (each launch zeroes the other set)
+    if (!ctx->misc.p) {
+        if ((rc = ensure(ctx, ctx->misc, kCounterBytes))) return rc;
+        CU(ctx, cudaMemsetAsync(ctx->misc.p, 0, kCounterBytes, ctx->stream));
         ctx->counter_flip = 0;
     }
     if (!ctx->h_flags) {
@@ -593,17 +664,17 @@ static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint3
         CU(ctx, cudaHostGetDevicePointer((void **)&ctx->d_flags, ctx->h_flags, 0));
     }
     if (ctx->counters_dirty) {
-        CU(ctx, cudaMemsetAsync(ctx->misc.p, 0, 256, ctx->stream));
+        CU(ctx, cudaMemsetAsync(ctx->misc.p, 0, kCounterBytes, ctx->stream));
         ctx->counter_flip = 0;
     }
     ctx->counters_dirty = true; // cleared when this call has completed all its launches
-    uint64_t *d_fwd = (uint64_t *)ctx->out_fwd.p, *d_rev = d_fwd + n_out;
+    uint64_t *d_fwd = (uint64_t *)ctx->out_dev[slot].p, *d_rev = d_fwd + n_out;
     if (spw > 1) {
         CU(ctx, cudaMemsetAsync(d_fwd, 0, 2 * n_out * 8, ctx->stream));
     }
 
     uint32_t launches = 0;
-    CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    CU(ctx, cudaEventRecord(S.k0, ctx->stream));
     if (!cached) {
         ctx->items_buf_id = 0;
         if ((rc = ensure(ctx, ctx->win_base, wb.size() * 8))) return rc;
@@ -647,14 +718,14 @@ static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint3
     }
 
     const uint64_t max_blocks = (uint64_t)ctx->sm_count * 8;
-    const int grid = ctx->sm_count; // launch helpers turn the SM count into the resident grid
+    const LaunchEnv env{ctx->sm_count, &ctx->occupancy, ctx->stream}; // launch helpers turn the SM count into the resident grid
 
-    unsigned long long *counters = (unsigned long long *)ctx->misc.p; // two queue counters, used alternately
+    unsigned long long *counters = (unsigned long long *)ctx->misc.p; // two sets of queue counters, used alternately
     unsigned long long *next_zeroed = nullptr;
     auto next_counter = [&]() -> unsigned long long * {
-        unsigned long long *c = counters + (ctx->counter_flip & 1u) * 8; // 64 bytes apart
+        unsigned long long *c = counters + (ctx->counter_flip & 1u) * (kQueues * kQueueStride);
         ctx->counter_flip ^= 1u;
-        next_zeroed = counters + (ctx->counter_flip & 1u) * 8;
+        next_zeroed = counters + (ctx->counter_flip & 1u) * (kQueues * kQueueStride);
         return c;
     };
 
@@ -682,7 +753,7 @@ static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint3
             ja.packed = nullptr;
             ja.n_items = n_ascii_items;
             ja.work_counter = next_counter(); ja.next_counter = next_zeroed;
-            f_ascii(ja, grid, ctx->stream);
+            f_ascii(ja, env);
             launches++;
         }
         if (n_ascii_items < n_items) {
@@ -690,7 +761,7 @@ static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint3
             jp.items = j.items + n_ascii_items;
             jp.n_items = n_items - n_ascii_items;
             jp.work_counter = next_counter(); jp.next_counter = next_zeroed;
-            f_packed(jp, grid, ctx->stream);
+            f_packed(jp, env);
             launches++;
         }
     };
@@ -736,7 +807,7 @@ static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint3
         WindowJob j2 = job;
         j2.q0 = fused[g0]; j2.nq = rq.nq;
         j2.work_counter = next_counter(); j2.next_counter = next_zeroed;
-        launch_planes(rq.nq == 1 ? (int)rq.len[0] : 0, j2, rq, grid, ctx->stream);
+        launch_planes(rq.nq == 1 ? (int)rq.len[0] : 0, j2, rq, env);
         launches++;
         g0 = g1;
     }
@@ -757,21 +828,35 @@ static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint3
         window_counts_bytes_kernel<<<g2 < 1 ? 1 : g2, kWarpsPerBlock * 32, 0, ctx->stream>>>(sj);
         launches++;
     }
-    CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    CU(ctx, cudaEventRecord(S.k1, ctx->stream));
     CU(ctx, cudaGetLastError());
 
-    if (out_rev == out_fwd + n_out) {
-        CU(ctx, cudaMemcpyAsync(out_fwd, d_fwd, 2 * n_out * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    } else {
-        CU(ctx, cudaMemcpyAsync(out_fwd, d_fwd, n_out * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(ctx, cudaMemcpyAsync(out_rev, d_rev, n_out * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    cudaStream_t cst = ctx->stream;
+    if (async) { // the copy runs beside the next call's kernels
+        cst = ctx->copy_st;
+        CU(ctx, cudaStreamWaitEvent(cst, S.k1, 0));
     }
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->counters_dirty = false;
+    if (out_rev == out_fwd + n_out) {
+        CU(ctx, cudaMemcpyAsync(out_fwd, d_fwd, 2 * n_out * 8, cudaMemcpyDeviceToHost, cst));
+    } else {
+        CU(ctx, cudaMemcpyAsync(out_fwd, d_fwd, n_out * 8, cudaMemcpyDeviceToHost, cst));
+        CU(ctx, cudaMemcpyAsync(out_rev, d_rev, n_out * 8, cudaMemcpyDeviceToHost, cst));
+    }
+    CU(ctx, cudaEventRecord(S.done, cst));
+    S.busy = true;
+    S.launches = launches;
+    ctx->wslot_next ^= 1u;
+    ctx->counters_dirty = false; // every launch of this call is enqueued; the counters are handed on in stream order
+    if (async) return TIDK_OK;
+    const float ms0 = ctx->pending_kernel_ms;
+    const uint32_t nl0 = ctx->pending_launches;
+    if ((rc = retire_slot(ctx, slot))) return rc;
+    ctx->last_kernel_ms = ctx->pending_kernel_ms - ms0;
+    ctx->last_kernel_launches = launches;
+    ctx->pending_kernel_ms = ms0; // a blocking call reports its own time; the pending totals belong to asynchronous calls
+    ctx->pending_launches = nl0;
     const uint32_t h_err = *(volatile uint32_t *)ctx->h_flags;
     if (h_err) ctx->h_flags[0] = 0; // flags are sticky: clear after reporting (the stream is idle here)
-    CU(ctx, cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev0, ctx->ev1));
-    ctx->last_kernel_launches = launches;
     if (kernel_ms) *kernel_ms = ctx->last_kernel_ms;
     if (kernel_launches) *kernel_launches = launches;
     if (h_err & 1u)
@@ -785,6 +870,34 @@ int tidk_cuda_window_counts_resident(tidk_ctx *ctx, const tidk_seqbuf *buf, uint
                                      float *kernel_ms, uint32_t *kernel_launches) {
     return window_counts_impl(ctx, buf, nullptr, window, queries, qlens, nq, out_fwd, out_rev, kernel_ms,
                               kernel_launches);
+}
+
+int tidk_cuda_window_counts_resident_async(tidk_ctx *ctx, const tidk_seqbuf *buf, uint64_t window,
+                                           const char *const *queries, const uint32_t *qlens,
+                                           uint32_t nq, uint64_t *out_fwd, uint64_t *out_rev) {
+    return window_counts_impl(ctx, buf, nullptr, window, queries, qlens, nq, out_fwd, out_rev, nullptr, nullptr, 0, /*async=*/true);
+}
+
+int tidk_cuda_wait(tidk_ctx *ctx, float *kernel_ms, uint32_t *kernel_launches) {
+    if (!ctx) return TIDK_EARG;
+    if (kernel_ms) *kernel_ms = 0.f;
+    if (kernel_launches) *kernel_launches = 0;
+    CU(ctx, cudaSetDevice(ctx->device));
+    int rc = drain_slots(ctx);
+    if (kernel_ms) *kernel_ms = ctx->pending_kernel_ms;
+    if (kernel_launches) *kernel_launches = ctx->pending_launches;
+    ctx->last_kernel_ms = ctx->pending_kernel_ms;
+    ctx->last_kernel_launches = ctx->pending_launches;
+    ctx->pending_kernel_ms = 0.f;
+    ctx->pending_launches = 0;
+    if (rc) return rc;
+    if (ctx->h_flags) {
+        const uint32_t h_err = *(volatile uint32_t *)ctx->h_flags;
+        if (h_err) ctx->h_flags[0] = 0;
+        if (h_err & 1u)
+            return fail(ctx, TIDK_ENONASCII, "sequence contains a byte >= 0x80 (the reference fails in str::from_utf8, search.rs:107)");
+    }
+    return TIDK_OK;
 }
 
 // ---- host-packed upload ----------------------------------------------------------------------

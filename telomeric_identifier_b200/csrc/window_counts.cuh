@@ -35,6 +35,13 @@ constexpr int kMaxFastLen = 32;        // plane kernels: one look-behind word
 constexpr int kMaxFastQueries = 16;    // queries per fused multi-query launch
 constexpr uint32_t kSegBytes = 32768;  // work-item span for windows larger than this
 constexpr int kWarpsPerBlock = 8;
+// Work queues per launch.  One shared ticket counter is an L2 atomic unit working on ONE address: at C4 size (309 000
+// items in 0.52 ms, a ticket per item from 4 736 warps) the kernel ran at either of two rates, 0.52 or 0.94 ms per
+// pass, the slower one bound by that unit (ncu: the wait for the ticket was the top stall).  Eight counters on eight
+// lines, a warp bound to one of them, queue q handing out the items q, q + 8, q + 16, ... behind the statically
+// assigned ones: an eighth of the traffic per address, and runs of slow items (N gaps) still spread over all queues.
+constexpr int kQueues = 8;
+constexpr int kQueueStride = 16;       // in 64-bit words: 128 bytes between counters
 
 struct __align__(32) ItemDesc {
     uint64_t scan0;       // absolute offset of block 0 (multiple of 32)
@@ -100,8 +107,8 @@ struct WindowJob {
     const ItemDesc *items;
     uint64_t *out_fwd;       // [record][query][window]
     uint64_t *out_rev;
-    unsigned long long *work_counter; // zero at launch
-    unsigned long long *next_counter; // zeroed by this launch for the next one (no memset per call)
+    unsigned long long *work_counter; // kQueues ticket counters, one per 128-byte line, zero at launch
+    unsigned long long *next_counter; // the other set: zeroed by this launch for the next one (no memset per call)
     uint32_t *err_flags;     // mapped host word; set to 1 when a non-ASCII byte is seen
     uint64_t n_items;
     uint32_t q0;             // first query index of this launch
@@ -335,8 +342,9 @@ window_counts_kernel(const WindowJob job, const typename M::Params mp) {
     const unsigned long long n_warps = (unsigned long long)gridDim.x * kWarpsPerBlock;
     const unsigned long long gw = (unsigned long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     unsigned long long item = gw, item_next = gw + n_warps;
-    const unsigned long long ticket0 = 2 * n_warps;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *job.next_counter = 0ull; // stream order: the next launch starts after this one ends
+    const unsigned long long ticket0 = 2 * n_warps + (gw & (kQueues - 1)); // first item of this warp's queue
+    uint32_t *const queue = reinterpret_cast<uint32_t *>(job.work_counter + (gw & (kQueues - 1)) * kQueueStride);
+    if (blockIdx.x == 0 && threadIdx.x < kQueues) job.next_counter[threadIdx.x * kQueueStride] = 0ull; // stream order: the next launch starts after this one ends
     if (item >= job.n_items) return;
 
     const uint4 *ip = reinterpret_cast<const uint4 *>(job.items);
@@ -358,8 +366,10 @@ window_counts_kernel(const WindowJob job, const typename M::Params mp) {
         const bool have_next = item_next < job.n_items;
         uint4 na = make_uint4(0, 0, 0, 0), nb = na;
         if (have_next) { na = __ldg(ip + 2 * item_next); nb = __ldg(ip + 2 * item_next + 1); }
-        unsigned long long t2 = 0;
-                if (lane == 0) t2 = ticket0 + atomicAdd(job.work_counter, 1ull);
+        // atom.inc, not atom.add: ptxas wraps a uniform-address add in its warp aggregation (vote, leader, add, SHFL of
+        // the result), which waits for the atomic on the spot.  The ticket is not touched before the end of the item.
+        uint32_t t2 = 0;
+        if (lane == 0) asm volatile("atom.global.inc.u32 %0, [%1], 0xffffffff;" : "=r"(t2) : "l"(queue) : "memory");
 
         uint32_t cf[M::NQ], cr[M::NQ];
 #pragma unroll
@@ -426,7 +436,7 @@ window_counts_kernel(const WindowJob job, const typename M::Params mp) {
         if (!have_next) break;
         item = item_next;
         da = na; db = nb;
-        item_next = __shfl_sync(0xFFFFFFFFu, t2, 0);
+        item_next = ticket0 + (unsigned long long)__shfl_sync(0xFFFFFFFFu, t2, 0) * kQueues;
     }
     if (__any_sync(0xFFFFFFFFu, nonascii != 0) && lane == 0) *(volatile uint32_t *)job.err_flags = 1u; // mapped host memory
 }
@@ -452,7 +462,7 @@ struct SlowJob {
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) window_counts_bytes_kernel(const SlowJob job) {
     const int lane = threadIdx.x & 31;
     uint32_t nonascii = 0;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *job.next_counter = 0ull;
+    if (blockIdx.x == 0 && threadIdx.x < kQueues) job.next_counter[threadIdx.x * kQueueStride] = 0ull;
     for (;;) {
         unsigned long long win = 0;
         if (lane == 0) win = atomicAdd(job.work_counter, 1ull);

@@ -353,3 +353,53 @@ def test_many_runtime_queries_fused_kernel(ctx):
     _cmp(ctx, seq, off, 10000, qs)
     _cmp(ctx, seq, off, 999, qs[:5] + [b"TTAGGG"] + qs[5:])  # a compile-time motif in the middle splits the run
     _cmp(ctx, seq, off, 40000, qs + qs[:8])                   # 20 run-time queries: two fused launches
+
+
+# ---- asynchronous entry point (tidk_cuda_window_counts_resident_async + tidk_cuda_wait) ----
+def test_async_equals_blocking(ctx):
+    from telomeric_identifier_b200 import synth
+    ids, seq, off = synth.config4(scale=0.002)
+    batch = ctx.upload(seq, off)
+    want = {}
+    for W, q in ((10000, b"TTAGGG"), (777, b"CCCTAA"), (50000, b"TTAGGG"), (10000, b"ACGTNA")):
+        f, r = ctx.window_counts_resident(batch, W, [q])
+        of, orr = O.window_counts(seq, off, W, [q], False)
+        assert np.array_equal(f, of) and np.array_equal(r, orr)
+        want[(W, q)] = (f.copy(), r.copy())
+    # several calls in flight, different windows / queries back to back, more calls than slots
+    outs = []
+    for rep in range(3):
+        for (W, q), (f, r) in want.items():
+            po = ctx.pinned_empty(2 * f.size * 8).view(np.uint64)
+            po[:] = 0xDEADBEEF
+            o = (po[:f.size], po[f.size:])
+            ctx.window_counts_resident_async(batch, W, [q], o)
+            outs.append(((W, q), o))
+    ms, nl = ctx.wait()
+    assert nl >= len(outs) and ms > 0
+    for key, o in outs:
+        assert np.array_equal(o[0], want[key][0]) and np.array_equal(o[1], want[key][1]), key
+    # a blocking call behind asynchronous ones collects them first
+    po = ctx.pinned_empty(2 * want[(10000, b"TTAGGG")][0].size * 8).view(np.uint64)
+    n = want[(10000, b"TTAGGG")][0].size
+    ctx.window_counts_resident_async(batch, 10000, [b"TTAGGG"], (po[:n], po[n:]))
+    f, r = ctx.window_counts_resident(batch, 777, [b"CCCTAA"])
+    assert np.array_equal(po[:n], want[(10000, b"TTAGGG")][0])
+    assert np.array_equal(f, want[(777, b"CCCTAA")][0]) and np.array_equal(r, want[(777, b"CCCTAA")][1])
+    assert ctx.wait()[1] >= 1  # the asynchronous call's launches are still reported by the next wait
+    batch.free()
+
+
+def test_async_reports_non_ascii_at_wait(ctx):
+    import telomeric_identifier_b200 as T
+    seq = np.frombuffer(b"ACGT" * 5000, dtype=np.uint8).copy()
+    seq[12345] = 0xC3
+    off = np.array([0, seq.size], dtype=np.uint64)
+    batch = ctx.upload(seq, off)
+    po = ctx.pinned_empty(2 * 2 * 8).view(np.uint64)
+    ctx.window_counts_resident_async(batch, 10000, [b"ACGT"], (po[:2], po[2:]))
+    with pytest.raises(T.TidkCudaError) as ei:
+        ctx.wait()
+    assert ei.value.code == T.api.TIDK_ENONASCII
+    ctx.wait()  # the error is reported once
+    batch.free()
