@@ -102,6 +102,12 @@ int tidk_cuda_last_kernel_time(const tidk_ctx *ctx, float *kernel_ms, uint32_t *
 int tidk_cuda_seqbuf_upload(tidk_ctx *ctx, const uint8_t *seq, const uint64_t *offsets,
                             uint32_t n_records, tidk_seqbuf **out);
 void tidk_cuda_seqbuf_free(tidk_ctx *ctx, tidk_seqbuf *buf);
+/* A batch uploaded with tidk_cuda_seqbuf_upload is transposed once on the device, behind the copy, into the
+ * bit-planes the scans compute on (lo = ASCII bit 1, hi = ASCII bit 2, validity, one "32 upper-case A C G T bytes"
+ * bit per word; 0.38 B per base next to the ASCII copy).  Every resident call whose queries have plane kernels, and
+ * the explore scan, then read 0.25 - 0.375 B per base instead of 1.  ready: planes exist (TIDK_PLANES=0 turns the
+ * conversion off); build_ms: device time of the conversion; bytes: device memory they take. */
+int tidk_cuda_seqbuf_planes_info(const tidk_seqbuf *buf, int *ready, float *build_ms, uint64_t *bytes);
 int tidk_cuda_window_counts_resident(tidk_ctx *ctx, const tidk_seqbuf *buf, uint64_t window,
                                      const char *const *queries, const uint32_t *qlens,
                                      uint32_t nq, uint64_t *out_fwd, uint64_t *out_rev,

@@ -19,7 +19,7 @@ EXPORTS = [
     "tidk_cuda_seqbuf_upload", "tidk_cuda_seqbuf_free", "tidk_cuda_window_counts_resident",
     "tidk_cuda_explore_runs", "tidk_cuda_explore_runs_resident", "tidk_cuda_free_runs",
     "tidk_cuda_last_explore_timings", "tidk_cuda_last_transfer", "tidk_cuda_last_kernel_time",
-    "tidk_cuda_window_counts_resident_async", "tidk_cuda_wait",
+    "tidk_cuda_window_counts_resident_async", "tidk_cuda_wait", "tidk_cuda_seqbuf_planes_info",
 ]
 
 
@@ -79,6 +79,8 @@ def load_library():
     L.tidk_cuda_window_counts_resident.restype = C.c_int
     L.tidk_cuda_window_counts_resident_async.argtypes = [vp, vp, C.c_uint64, C.POINTER(C.c_char_p), u32p, C.c_uint32, vp, vp]
     L.tidk_cuda_window_counts_resident_async.restype = C.c_int
+    L.tidk_cuda_seqbuf_planes_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_float), u64p]
+    L.tidk_cuda_seqbuf_planes_info.restype = C.c_int
     L.tidk_cuda_wait.argtypes = [vp, C.POINTER(C.c_float), u32p]
     L.tidk_cuda_wait.restype = C.c_int
     L.tidk_cuda_explore_runs.argtypes = [vp, vp, vp, C.c_uint32, C.c_double, C.c_uint32, C.c_uint32, C.c_uint64,
@@ -116,6 +118,12 @@ class SeqBatch:
 
     def __init__(self, ctx: "Context", handle, offsets: np.ndarray):
         self._ctx, self._h, self.offsets = ctx, handle, offsets
+
+    def planes_info(self):
+        """(ready, build_ms, bytes) of the batch's resident bit-planes (K1, built once behind the upload)."""
+        r, ms, b = C.c_int(0), C.c_float(0), C.c_uint64(0)
+        self._ctx._L.tidk_cuda_seqbuf_planes_info(self._h, C.byref(r), C.byref(ms), C.byref(b))
+        return bool(r.value), ms.value, b.value
 
     def free(self):
         if self._h:

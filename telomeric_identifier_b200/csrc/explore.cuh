@@ -57,7 +57,7 @@ struct KeyFmt {
     uint32_t cb, sb; // bits of the chunk and slice fields; k sits above them, type and joins below
     __host__ __device__ uint32_t total_bits(uint32_t kmax) const {
         uint32_t kb = 1;
-        while ((1u << kb) <= kmax) kb++;
+        while ((1u << kb) <= kmax + 1) kb++; // a real k is never all ones: the all-ones key is the filler of unused event slots
         return kb + sb + cb + 2;
     }
 };

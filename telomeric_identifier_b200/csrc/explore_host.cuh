@@ -11,6 +11,11 @@
 
 namespace tidk {
 
+// ExploreScratch::misc: +0 work counter of the byte-wise kernel, +8 event slots handed out, +16 fillers among them,
+// +32 compaction count, +128 error flags, +1024 the plane kernel's ticket queues (kQueues x 128 bytes)
+constexpr size_t kExMiscQueues = 1024;
+constexpr size_t kExMiscBytes = kExMiscQueues + (size_t)kQueues * kQueueStride * 8;
+
 // split_seq_by_distance (explore.rs:151-160) for every record, plus the tiles each slice is cut into
 __global__ void __launch_bounds__(256) explore_slices_kernel(const uint64_t *off, uint32_t n_records, double d, uint64_t tile,
                                                              uint32_t extra, SliceDesc *slices, uint64_t *tiles) {
@@ -46,7 +51,8 @@ inline int explore_runs_device(ExploreScratch &sc, cudaStream_t st, cudaEvent_t 
                                uint64_t *n_runs, float *kernel_ms, uint32_t *kernel_launches,
                                std::string &err, float *scan_ms = nullptr, float *post_ms = nullptr,
                                float *host_ms = nullptr /* [0] slice table + uploads, [1] post-processing wall incl. D2H */,
-                               const SliceDesc *h_slices = nullptr /* slices laid out by the caller (compacted upload) */) {
+                               const SliceDesc *h_slices = nullptr /* slices laid out by the caller (compacted upload) */,
+                               const uint32_t *d_planes = nullptr, const uint32_t *d_plainbits = nullptr /* resident bit-planes of the batch */) {
     if (scan_ms) *scan_ms = 0.f;
     if (post_ms) *post_ms = 0.f;
     const auto t_begin = std::chrono::steady_clock::now();
@@ -102,7 +108,7 @@ inline int explore_runs_device(ExploreScratch &sc, cudaStream_t st, cudaEvent_t 
         if ((e = grow(sc.tile_base, sc.tile_cap, ((size_t)n_slices + 1) * 8)) != cudaSuccess) return cuerr(e, "cudaMalloc(tile_base)");
         if ((e = grow(sc.tiles, sc.tiles_cap, ((size_t)n_slices + 1) * 8)) != cudaSuccess) return cuerr(e, "cudaMalloc(tiles)");
         if (planes && (e = grow(sc.items, sc.items_cap, n_tiles * sizeof(ExItem))) != cudaSuccess) return cuerr(e, "cudaMalloc(items)");
-        if (!sc.misc && (e = cudaMalloc(&sc.misc, 256)) != cudaSuccess) { sc.misc = nullptr; return cuerr(e, "cudaMalloc(misc)"); }
+        if (!sc.misc && (e = cudaMalloc(&sc.misc, kExMiscBytes)) != cudaSuccess) { sc.misc = nullptr; return cuerr(e, "cudaMalloc(misc)"); }
         size_t scan_bytes = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr, (int)(n_slices + 1), st);
         if ((e = grow(sc.temp, sc.temp_cap, scan_bytes)) != cudaSuccess) return cuerr(e, "cudaMalloc(temp)");
@@ -125,9 +131,9 @@ inline int explore_runs_device(ExploreScratch &sc, cudaStream_t st, cudaEvent_t 
         bool items_ready = false;
         for (int attempt = 0; attempt < 3; attempt++) {
             if ((e = grow(sc.events, sc.events_cap, cap * (packed ? sizeof(uint64_t) : sizeof(RunEvent)))) != cudaSuccess) return cuerr(e, "cudaMalloc(events)");
-            if ((e = cudaMemsetAsync(sc.misc, 0, 256, st)) != cudaSuccess) return cuerr(e, "memset");
+            if ((e = cudaMemsetAsync(sc.misc, 0, kExMiscBytes, st)) != cudaSuccess) return cuerr(e, "memset");
             const uint64_t want = (n_tiles + 7) / 8, maxb = (uint64_t)sm_count * 8;
-            const int grid = (int)std::max<uint64_t>(1, std::min(want, maxb));
+            int grid = (int)std::max<uint64_t>(1, std::min(want, maxb));
             if (host_ms && attempt == 0) host_ms[0] = since(t_begin);
             cudaEventRecord(ev0, st);
             if (planes) {
@@ -145,13 +151,30 @@ inline int explore_runs_device(ExploreScratch &sc, cudaStream_t st, cudaEvent_t 
                 job.kmin = kmin; job.kmax = kmax;
                 job.events = (RunEvent *)sc.events;
                 job.cap_events = cap;
-                job.work_counter = (unsigned long long *)sc.misc;
+                job.work_counter = (unsigned long long *)((char *)sc.misc + kExMiscQueues);
                 job.n_events = (unsigned long long *)sc.misc + 1;
+                job.n_unused = (unsigned long long *)sc.misc + 2;
+                job.zero = 0;
                 job.err_flags = (uint32_t *)((char *)sc.misc + 128);
                 job.packed = packed ? 1u : 0u;
                 job.fmt = fmt;
-                if (kmin == 5 && kmax == 12) explore_planes_kernel<5, 12><<<grid, 256, 0, st>>>(job);
-                else explore_planes_kernel<0, 0><<<grid, 256, 0, st>>>(job);
+                job.planes = d_planes;
+                job.plainbits = d_plainbits;
+                const bool from_planes = d_planes && d_plainbits && !h_slices;
+                // persistent launch: the grid is the resident set (the first items are assigned statically)
+                auto launch = [&](auto kernel) {
+                    int per_sm = 0;
+                    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+                    grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)sm_count * per_sm));
+                    kernel<<<grid, 256, 0, st>>>(job);
+                };
+                if (kmin == 5 && kmax == 12) {
+                    if (from_planes) launch(explore_planes_kernel<5, 12, true>);
+                    else launch(explore_planes_kernel<5, 12, false>);
+                } else {
+                    if (from_planes) launch(explore_planes_kernel<0, 0, true>);
+                    else launch(explore_planes_kernel<0, 0, false>);
+                }
             } else {
                 ExploreJob job{};
                 job.seq = d_seq;
@@ -172,21 +195,22 @@ inline int explore_runs_device(ExploreScratch &sc, cudaStream_t st, cudaEvent_t 
             cudaEventRecord(ev1, st);
             launches++;
             if ((e = cudaGetLastError()) != cudaSuccess) return cuerr(e, "explore kernel launch");
-            unsigned long long h_counts[2] = {0, 0};
+            unsigned long long h_counts[3] = {0, 0, 0};
             uint32_t h_err = 0;
-            if ((e = cudaMemcpyAsync(h_counts, sc.misc, 16, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuerr(e, "D2H counters");
+            if ((e = cudaMemcpyAsync(h_counts, sc.misc, 24, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuerr(e, "D2H counters");
             if ((e = cudaMemcpyAsync(&h_err, (char *)sc.misc + 128, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuerr(e, "D2H flags");
             if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuerr(e, "explore kernel");
             float ms = 0.f;
             cudaEventElapsedTime(&ms, ev0, ev1);
             ms_total += ms;
             if (h_err & 1u) { err = "sequence contains a byte >= 0x80 (str::from_utf8 panics, explore.rs:212)"; return TIDK_ENONASCII; }
-            const uint64_t ne = h_counts[1];
-            if (ne > cap) { cap = ne; continue; } // event buffer too small: rerun with the exact size
+            const uint64_t ne = h_counts[1];               // slots handed out: events + fillers of unused reservations
+            const uint64_t n_real = ne - h_counts[2];
+            if (ne > cap) { cap = ne + ne / 16 + 65536; continue; } // event buffer too small: rerun (reservations make the count vary a little)
             if (packed) { // sort, build runs, filter and compact on the device
                 const auto t_post = std::chrono::steady_clock::now();
                 cudaEventRecord(ev0, st);
-                const int prc = explore_post_device(sc, st, ne, fmt, key_bits, threshold, out_runs, n_runs, &launches, err);
+                const int prc = explore_post_device(sc, st, n_real, ne, fmt, key_bits, threshold, out_runs, n_runs, &launches, err);
                 cudaEventRecord(ev1, st);
                 cudaStreamSynchronize(st);
                 if (host_ms) host_ms[1] = since(t_post);
@@ -200,6 +224,8 @@ inline int explore_runs_device(ExploreScratch &sc, cudaStream_t st, cudaEvent_t 
             }
             events.resize(ne);
             if (ne && (e = cudaMemcpy(events.data(), sc.events, ne * sizeof(RunEvent), cudaMemcpyDeviceToHost)) != cudaSuccess) return cuerr(e, "D2H events");
+            events.erase(std::remove_if(events.begin(), events.end(), [](const RunEvent &ev) { return ev.k == 0xFF && ev.type == 0xFF; }), events.end()); // fillers
+            if (events.size() != n_real) { err = "internal: event count does not match"; return TIDK_ECUDA; }
             break;
         }
         if (kernel_ms) *kernel_ms = ms_total;

@@ -29,6 +29,7 @@
 
 #include "explore.cuh"
 #include "planes.cuh"
+#include "planes_build.cuh"
 
 #ifndef TIDK_EX_LDS_PRMT
 #define TIDK_EX_LDS_PRMT 1 // chunk-end masks: table address and phase folded by one PRMT (see phase_addr)
@@ -105,12 +106,18 @@ struct ExJob {
     uint64_t n_items;
     uint32_t kmin, kmax;
     RunEvent *events;
-    unsigned long long *n_events;
+    unsigned long long *n_events;  // slots handed out (events + the sentinels that fill abandoned reservations)
+    unsigned long long *n_unused;  // sentinels among them
     uint64_t cap_events;
-    unsigned long long *work_counter;
+    unsigned long long *work_counter; // kQueues ticket counters, one per 128-byte line (window_counts.cuh)
+    uint32_t zero;                 // 0: keeps ptxas from proving an atomic's address warp-uniform (see reserve_slots)
     uint32_t *err_flags;
     uint32_t packed; // events are 64-bit keys (pack_event) instead of RunEvent structs
     KeyFmt fmt;
+    // resident bit-planes of the batch (planes_build.cuh), PLANES variant of the scan: lo / hi words in the chunked
+    // layout and one "all 32 bytes are upper-case A C G T" bit per word
+    const uint32_t *planes;
+    const uint32_t *plainbits;
 };
 
 // Events are appended with one atomicAdd each on a global counter (the compiler aggregates the lanes
@@ -133,6 +140,49 @@ __device__ __forceinline__ void emit_event(const ExJob &job, uint32_t slice, uin
             job.events[idx] = ev;
         }
     }
+}
+
+// Event slots are handed to a warp in ranges of kExReserve, requested ahead of need: a returning atomic per event made
+// the emitting lane -- and with it the warp -- wait out an L2 round trip for every run boundary (20 % of the stall
+// samples of the scan).  The part of a range that is never used is filled with sentinel keys (all ones: above every
+// real key, the k field of a real key is never all ones) that the sort sends to the end, and counted in n_unused.
+constexpr uint32_t kExReserve = 32;
+
+__device__ __forceinline__ void store_sentinel(const ExJob &job, unsigned long long idx) {
+    if (idx >= job.cap_events) return;
+    if (job.packed) ((uint64_t *)job.events)[idx] = ~0ull;
+    else {
+        RunEvent ev;
+        ev.slice = 0xFFFFFFFFu; ev.k = 0xFF; ev.type = 0xFF; ev.joins = 0; ev.pad = 0; ev.chunk = ~0ull;
+        job.events[idx] = ev;
+    }
+}
+
+// lane 0 asks for the next range; nothing waits for the answer here.  The address is "lane-dependent" (job.zero is 0):
+// for a provably uniform address ptxas emits its warp-aggregated form, whose closing SHFL consumes the result at once.
+__device__ __forceinline__ void reserve_slots(const ExJob &job, int lane, unsigned long long &raw) {
+    if (lane == 0) {
+        const unsigned long long *a = job.n_events + (size_t)threadIdx.x * job.zero; // (lane is known to be 0 here, threadIdx.x is not)
+        asm volatile("atom.global.add.u64 %0, [%1], %2;" : "=l"(raw) : "l"(a), "l"((unsigned long long)kExReserve) : "memory");
+    }
+}
+
+struct SlotState {
+    unsigned long long base; // next free slot of the current range
+    unsigned long long raw;  // lane 0: answer to the outstanding request
+    uint32_t left;           // free slots in the current range
+    uint32_t unused;         // sentinels written so far
+    bool pending;            // a request is outstanding
+};
+
+// make room for n (<= 32) events: abandon what is left of the current range, move on to the requested one
+__device__ __forceinline__ void next_range(const ExJob &job, int lane, SlotState &st) {
+    if ((uint32_t)lane < st.left) store_sentinel(job, st.base + (uint32_t)lane);
+    st.unused += st.left;
+    if (!st.pending) reserve_slots(job, lane, st.raw); // (first events of a warp, or a burst: wait for it)
+    st.base = __shfl_sync(0xFFFFFFFFu, st.raw, 0);
+    st.left = kExReserve;
+    st.pending = false;
 }
 
 // byte-wise G_k[q] (exact for any bytes)
@@ -356,7 +406,11 @@ __device__ __forceinline__ uint32_t div_exact(uint32_t q, uint32_t k) { return (
 #ifndef TIDK_EX_MINB
 #define TIDK_EX_MINB 3
 #endif
-template <int KMIN, int KMAX>
+// PLANES: the batch's resident bit-planes are the source.  A block whose 32 words are all plain (one bit per word,
+// built with the planes) IS its lo / hi words: no ASCII is read and nothing is transposed; any other block -- lower
+// case, N, IUPAC codes, the tail behind the last base -- is taken from the ASCII copy by the general path below,
+// exactly as in the ASCII variant.
+template <int KMIN, int KMAX, bool PLANES = false>
 __global__ void __launch_bounds__(256, TIDK_EX_MINB) explore_planes_kernel(const ExJob job) {
     __shared__ EvStash<(KMIN > 0 ? KMAX - KMIN + 1 : kPlaneMaxK)> stash;
     __shared__ __align__(256) HTable htab;
@@ -384,24 +438,34 @@ __global__ void __launch_bounds__(256, TIDK_EX_MINB) explore_planes_kernel(const
     // an item is scanned, the next item's block 0 address is fetched at the start of the current item,
     // and its first 1 KiB is requested before the current item's last block is evaluated -- a warp never
     // sits through ticket -> descriptor -> data round trips between items.
-    unsigned long long item = 0, item_next = 0;
-    if (lane == 0) {
-        item = atomicAdd(job.work_counter, 2ull);
-        item_next = item + 1;
-    }
-    item = __shfl_sync(0xFFFFFFFFu, item, 0);
-    item_next = __shfl_sync(0xFFFFFFFFu, item_next, 0);
+    // The grid is the resident set: the first two items of every warp are assigned statically, the rest come from
+    // kQueues ticket counters (queue q hands out the items q, q + kQueues, ... behind the static ones), drawn with
+    // atom.inc two items ahead and not looked at before the end of the item (see window_counts.cuh).
+    const unsigned long long n_warps = (unsigned long long)gridDim.x * 8;
+    const unsigned long long gw = (unsigned long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    unsigned long long item = gw, item_next = gw + n_warps;
+    const unsigned long long ticket0 = 2 * n_warps + (gw & (kQueues - 1));
+    uint32_t *const queue = reinterpret_cast<uint32_t *>(job.work_counter + (gw & (kQueues - 1)) * kQueueStride);
+    SlotState slots = {0ull, 0ull, 0u, 0u, false};
     uint32_t w[8];
-    if (item < job.n_items) ld256_stream(job.seq + job.items[item].scan0 + (uint32_t)lane * 32u, w);
+    uint32_t n_lo = 0, n_hi = 0, n_f0 = 0, n_f1 = 0; // PLANES: the next block's words and plain bits, requested a block ahead
+    auto request = [&](uint64_t byte_off) {       // first lane word of a block -> this lane's data
+        if constexpr (PLANES) {
+            const uint32_t *pw = plane_word_ptr(job.planes, (byte_off >> 5) + (uint32_t)lane);
+            n_lo = __ldg(pw); n_hi = __ldg(pw + kPackWords);
+            n_f0 = __ldg(job.plainbits + (byte_off >> 10)); n_f1 = __ldg(job.plainbits + (byte_off >> 10) + 1);
+        } else {
+            ld256_stream(job.seq + byte_off + (uint32_t)lane * 32u, w);
+        }
+    };
+    if (item < job.n_items) request(job.items[item].scan0);
     while (item < job.n_items) {
         const ExItem *ip = job.items + item;
         const bool have_next = item_next < job.n_items;
         uint64_t scan0_next = 0;
         if (have_next) scan0_next = job.items[item_next].scan0;
-        unsigned long long t2 = 0;
-        // (a plain atom: only lane 0 gets here, the compiler's warp-aggregated atomicAdd would add a vote, a leader
-        // election and two shuffles per item)
-        if (lane == 0) asm volatile("atom.global.add.u64 %0, [%1], 1;" : "=l"(t2) : "l"(job.work_counter) : "memory");
+        uint32_t t2 = 0;
+        if (lane == 0) asm volatile("atom.global.inc.u32 %0, [%1], 0xffffffff;" : "=r"(t2) : "l"(queue) : "memory");
         const uint64_t scan0 = ip->scan0;
         const int64_t rel0 = ip->rel0;
         const int64_t m = (int64_t)ip->slice_len;
@@ -431,13 +495,21 @@ __global__ void __launch_bounds__(256, TIDK_EX_MINB) explore_planes_kernel(const
         // before the last one
         const uint32_t ntail = v_hi <= (int)((nblk - 1u) << 10) ? 2u : 1u;
 
-        const uint8_t *ptr = job.seq + scan0 + (uint32_t)lane * 32u;
-        if (nblk == 0 && have_next) ld256_stream(job.seq + scan0_next + (uint32_t)lane * 32u, w); // (never: every tile owns a position)
+        const uint32_t fsh = (uint32_t)(scan0 >> 5) & 31u; // PLANES: bit of the block's first word in its plain-bits word
+        if (nblk == 0 && have_next) request(scan0_next); // (never: every tile owns a position)
         for (uint32_t blk = 0; blk < nblk; blk++) {
-            const Nibbles nib = to_nibbles(w); // w is dead from here: refill it
-            if (blk + 1 < nblk) { ptr += 1024; ld256_stream(ptr, w); }
-            else if (have_next) ld256_stream(job.seq + scan0_next + (uint32_t)lane * 32u, w);
-            const PlaneCore core = extract_core(nib);
+            Nibbles nib;
+            PlaneCore core;
+            uint32_t plain_lanes;
+            if constexpr (PLANES) {
+                core.lo = n_lo; core.hi = n_hi; core.b0 = 0u; core.bad = 0u;
+                plain_lanes = __funnelshift_r(n_f0, n_f1, fsh);
+            } else {
+                nib = to_nibbles(w); // w is dead from here: refill it
+            }
+            if (blk + 1 < nblk) request(scan0 + ((uint64_t)(blk + 1) << 10));
+            else if (have_next) request(scan0_next);
+            if constexpr (!PLANES) core = extract_core(nib);
             const int prel = (int)(blk << 10) + lane * 32;
             // slice edges (and the item's owned range) can only fall into the first block (the first two
             // of a later tile, which starts one block early) and the last block (or two) of an item
@@ -450,10 +522,13 @@ __global__ void __launch_bounds__(256, TIDK_EX_MINB) explore_planes_kernel(const
 
             // The common block -- interior, every base one of A C G T in upper case, and the block before it
             // of the same kind -- is recognised with ONE warp vote and needs nothing but the lo / hi planes.
-            const uint32_t any_l = nib.Y[0] | nib.Y[1] | nib.Y[2] | nib.Y[3]; // ASCII bit 5 = bit 1 of the high nibbles
-            const bool lane_plain = core.bad == 0u && (core.b0 ^ (core.hi & ~core.lo)) == 0xFFFFFFFFu &&
-                                    (any_l & 0x22222222u) == 0u;
-            const uint32_t plain_lanes = __ballot_sync(0xFFFFFFFFu, lane_plain);
+            uint32_t any_l = 0u;
+            if constexpr (!PLANES) {
+                any_l = nib.Y[0] | nib.Y[1] | nib.Y[2] | nib.Y[3]; // ASCII bit 5 = bit 1 of the high nibbles
+                const bool lane_plain = core.bad == 0u && (core.b0 ^ (core.hi & ~core.lo)) == 0xFFFFFFFFu &&
+                                        (any_l & 0x22222222u) == 0u;
+                plain_lanes = __ballot_sync(0xFFFFFFFFu, lane_plain);
+            }
             // (after a block whose in-slice bases were all upper-case A/C/G/T the case / N / dirty state is
             // the initial one, whichever path evaluated it; the fast path leaves it untouched)
             const bool all_plain = plain_lanes == 0xFFFFFFFFu, calm = !had_n_prev && !dirty_prev;
@@ -502,6 +577,13 @@ __global__ void __launch_bounds__(256, TIDK_EX_MINB) explore_planes_kernel(const
                 TIDK_EXALL(true, false, true)
             } else {
             {
+                if constexpr (PLANES) { // not a plain block, or the state behind one: the bytes themselves
+                    uint32_t wa[8];
+                    ld256_stream(job.seq + scan0 + ((uint64_t)blk << 10) + (uint32_t)lane * 32u, wa);
+                    nib = to_nibbles(wa);
+                    core = extract_core(nib);
+                    any_l = nib.Y[0] | nib.Y[1] | nib.Y[2] | nib.Y[3];
+                }
                 uint32_t na = 0;
                 const Planes P = finish_planes(nib, core, __any_sync(0xFFFFFFFFu, core.bad != 0u), na);
                 if (edge) {
@@ -558,13 +640,24 @@ __global__ void __launch_bounds__(256, TIDK_EX_MINB) explore_planes_kernel(const
             } // !fast
 #undef TIDK_EXALL
 #undef TIDK_EXK
-            if (any_ev) { // rare: this lane found run boundaries in this block
-                for (uint32_t rows = any_ev; rows; rows &= rows - 1) { // only the k that have one
-                    const uint32_t k = (uint32_t)KBASE + (uint32_t)(__ffs(rows) - 1);
-                    uint32_t ev = stash.ev[k - KBASE][threadIdx.x];
-                    while (ev) {
-                        const int b = __ffs(ev) - 1;
-                        ev &= ev - 1;
+            if (__any_sync(0xFFFFFFFFu, any_ev != 0u)) { // some lane found run boundaries in this block: emitted by the warp together
+                uint32_t pend = any_ev, cur_ev = 0u, cur_k = 0u;
+                for (;;) {
+                    if (cur_ev == 0u && pend != 0u) { // next k of this lane that has boundaries
+                        const uint32_t row = (uint32_t)(__ffs(pend) - 1);
+                        pend &= pend - 1;
+                        cur_ev = stash.ev[row][threadIdx.x];
+                        cur_k = (uint32_t)KBASE + row;
+                    }
+                    const bool has = cur_ev != 0u;
+                    const uint32_t mask = __ballot_sync(0xFFFFFFFFu, has);
+                    if (mask == 0u) break;
+                    const uint32_t n = (uint32_t)__popc(mask);
+                    if (slots.left < n) next_range(job, lane, slots);
+                    if (has) {
+                        const int b = __ffs(cur_ev) - 1;
+                        cur_ev &= cur_ev - 1;
+                        const uint32_t k = cur_k;
                         const uint64_t q1 = (uint64_t)(p + b) + 1; // chunk end + 1, a multiple of k
                         const uint64_t j = (q1 >> 32 ? q1 / k : (uint64_t)div_exact((uint32_t)q1, k)) - 2;
                         // a run start in a uniform-case block never joins the previous chunk (they differ
@@ -578,8 +671,24 @@ __global__ void __launch_bounds__(256, TIDK_EX_MINB) explore_planes_kernel(const
                         // wherever the plane path emits); elsewhere the type bit is left 0.
                         const bool start = !need_cs || g_bytes(t, m, (int)k, p + b);
                         const bool joins = need_cs && start && j > 0 && chunks_equal_upper(t, (int)k, j);
-                        emit_event(job, slice, k, j, start, joins);
+                        const unsigned long long idx = slots.base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+                        if (idx < job.cap_events) {
+                            const uint32_t type = start ? 0u : 1u, jn = joins ? 1u : 0u;
+                            if (job.packed) ((uint64_t *)job.events)[idx] = pack_event(job.fmt, slice, k, j, type, jn);
+                            else {
+                                RunEvent ev;
+                                ev.slice = slice; ev.k = (uint8_t)k; ev.type = (uint8_t)type; ev.joins = (uint8_t)jn; ev.pad = 0;
+                                ev.chunk = j;
+                                job.events[idx] = ev;
+                            }
+                        }
                     }
+                    slots.base += n;
+                    slots.left -= n;
+                }
+                if (!slots.pending && slots.left < kExReserve / 2) { // ask for the next range while this one lasts
+                    reserve_slots(job, lane, slots.raw);
+                    slots.pending = true;
                 }
             }
             if (special) { // exact byte-wise evaluation of this block's owned chunk ends
@@ -590,8 +699,17 @@ __global__ void __launch_bounds__(256, TIDK_EX_MINB) explore_planes_kernel(const
             phase_step_all<KBASE, NREG>(ph); // the next block lies 1024 bases further on
         }
         item = item_next;
-        item_next = __shfl_sync(0xFFFFFFFFu, t2, 0);
+        item_next = ticket0 + (unsigned long long)__shfl_sync(0xFFFFFFFFu, t2, 0) * kQueues;
     }
+    // slots this warp was handed and did not use
+    if ((uint32_t)lane < slots.left) store_sentinel(job, slots.base + (uint32_t)lane);
+    slots.unused += slots.left;
+    if (slots.pending) {
+        const unsigned long long b2 = __shfl_sync(0xFFFFFFFFu, slots.raw, 0);
+        store_sentinel(job, b2 + (uint32_t)lane);
+        slots.unused += kExReserve;
+    }
+    if (lane == 0 && slots.unused) atomicAdd(job.n_unused, (unsigned long long)slots.unused);
     if (__any_sync(0xFFFFFFFFu, nonascii != 0) && lane == 0) atomicOr(job.err_flags, 1u);
 }
 

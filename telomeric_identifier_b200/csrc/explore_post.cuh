@@ -99,7 +99,8 @@ __global__ void __launch_bounds__(256) runs_from_keys_kernel(const uint64_t *key
 }
 
 // keys: n_events packed keys in sc.events.  On success *out_runs (malloc) / *n_runs hold the result.
-inline int explore_post_device(ExploreScratch &sc, cudaStream_t st, uint64_t n_events, KeyFmt fmt, int key_bits, uint64_t threshold,
+// n_sorted >= n_events keys sit in sc.events; the surplus are all-ones fillers, which the sort sends behind every event
+inline int explore_post_device(ExploreScratch &sc, cudaStream_t st, uint64_t n_events, uint64_t n_sorted, KeyFmt fmt, int key_bits, uint64_t threshold,
                                tidk_run **out_runs, uint64_t *n_runs, uint32_t *launches, std::string &err) {
     auto cuerr = [&](cudaError_t e, const char *what) {
         err = std::string(what) + " failed: " + cudaGetErrorString(e);
@@ -117,11 +118,11 @@ inline int explore_post_device(ExploreScratch &sc, cudaStream_t st, uint64_t n_e
     if (n_events == 0) return TIDK_OK;
     if (n_events & 1) { err = "internal: odd number of run events"; return TIDK_ECUDA; }
     const uint64_t n_pairs = n_events / 2;
-    if (n_events > 0x7FFFFFFFull) { err = "too many run events for the device path"; return TIDK_EARG; }
+    if (n_sorted > 0x7FFFFFFFull) { err = "too many run events for the device path"; return TIDK_EARG; }
     cudaError_t e;
-    if ((e = grow(sc.keys2, sc.keys2_cap, n_events * 8)) != cudaSuccess) return cuerr(e, "cudaMalloc(keys)");
+    if ((e = grow(sc.keys2, sc.keys2_cap, n_sorted * 8)) != cudaSuccess) return cuerr(e, "cudaMalloc(keys)");
     size_t temp_sort = 0, temp_sel = 0;
-    cub::DeviceRadixSort::SortKeys(nullptr, temp_sort, (const uint64_t *)sc.events, (uint64_t *)sc.keys2, (int)n_events, 0, key_bits, st);
+    cub::DeviceRadixSort::SortKeys(nullptr, temp_sort, (const uint64_t *)sc.events, (uint64_t *)sc.keys2, (int)n_sorted, 0, key_bits, st);
     cub::DeviceSelect::Flagged(nullptr, temp_sel, (const tidk_run *)nullptr, (const uint8_t *)nullptr, (tidk_run *)nullptr,
                                (unsigned long long *)nullptr, (int)n_pairs, st);
     if ((e = grow(sc.temp, sc.temp_cap, std::max(temp_sort, temp_sel))) != cudaSuccess) return cuerr(e, "cudaMalloc(temp)");
@@ -129,7 +130,7 @@ inline int explore_post_device(ExploreScratch &sc, cudaStream_t st, uint64_t n_e
     if ((e = grow(sc.runs_out, sc.runs_out_cap, n_pairs * sizeof(tidk_run))) != cudaSuccess) return cuerr(e, "cudaMalloc(runs_out)");
     if ((e = grow(sc.flags, sc.flags_cap, n_pairs)) != cudaSuccess) return cuerr(e, "cudaMalloc(flags)");
     size_t tb = sc.temp_cap;
-    if ((e = cub::DeviceRadixSort::SortKeys(sc.temp, tb, (const uint64_t *)sc.events, (uint64_t *)sc.keys2, (int)n_events, 0, key_bits, st)) != cudaSuccess)
+    if ((e = cub::DeviceRadixSort::SortKeys(sc.temp, tb, (const uint64_t *)sc.events, (uint64_t *)sc.keys2, (int)n_sorted, 0, key_bits, st)) != cudaSuccess)
         return cuerr(e, "radix sort");
     uint32_t *d_err = (uint32_t *)((char *)sc.misc + 128);
     unsigned long long *d_nsel = (unsigned long long *)sc.misc + 4;

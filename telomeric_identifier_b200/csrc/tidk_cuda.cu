@@ -21,6 +21,7 @@
 
 #include "explore_host.cuh"
 #include "host_pack.hpp"
+#include "planes_build.cuh"
 #include "window_counts.cuh"
 
 using namespace tidk;
@@ -44,6 +45,12 @@ struct tidk_seqbuf {
     uint32_t n_records = 0;
     uint64_t total = 0;
     uint64_t id = 0; // changes whenever the contents change (invalidates ctx-side caches)
+    // resident bit-planes (planes_build.cuh), built once behind the upload of a batch that stays resident
+    uint32_t *d_planes = nullptr, *d_plainbits = nullptr, *d_validbits = nullptr;
+    size_t planes_cap = 0, bits_cap = 0;
+    bool planes_ready = false;
+    bool planes_nonascii = false; // the conversion saw a byte >= 0x80
+    float planes_ms = 0.f;        // device time of the conversion
 };
 
 // Packer threads of the host-packed upload, kept parked between calls: creating and joining 15 threads per call
@@ -305,7 +312,55 @@ int seqbuf_fill(tidk_ctx *ctx, tidk_seqbuf *b, const uint8_t *seq, const uint64_
 void seqbuf_release(tidk_seqbuf *b) {
     if (b->d_seq) cudaFree(b->d_seq);
     if (b->d_off) cudaFree(b->d_off);
+    for (uint32_t *p : {b->d_planes, b->d_plainbits, b->d_validbits})
+        if (p) cudaFree(p);
     b->d_seq = nullptr; b->d_off = nullptr; b->seq_cap = b->off_cap = 0;
+    b->d_planes = b->d_plainbits = b->d_validbits = nullptr;
+    b->planes_cap = b->bits_cap = 0;
+    b->planes_ready = false;
+}
+
+// K1 (planes_build.cuh) over the whole batch, in stream order behind its upload.  Blocks until done (the caller
+// of an upload waits for the copy anyway) and records the device time.
+int seqbuf_build_planes(tidk_ctx *ctx, tidk_seqbuf *b) {
+    b->planes_ready = false;
+    const uint64_t n_blocks = (b->total + 1023) / 1024 + kSeqPad / 1024; // the data and the zero padding behind it
+    const uint64_t n_chunks = (n_blocks * 32 + kPackWords - 1) / kPackWords;
+    const size_t plane_bytes = (size_t)n_chunks * 3 * kPackWords * 4, bits_bytes = ((size_t)n_blocks + 2) * 4;
+    auto grow = [&](uint32_t *&p, size_t &cap, size_t need) -> int {
+        if (p && need <= cap) return TIDK_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        const cudaError_t e = cudaMalloc((void **)&p, need);
+        if (e != cudaSuccess) { p = nullptr; return fail(ctx, TIDK_ENOMEM, "cudaMalloc(planes %zu) failed: %s", need, cudaGetErrorString(e)); }
+        cap = need;
+        return TIDK_OK;
+    };
+    int rc;
+    size_t cap2 = b->bits_cap;
+    if ((rc = grow(b->d_planes, b->planes_cap, plane_bytes))) return rc;
+    if ((rc = grow(b->d_plainbits, b->bits_cap, bits_bytes))) return rc;
+    if ((rc = grow(b->d_validbits, cap2, bits_bytes))) return rc;
+    if (!ctx->h_flags) {
+        CU(ctx, cudaHostAlloc((void **)&ctx->h_flags, 64, cudaHostAllocMapped));
+        memset(ctx->h_flags, 0, 64);
+        CU(ctx, cudaHostGetDevicePointer((void **)&ctx->d_flags, ctx->h_flags, 0));
+    }
+    // (the plain / valid words behind the last converted block are read by the scans' look-ahead: zero)
+    CU(ctx, cudaMemsetAsync(b->d_plainbits + n_blocks, 0, 8, ctx->stream));
+    CU(ctx, cudaMemsetAsync(b->d_validbits + n_blocks, 0, 8, ctx->stream));
+    PlaneBuildJob job{b->d_seq, b->d_planes, b->d_plainbits, b->d_validbits, n_blocks, ctx->d_flags + 1};
+    const uint64_t want = (n_blocks + 7) / 8, cap = (uint64_t)ctx->sm_count * 8;
+    CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    planes_build_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, ctx->stream>>>(job);
+    CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaEventElapsedTime(&b->planes_ms, ctx->ev0, ctx->ev1));
+    b->planes_nonascii = (ctx->h_flags[1] & 1u) != 0;
+    ctx->h_flags[1] = 0;
+    b->planes_ready = true;
+    return TIDK_OK;
 }
 
 inline bool is_acgt(uint8_t c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
@@ -552,6 +607,9 @@ int tidk_cuda_seqbuf_upload(tidk_ctx *ctx, const uint8_t *seq, const uint64_t *o
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) rc = fail(ctx, TIDK_ECUDA, "upload failed: %s", cudaGetErrorString(e));
     }
+    // a batch that stays resident is transposed once (K1): every later pass reads the planes
+    static const bool planes_on = !(getenv("TIDK_PLANES") && atoi(getenv("TIDK_PLANES")) == 0);
+    if (rc == TIDK_OK && planes_on && b->total > 0) rc = seqbuf_build_planes(ctx, b);
     if (rc != TIDK_OK) { seqbuf_release(b); delete b; return rc; }
     *out = b;
     return TIDK_OK;
@@ -864,18 +922,54 @@ static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint3
     return TIDK_OK;
 }
 
+// every query runs on a compile-time plane kernel that reads packed planes (directly, as a known clade, or through
+// its reverse complement)
+static bool queries_packable(const char *const *queries, const uint32_t *qlens, uint32_t nq) {
+    if (!queries || !qlens || nq == 0) return false;
+    if (find_clade_set(queries, qlens, nq, true)) return true;
+    uint8_t rcbuf[kMaxFastLen];
+    for (uint32_t q = 0; q < nq; q++) {
+        bool ok = queries[q] && qlens[q] >= 1 && qlens[q] <= (uint32_t)kMaxFastLen;
+        for (uint32_t j = 0; ok && j < qlens[q]; j++) ok = is_acgt((uint8_t)queries[q][j]);
+        if (!ok) return false;
+        revcomp_host((const uint8_t *)queries[q], qlens[q], rcbuf);
+        if (!find_static((const uint8_t *)queries[q], qlens[q], true) && !find_static(rcbuf, qlens[q], true)) return false;
+    }
+    return true;
+}
+
+// The planes of a resident batch are the source whenever every query has a plane-reading kernel (0.375 B per base
+// instead of 1, nothing transposed); other queries scan the ASCII copy.
+static const uint32_t *resident_planes(tidk_ctx *ctx, const tidk_seqbuf *buf, const char *const *queries, const uint32_t *qlens,
+                                       uint32_t nq, int *rc) {
+    *rc = TIDK_OK;
+    static const bool on = !(getenv("TIDK_PLANES_COUNT") && atoi(getenv("TIDK_PLANES_COUNT")) == 0);
+    if (!on || !buf || !buf->planes_ready || !queries_packable(queries, qlens, nq)) return nullptr;
+    if (buf->planes_nonascii)
+        *rc = fail(ctx, TIDK_ENONASCII, "sequence contains a byte >= 0x80 (the reference fails in str::from_utf8, search.rs:107)");
+    return buf->d_planes;
+}
+
 int tidk_cuda_window_counts_resident(tidk_ctx *ctx, const tidk_seqbuf *buf, uint64_t window,
                                      const char *const *queries, const uint32_t *qlens,
                                      uint32_t nq, uint64_t *out_fwd, uint64_t *out_rev,
                                      float *kernel_ms, uint32_t *kernel_launches) {
-    return window_counts_impl(ctx, buf, nullptr, window, queries, qlens, nq, out_fwd, out_rev, kernel_ms,
+    if (!ctx) return TIDK_EARG;
+    int rc;
+    const uint32_t *planes = resident_planes(ctx, buf, queries, qlens, nq, &rc);
+    if (rc) return rc;
+    return window_counts_impl(ctx, buf, planes, window, queries, qlens, nq, out_fwd, out_rev, kernel_ms,
                               kernel_launches);
 }
 
 int tidk_cuda_window_counts_resident_async(tidk_ctx *ctx, const tidk_seqbuf *buf, uint64_t window,
                                            const char *const *queries, const uint32_t *qlens,
                                            uint32_t nq, uint64_t *out_fwd, uint64_t *out_rev) {
-    return window_counts_impl(ctx, buf, nullptr, window, queries, qlens, nq, out_fwd, out_rev, nullptr, nullptr, 0, /*async=*/true);
+    if (!ctx) return TIDK_EARG;
+    int rc;
+    const uint32_t *planes = resident_planes(ctx, buf, queries, qlens, nq, &rc);
+    if (rc) return rc;
+    return window_counts_impl(ctx, buf, planes, window, queries, qlens, nq, out_fwd, out_rev, nullptr, nullptr, 0, /*async=*/true);
 }
 
 int tidk_cuda_wait(tidk_ctx *ctx, float *kernel_ms, uint32_t *kernel_launches) {
@@ -1181,19 +1275,7 @@ int tidk_cuda_window_counts(tidk_ctx *ctx, const uint8_t *seq, const uint64_t *o
     // and writes + re-reads the planes -- only adds to that: measured 180 vs 184 Gbases/s on 8 GPUs.
     const char *eh = getenv("TIDK_HYBRID_UPLOAD");
     const bool hybrid = window <= kSegBytes && (eh ? atoi(eh) != 0 : true); // windows of one 32 KiB item can be split between the sources
-    bool packable = total >= (32u << 20) && seq && queries && qlens && nq > 0 && (env ? atoi(env) != 0 : T >= 12) && T >= 1;
-    if (packable && !find_clade_set(queries, qlens, nq, true)) {
-        uint8_t rcbuf[kMaxFastLen];
-        for (uint32_t q = 0; q < nq && packable; q++) {
-            bool ok = queries[q] && qlens[q] >= 1 && qlens[q] <= (uint32_t)kMaxFastLen;
-            for (uint32_t j = 0; ok && j < qlens[q]; j++) ok = is_acgt((uint8_t)queries[q][j]);
-            if (ok) {
-                revcomp_host((const uint8_t *)queries[q], qlens[q], rcbuf);
-                ok = find_static((const uint8_t *)queries[q], qlens[q], true) || find_static(rcbuf, qlens[q], true);
-            }
-            packable = ok;
-        }
-    }
+    const bool packable = total >= (32u << 20) && seq && (env ? atoi(env) != 0 : T >= 12) && T >= 1 && queries_packable(queries, qlens, nq);
     uint64_t n_out = 0;
     for (uint32_t r = 0; r < n_records && offsets; r++) {
         const uint64_t len = offsets[r + 1] - offsets[r];
@@ -1233,7 +1315,8 @@ int tidk_cuda_explore_runs_resident(tidk_ctx *ctx, const tidk_seqbuf *buf, doubl
     int rc = explore_runs_device(ctx->ex, ctx->stream, ctx->ev0, ctx->ev1, ctx->sm_count, buf->d_seq,
                                  buf->d_off, buf->h_off.data(), buf->n_records, distance, kmin, kmax,
                                  threshold, out_runs, n_runs, kernel_ms, kernel_launches, err,
-                                 &ctx->explore_scan_ms, &ctx->explore_post_ms, ctx->explore_host_ms);
+                                 &ctx->explore_scan_ms, &ctx->explore_post_ms, ctx->explore_host_ms, nullptr,
+                                 buf->planes_ready ? buf->d_planes : nullptr, buf->planes_ready ? buf->d_plainbits : nullptr);
     if (rc) return fail(ctx, rc, "%s", err.c_str());
     return TIDK_OK;
 }
@@ -1325,6 +1408,14 @@ int tidk_cuda_explore_runs(tidk_ctx *ctx, const uint8_t *seq, const uint64_t *of
 void tidk_cuda_free_runs(tidk_run *runs) {
     if (!runs) return;
     if (!tidk::RunBlockPool::get().give_back(runs)) free(runs); // large lists live in pooled pinned blocks (explore_post.cuh)
+}
+
+int tidk_cuda_seqbuf_planes_info(const tidk_seqbuf *buf, int *ready, float *build_ms, uint64_t *bytes) {
+    if (!buf) return TIDK_EARG;
+    if (ready) *ready = buf->planes_ready ? 1 : 0;
+    if (build_ms) *build_ms = buf->planes_ready ? buf->planes_ms : 0.f;
+    if (bytes) *bytes = buf->planes_ready ? (uint64_t)buf->planes_cap + 2 * (uint64_t)buf->bits_cap : 0;
+    return TIDK_OK;
 }
 
 int tidk_cuda_last_transfer(const tidk_ctx *ctx, uint64_t *h2d_bytes, uint64_t *d2h_bytes, int *host_packed) {
