@@ -226,8 +226,13 @@ def explore_block(ctx, peak):
     pseq = ctx.pinned_empty(seq.size)
     pseq[:] = seq
     batch = ctx.upload(pseq, off)
+    p_ready, p_ms, p_bytes = batch.planes_info()
     out = {"workload": f"C5-shaped: {n_reads} reads, {seq.size} bases, explore --minimum 5 --maximum 12 --threshold 100 --distance 0.5",
-           "scanned_bases": scanned, "k_range": [5, 12], "threshold": 100}
+           "scanned_bases": scanned, "k_range": [5, 12], "threshold": 100,
+           "kernels": "scan = explore_slices_kernel + prefix sums + vt_items_kernel + explore_vertical_kernel<5,12> on the resident "
+                      "bit-planes (tiles with anything but upper-case A C G T: explore_planes_kernel on the ASCII copy); post = radix "
+                      "sort of the event keys + runs_from_keys_kernel + compaction (CUB)",
+           "k1_planes_build_ms": p_ms, "k1_frac_of_hbm_peak": 1.375 * seq.size / (p_ms * 1e-3) / 1e9 / peak if p_ms > 0 else None}
     runs = None
     for name, kmin, kmax in (("k5_12", 5, 12), ("k6_single", 6, 6)):
         best = None
@@ -241,10 +246,13 @@ def explore_block(ctx, peak):
         if name == "k5_12":
             runs = r
         ach = scanned / (best[0] * 1e-3) / 1e9
+        all_ms = best[0] + best[1]
         out[name] = {"scan_kernel_ms": best[0], "post_ms": best[1], "resident_call_wall_ms": best[2] * 1e3, "runs": int(r.size),
                      "scan_gbases_per_s": ach,
-                     "roofline": {"bound": "alu pipe (instruction issue), not hbm: see DESIGN.md 3.3", "achieved": ach, "peak": peak,
-                                  "unit": "GB/s", "frac": ach / peak, "algorithmic_bytes_per_launch": scanned}}
+                     "roofline": {"bound": "alu pipe + instruction fetch, not hbm (0.25 B per base cross HBM): see DESIGN.md 3.3",
+                                  "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "algorithmic_bytes_per_launch": scanned},
+                     "all_kernels": {"ms": all_ms, "achieved": scanned / (all_ms * 1e-3) / 1e9, "frac": scanned / (all_ms * 1e-3) / 1e9 / peak,
+                                     "with_k1": {"ms": all_ms + p_ms, "frac": scanned / ((all_ms + p_ms) * 1e-3) / 1e9 / peak}}}
     # the same call through the host-pointer entry point (upload inside)
     e2e_ms = None
     for _ in range(3):
@@ -436,6 +444,20 @@ def main():
         ctx.window_counts_resident(batch, WINDOW, QUERY, out=outs[0])
         kb += ctx.last_kernel_ms
     blocking = {"wall_ms_per_call": (time.perf_counter() - t_b) / nb * 1e3, "kernel_ms_per_call": kb / nb}
+    # the same passes with the ASCII copy as the source (1 B per base from HBM, planes formed in registers): the kernel
+    # round 1 reported, kept beside the default -- the bit-planes K1 builds once at upload (0.375 B per base)
+    planes_ready, planes_ms, planes_bytes = batch.planes_info()
+    os.environ["TIDK_PLANES_COUNT"] = "0"
+    try:
+        ctx.window_counts_resident(batch, WINDOW, QUERY, out=outs[0])
+        ka = []
+        for _ in range(8):
+            ctx.window_counts_resident(batch, WINDOW, QUERY, out=outs[0])
+            ka.append(ctx.last_kernel_ms)
+        ascii_ms = float(np.median(ka))
+        assert np.array_equal(outs[0][0], f) and np.array_equal(outs[0][1], r), "ASCII-source counts differ"
+    finally:
+        os.environ.pop("TIDK_PLANES_COUNT", None)
 
     # end to end through the C ABI with host buffers
     e2e_steps = args.e2e_steps or min(steps, 5)
@@ -464,9 +486,9 @@ def main():
     del dst, src
 
     if dist is not None:
-        t = torch.tensor([dt, dt_e2e, kernel_ms], device="cuda", dtype=torch.float64)
+        t = torch.tensor([dt, dt_e2e, kernel_ms, ascii_ms, planes_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt, dt_e2e, kernel_ms = (float(x) for x in t.tolist())
+        dt, dt_e2e, kernel_ms, ascii_ms, planes_ms = (float(x) for x in t.tolist())
         tot = torch.tensor([float(bases), float(launches), float(f.sum()), float(r.sum()), float(h2d_bytes), float(d2h_bytes)],
                            device="cuda", dtype=torch.float64)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
@@ -517,10 +539,26 @@ def main():
         k_ms = kernel_ms / (steps * PASSES)  # max over ranks of the mean device time per pass
         per_gpu = total_bases / world
         achieved = per_gpu / (k_ms * 1e-3) / 1e9  # GB/s per GPU at 1 B per scanned base
+        src_name = "PackedSource" if planes_ready else "AsciiSource"
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "window_counts_kernel<StaticMatcher<6,TTAGGG>,4,AsciiSource>", "kernel_ms": k_ms,
+                "traffic": None, "kernel": f"window_counts_kernel<StaticMatcher<6,TTAGGG>,4,{src_name}>", "kernel_ms": k_ms,
                 "algorithmic_bytes_per_launch": per_gpu, "peak_source": peak_src,
-                "note": "per GPU: bases of one rank's range / slowest rank's mean kernel time per pass"}
+                "note": "per GPU: bases of one rank's range / slowest rank's mean kernel time per pass; `achieved` counts the "
+                        "ALGORITHMIC 1 B per scanned base (SURVEY.md 8d)"}
+        if planes_ready:
+            # the resident batch is read as bit-planes (lo / hi / validity, 0.375 B per base) that K1 built once behind the
+            # upload: frac above 1 means less than one byte per base crosses HBM, not that the peak was beaten
+            dram = 0.375 * per_gpu
+            roof["source"] = {"what": "resident bit-planes, built once per upload by planes_build_kernel (K1)",
+                              "dram_bytes_per_launch_estimate": dram, "dram_gbs_estimate": dram / (k_ms * 1e-3) / 1e9,
+                              "frac_of_peak_on_dram_bytes": dram / (k_ms * 1e-3) / 1e9 / peak,
+                              "k1_planes_build_ms": planes_ms, "k1_bytes": "1 B read + 0.375 B written per base",
+                              "k1_frac_of_peak": 1.375 * per_gpu / (planes_ms * 1e-3) / 1e9 / peak if planes_ms > 0 else None,
+                              "planes_device_bytes": planes_bytes}
+            roof["ascii_source"] = {"kernel": "window_counts_kernel<StaticMatcher<6,TTAGGG>,4,AsciiSource>", "kernel_ms": ascii_ms,
+                                    "achieved": per_gpu / (ascii_ms * 1e-3) / 1e9, "frac": per_gpu / (ascii_ms * 1e-3) / 1e9 / peak,
+                                    "note": "same passes with TIDK_PLANES_COUNT=0: 1 B per base from HBM, planes formed in registers "
+                                            "(blocking calls, median of 8)"}
         tr = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tr) and world == 1 and SCALE == 1.0:
             try:

@@ -33,7 +33,12 @@ extern "C" {
 #define TIDK_ECUDA (-2)     /* CUDA runtime / launch failure, or no device */
 #define TIDK_ENOMEM (-3)    /* host or device allocation failed */
 #define TIDK_ENONASCII (-4) /* sequence byte >= 0x80: the reference errors in str::from_utf8
-                               (search.rs:107, finder.rs:146) or changes length in to_uppercase */
+                               (search.rs:107, finder.rs:146) or changes length in to_uppercase.
+                               explore: STRICTER than the reference ON PURPOSE -- explore.rs:212 only
+                               panics when such a byte sits in a chunk that equals its neighbour; the
+                               library rejects it anywhere inside a scanned slice (a byte >= 0x80 is never
+                               valid FASTA sequence, and one rule per slice keeps the scan free of a
+                               per-chunk check) */
 
 typedef struct tidk_ctx tidk_ctx;
 typedef struct tidk_seqbuf tidk_seqbuf;
@@ -41,9 +46,13 @@ typedef struct tidk_seqbuf tidk_seqbuf;
 /* ABI version of this header (bumped on any signature change). */
 uint32_t tidk_cuda_abi_version(void);
 
-/* Create a context on the given CUDA devices (device_ids == NULL: device 0).
- * Round 1 drives one device per ctx; multi-GPU runs use one process (and ctx)
- * per GPU, sharding records/windows with no data-path collective. */
+/* Create a context on the given CUDA devices (device_ids == NULL or n_devices == 0: device 0).
+ * n_devices > 1: ONE context that fans every call out to all listed devices (one worker thread per device inside the
+ * call, no data-path collective): host-pointer window counts are cut into equal contiguous window ranges (long records at
+ * multiples of the window, search.rs:98,105-110), explore and resident batches into contiguous groups of whole records;
+ * counts land in the usual [record][query][window] arrays, runs come back in the reference's arrival order.  This is what
+ * a single-process host -- the reference's drivers are one sequential loop, search.rs:57 -- binds to use a whole box.
+ * The same id may be listed twice (two contexts on one device).  One process per GPU (bench.py) remains possible. */
 int tidk_cuda_create(const int *device_ids, int n_devices, tidk_ctx **out);
 void tidk_cuda_destroy(tidk_ctx *ctx);
 /* ctx-owned string, valid until the next call on ctx.  ctx == NULL returns the

@@ -3,6 +3,7 @@ would bind (include/tidk_cuda.h)."""
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 import os
 from typing import List, Optional, Sequence, Tuple
 
@@ -118,6 +119,7 @@ class SeqBatch:
 
     def __init__(self, ctx: "Context", handle, offsets: np.ndarray):
         self._ctx, self._h, self.offsets = ctx, handle, offsets
+        ctx._batches.add(self)
 
     def planes_info(self):
         """(ready, build_ms, bytes) of the batch's resident bit-planes (K1, built once behind the upload)."""
@@ -126,9 +128,10 @@ class SeqBatch:
         return bool(r.value), ms.value, b.value
 
     def free(self):
-        if self._h:
+        if self._h and self._ctx._h:  # (a closed context has freed the batch already)
             self._ctx._L.tidk_cuda_seqbuf_free(self._ctx._h, self._h)
-            self._h = None
+        self._h = None
+        self._ctx._batches.discard(self)
 
     def __del__(self):
         try:
@@ -138,21 +141,32 @@ class SeqBatch:
 
 
 class Context:
-    """tidk_ctx: one CUDA device, one stream."""
+    """tidk_ctx: one CUDA device, one stream -- or, with a list of device ids, one context over several devices
+    (tidk_cuda_create with n_devices > 1: every call is fanned out, include/tidk_cuda.h)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device=0):
         self._L = load_library()
         h = C.c_void_p()
-        ids = (C.c_int * 1)(device)
-        rc = self._L.tidk_cuda_create(ids, 1, C.byref(h))
+        devs = [int(device)] if np.isscalar(device) else [int(d) for d in device]
+        ids = (C.c_int * len(devs))(*devs)
+        rc = self._L.tidk_cuda_create(ids, len(devs), C.byref(h))
         if rc != 0:
             raise TidkCudaError(rc, (self._L.tidk_cuda_last_error(None) or b"").decode())
         self._h = h
         self.last_kernel_ms = 0.0
         self.last_kernel_launches = 0
+        self._pinned = []          # blocks handed out by pinned_empty
+        self._batches = weakref.WeakSet()  # live SeqBatch handles
 
     def close(self):
+        """Frees the resident batches and the pinned blocks of this context, then the context.  Arrays returned by
+        pinned_empty must not be touched afterwards."""
         if self._h:
+            for b in list(self._batches):
+                b.free()
+            for p in self._pinned:
+                self._L.tidk_cuda_host_free(self._h, p)
+            self._pinned = []
             self._L.tidk_cuda_destroy(self._h)
             self._h = None
 
@@ -174,7 +188,6 @@ class Context:
         buf = (C.c_uint8 * max(nbytes, 1)).from_address(p)
         arr = np.frombuffer(buf, dtype=np.uint8, count=nbytes)
         arr.flags.writeable = True
-        self._pinned = getattr(self, "_pinned", [])
         self._pinned.append(p)
         return arr
 

@@ -96,12 +96,14 @@ struct ExploreJob {
 struct ExploreScratch {
     void *slices = nullptr, *tile_base = nullptr, *tiles = nullptr, *events = nullptr, *misc = nullptr, *items = nullptr;
     void *keys2 = nullptr, *temp = nullptr, *runs = nullptr, *flags = nullptr, *runs_out = nullptr;
+    void *vtiles = nullptr; // tile list of the vertical scan (explore_vertical.cuh)
+    size_t vtiles_cap = 0;
     size_t slices_cap = 0, tile_cap = 0, tiles_cap = 0, events_cap = 0, items_cap = 0;
     size_t keys2_cap = 0, temp_cap = 0, runs_cap = 0, flags_cap = 0, runs_out_cap = 0;
 };
 
 inline void explore_scratch_release(ExploreScratch &s) {
-    for (void *p : {s.slices, s.tile_base, s.tiles, s.events, s.misc, s.items, s.keys2, s.temp, s.runs, s.flags, s.runs_out})
+    for (void *p : {s.slices, s.tile_base, s.tiles, s.events, s.misc, s.items, s.keys2, s.temp, s.runs, s.flags, s.runs_out, s.vtiles})
         if (p) cudaFree(p);
     s = ExploreScratch();
 }

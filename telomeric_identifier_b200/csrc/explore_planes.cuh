@@ -64,6 +64,32 @@ struct ExPrepJob {
     uint32_t n_slices, kmax, tile;
 };
 
+// The work item that owns the chunk-end positions [own_beg, own_end) (slice-relative) of slice `slice`.  A range that
+// does not start at the slice start is scanned from one block earlier: real look-behind planes for its first block.
+__device__ __forceinline__ ExItem make_ex_item(const SliceDesc sd, uint32_t slice, uint64_t own_beg, uint64_t own_end) {
+    ExItem d;
+    memset(&d, 0, sizeof d);
+    uint64_t scan0 = (sd.beg + own_beg) & ~31ull;
+    if (own_beg > 0) scan0 -= 1024;
+    d.scan0 = scan0;
+    d.rel0 = (int64_t)scan0 - (int64_t)sd.beg;
+    d.slice_len = sd.len;
+    d.slice = slice;
+    const uint64_t end_abs = sd.beg + own_end;
+    d.nblk = (uint16_t)((end_abs - scan0 + 1023) >> 10);
+    d.own_lo = (uint16_t)(sd.beg + own_beg - scan0);
+    d.own_hi = (uint16_t)(end_abs - scan0);
+    d.v_lo = (uint16_t)(d.rel0 < 0 ? -d.rel0 : 0);
+    const int64_t vhi = (int64_t)sd.len - d.rel0;
+    d.v_hi = (uint16_t)(vhi < 0 ? 0 : (vhi > 65535 ? 65535 : vhi));
+    for (int k = 1; k <= kPlaneMaxK; k++) {
+        int64_t r = d.rel0 % k;
+        if (r < 0) r += k;
+        d.r0[k - 1] = (uint8_t)r;
+    }
+    return d;
+}
+
 __global__ void __launch_bounds__(256) explore_items_kernel(const ExPrepJob job) {
     const uint64_t item = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (item >= job.n_items) return;
@@ -76,27 +102,7 @@ __global__ void __launch_bounds__(256) explore_items_kernel(const ExPrepJob job)
     const uint64_t tile_off = (item - job.tile_base[lo]) * (uint64_t)job.tile;
     const uint64_t q_end = sd.len + job.kmax; // chunk ends up to m + k - 1 close the last run
     const uint64_t own_end = tile_off + job.tile < q_end ? tile_off + job.tile : q_end;
-    ExItem d;
-    memset(&d, 0, sizeof d);
-    uint64_t scan0 = (sd.beg + tile_off) & ~31ull;
-    if (tile_off > 0) scan0 -= 1024; // real look-behind planes for the first owned block
-    d.scan0 = scan0;
-    d.rel0 = (int64_t)scan0 - (int64_t)sd.beg;
-    d.slice_len = sd.len;
-    d.slice = lo;
-    const uint64_t end_abs = sd.beg + own_end;
-    d.nblk = (uint16_t)((end_abs - scan0 + 1023) >> 10);
-    d.own_lo = (uint16_t)(sd.beg + tile_off - scan0);
-    d.own_hi = (uint16_t)(end_abs - scan0);
-    d.v_lo = (uint16_t)(d.rel0 < 0 ? -d.rel0 : 0);
-    const int64_t vhi = (int64_t)sd.len - d.rel0;
-    d.v_hi = (uint16_t)(vhi < 0 ? 0 : (vhi > 65535 ? 65535 : vhi));
-    for (int k = 1; k <= kPlaneMaxK; k++) {
-        int64_t r = d.rel0 % k;
-        if (r < 0) r += k;
-        d.r0[k - 1] = (uint8_t)r;
-    }
-    job.items[item] = d;
+    job.items[item] = make_ex_item(sd, lo, tile_off, own_end);
 }
 
 struct ExJob {
@@ -118,6 +124,8 @@ struct ExJob {
     // layout and one "all 32 bytes are upper-case A C G T" bit per word
     const uint32_t *planes;
     const uint32_t *plainbits;
+    // when set, the number of items is read from here (the list the vertical scan leaves behind, explore_vertical.cuh)
+    const unsigned long long *n_items_dev;
 };
 
 // Events are appended with one atomicAdd each on a global counter (the compiler aggregates the lanes
@@ -458,10 +466,11 @@ __global__ void __launch_bounds__(256, TIDK_EX_MINB) explore_planes_kernel(const
             ld256_stream(job.seq + byte_off + (uint32_t)lane * 32u, w);
         }
     };
-    if (item < job.n_items) request(job.items[item].scan0);
-    while (item < job.n_items) {
+    const unsigned long long n_items = job.n_items_dev ? *job.n_items_dev : job.n_items;
+    if (item < n_items) request(job.items[item].scan0);
+    while (item < n_items) {
         const ExItem *ip = job.items + item;
-        const bool have_next = item_next < job.n_items;
+        const bool have_next = item_next < n_items;
         uint64_t scan0_next = 0;
         if (have_next) scan0_next = job.items[item_next].scan0;
         uint32_t t2 = 0;

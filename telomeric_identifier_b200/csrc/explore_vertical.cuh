@@ -1,0 +1,360 @@
+// explore_vertical.cuh -- the explore scan on resident bit-planes in VERTICAL (transposed) form.
+//
+// Same contract as explore_planes_kernel (explore_planes.cuh): one event per raw-run boundary of every (slice, k)
+// (explore.rs:178-233; the look-behind restatement and the arithmetic are in explore_vertical_core.hpp).  A lane owns
+// a tile of 1024 consecutive bases of one slice, a warp 32 such tiles; tiles of a slice start every 960 bases at the
+// slice start (not at a word boundary: the lane funnel-shifts its 33 plane words into place), so the first tile needs
+// no validity mask -- what lies before the slice is the zero column the transposed form shifts in -- and a later
+// tile's first 64 positions are look-behind only.  Nothing of the k loop needs a shuffle, a carry or a phase-dependent
+// shift: all 32 bit columns of a vertical word are independent positions 32 bases apart.
+//
+// Exactness.  The lo / hi planes are the bytes only where a 32-base word is "plain" (32 upper-case A C G T; one bit
+// per word, built with the planes).  A tile whose in-slice words are all plain is scanned here; any other tile -- lower
+// case, N, IUPAC codes, whatever else -- is appended as an ordinary work item to a list that explore_planes_kernel
+// (ASCII source, every byte value, letter case, joins) works off right behind this kernel.  Both own the same chunk-end
+// positions per tile and write into the same event buffer, so which of them scanned a tile does not show in the result.
+// What lies behind the end of a slice is never masked: events found there are dropped when they are emitted, and the
+// run that touches the slice end is closed by the parity rule of vt_emit.
+#pragma once
+#include "explore_planes.cuh"
+#include "explore_vertical_core.hpp"
+
+namespace tidk {
+
+constexpr int kVWarps = 4;          // warps per CTA
+constexpr uint32_t kVEvBuf = 64;    // events a warp collects in shared memory per 32 tiles before it asks for global slots
+
+struct VJob {
+    const uint32_t *planes;    // chunked [lo][hi][va] (planes_build.cuh)
+    const uint32_t *plainbits; // one bit per 32-base word
+    const SliceDesc *slices;
+    const VTile *vtiles;       // [n_vtiles] (slice, tile of the slice), slice by slice
+    uint64_t n_vtiles;
+    uint32_t kmin, kmax;
+    uint64_t *events;              // packed keys (pack_event)
+    unsigned long long *n_events;  // slots handed out
+    uint64_t cap_events;
+    uint32_t *work_counter;        // zero at launch
+    KeyFmt fmt;
+    ExItem *slow_items;            // tiles left to explore_planes_kernel
+    unsigned long long *n_slow;
+};
+
+// The tile list (base = prefix sums of vt_count over the slices): a thread writes the tiles of its slice when they are
+// few (reads), the warp writes them together when they are many (chromosome ends).  (A binary search per tile cost
+// 33 us on two million tiles; the same search inside the scan, 18 dependent loads per item, cost more than that in
+// exposed latency; one warp per slice 21 us.)
+__global__ void __launch_bounds__(256) vt_items_kernel(const uint64_t *base /* [n_slices + 1] */, uint32_t n_slices, VTile *out) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    uint64_t b = 0, n = 0;
+    if (s < n_slices) {
+        b = base[s];
+        n = base[s + 1] - b;
+    }
+    const bool big = n > 32;
+    if (!big)
+        for (uint32_t t = 0; t < (uint32_t)n; t++) out[b + t] = VTile{s, t};
+    uint32_t todo = __ballot_sync(0xFFFFFFFFu, big);
+    while (todo) {
+        const int src = __ffs((int)todo) - 1;
+        todo &= todo - 1;
+        const uint64_t bb = __shfl_sync(0xFFFFFFFFu, b, src), nn = __shfl_sync(0xFFFFFFFFu, n, src);
+        const uint32_t ss = __shfl_sync(0xFFFFFFFFu, s, src);
+        for (uint64_t t = (uint32_t)lane; t < nn; t += 32) out[bb + t] = VTile{ss, (uint32_t)t};
+    }
+}
+
+// Shared memory of a CTA (dynamic): per warp two staging buffers (the horizontal words of 32 tiles: 33 words x 2 planes
+// each; the buffer of the tile in work becomes the E stash once its words are in registers, the other one receives
+// the next tiles' words by cp.async meanwhile) and the event buffer; one chunk-end mask table.
+constexpr uint32_t kVStageWords = 2 * 32 * 33;
+struct __align__(16) VWarpShared {
+    uint32_t stage[2][kVStageWords];
+    unsigned long long ev[kVEvBuf];
+};
+struct __align__(16) VShared {
+    VWarpShared w[kVWarps];
+    uint32_t mask[kVMaskWords];
+};
+
+// the chunk-end mask table (explore_vertical_core.hpp), built at compile time; every CTA copies it into shared memory
+struct VtMaskTable {
+    uint32_t w[kVMaskWords];
+    constexpr VtMaskTable() : w{} {
+        for (int k = 1; k <= kVMaxK; k++)
+            for (int x = 0; x < k + 32; x++) {
+                uint32_t m = 0;
+                for (int b = 0; b < 32; b++)
+                    if ((x + 32 * b + 1) % k == 0) m |= 1u << b;
+                w[vt_mask_row(k) + x] = m;
+            }
+    }
+};
+__constant__ VtMaskTable c_vt_mask = VtMaskTable();
+
+// chunk-end masks of a k that divides the tile step (960 = 2^6 * 3 * 5: k = 5, 6, 8, 10, 12, ...): every tile of a slice
+// starts at chunk phase 0, the 32 mask words are compile-time constants and end up as LOP3 immediates
+template <int K>
+struct VtMaskConst {
+    uint32_t w[32];
+    constexpr VtMaskConst() : w{} {
+        for (int i = 0; i < 32; i++) {
+            uint32_t x = 0;
+            for (int b = 0; b < 32; b++)
+                if ((i + 32 * b + 1) % K == 0) x |= 1u << b;
+            w[i] = x;
+        }
+    }
+};
+
+// one k of one tile: E words into the lane's stash column (uint4 [8][32] over the staging area), OR of them back
+template <int K>
+__device__ __forceinline__ uint32_t vt_run_k(const uint32_t (&lo)[32], const uint32_t (&hi)[32], const uint32_t *mask_tab, uint32_t t, uint4 *stash_lane) {
+    uint32_t eb[32];
+    auto out = [&](int i, uint32_t e) {
+        eb[i] = e;
+        if (vt_group_done<K>(i)) stash_lane[(i >> 2) * 32] = make_uint4(eb[i & ~3], eb[(i & ~3) + 1], eb[(i & ~3) + 2], eb[(i & ~3) + 3]);
+    };
+    if constexpr (kVStep % K == 0) {
+        constexpr VtMaskConst<K> mc{};
+        return vt_compute<K>(lo, hi, [&](int i) { return mc.w[i]; }, out);
+    } else {
+        const uint32_t *mrow = mask_tab + vt_mask_row(K) + ((t % K) * (kVStep % K)) % K; // phase = (960 t) mod K
+        return vt_compute<K>(lo, hi, [&](int i) { return mrow[i]; }, out);
+    }
+}
+
+// event number `pos` of the warp's current item: into the warp's buffer, or, in a burst (tiles full of short repeats),
+// straight to the global buffer
+__device__ __forceinline__ void vt_put(const VJob &job, unsigned long long *evbuf, uint32_t pos, uint64_t key) {
+    if (pos < kVEvBuf) {
+        evbuf[pos] = key;
+    } else {
+        const unsigned long long idx = atomicAdd(job.n_events, 1ull);
+        if (idx < job.cap_events) job.events[idx] = key;
+    }
+}
+
+struct VDesc { // one lane's tile
+    VTile d;
+    SliceDesc sd;
+    bool valid;
+};
+__device__ __forceinline__ VDesc vt_desc(const VJob &job, uint64_t item, int lane) {
+    VDesc r;
+    const uint64_t v = item * 32 + (uint32_t)lane;
+    r.valid = v < job.n_vtiles;
+    r.d = VTile{0u, 0u};
+    r.sd = SliceDesc{0ull, 0ull};
+    if (r.valid) {
+        r.d = job.vtiles[v];
+        r.sd = job.slices[r.d.slice];
+    }
+    return r;
+}
+
+// the 32 x 33 words of each plane that the warp's tiles start in, row by row (a tile's words are consecutive in the
+// plane: coalesced), straight into shared memory; wa = this lane's first word
+__device__ __forceinline__ void vt_stage_async(const uint32_t *planes, uint32_t wa, uint32_t *stage, int lane) {
+    const uint32_t s_lo = (uint32_t)__cvta_generic_to_shared(stage), s_hi = s_lo + 32 * 33 * 4;
+#pragma unroll 8
+    for (int L = 0; L < 32; L++) {
+        const uint32_t wl = __shfl_sync(0xFFFFFFFFu, wa, L);
+        const uint32_t *p = plane_word_ptr(planes, (uint64_t)wl + (uint32_t)lane);
+        const uint32_t off = (uint32_t)(L * 33 + lane) * 4u;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_lo + off), "l"(p) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_hi + off), "l"(p + kPackWords) : "memory");
+    }
+    const uint32_t *p = plane_word_ptr(planes, (uint64_t)wa + 32u);
+    const uint32_t off = (uint32_t)(lane * 33 + 32) * 4u;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_lo + off), "l"(p) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_hi + off), "l"(p + kPackWords) : "memory");
+}
+
+// KMIN > 0: the k range is a compile-time constant; KMIN == 0: run-time range (job.kmin .. job.kmax, <= kVMaxK).
+#ifndef TIDK_V_MINB
+#define TIDK_V_MINB 3
+#endif
+template <int KMIN, int KMAX>
+__global__ void __launch_bounds__(kVWarps * 32, TIDK_V_MINB) explore_vertical_kernel(const VJob job) {
+    extern __shared__ __align__(16) unsigned char vt_smem[];
+    VShared &sh = *reinterpret_cast<VShared *>(vt_smem);
+    for (uint32_t e = threadIdx.x; e < kVMaskWords; e += blockDim.x) sh.mask[e] = c_vt_mask.w[e];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    VWarpShared &ws = sh.w[wid];
+    unsigned long long *const evbuf = ws.ev;
+    const uint32_t k0 = KMIN > 0 ? KMIN : job.kmin, k1 = KMIN > 0 ? KMAX : job.kmax;
+
+    // Items (32 tiles each): the first two of a warp are assigned statically, the rest come from one ticket counter,
+    // drawn two items ahead.  The words of item n + 1 are on their way into the other staging buffer while item n is
+    // in work; its descriptors are fetched as soon as its ticket has arrived.  (One CTA of twelve warps per SM whose
+    // warps enter the code of every k together, behind a barrier, was measured: 0.77 against 0.68 ms.)
+    const uint64_t n_items = (job.n_vtiles + 31) >> 5;
+    const uint64_t n_warps = (uint64_t)gridDim.x * kVWarps;
+    uint64_t item = (uint64_t)blockIdx.x * kVWarps + wid, item_next = item + n_warps;
+    VDesc cur = vt_desc(job, item, lane);
+    if (item < n_items) vt_stage_async(job.planes, (uint32_t)((cur.sd.beg + (uint64_t)kVStep * cur.d.t) >> 5), ws.stage[0], lane);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    VDesc nxt = vt_desc(job, item_next < n_items ? item_next : n_items, lane);
+    uint32_t buf = 0;
+    while (item < n_items) {
+        uint32_t ticket = 0;
+        if (lane == 0) asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(ticket) : "l"(job.work_counter) : "memory");
+        uint32_t *const stage = ws.stage[buf];
+        uint4 *const stash_lane = reinterpret_cast<uint4 *>(stage) + lane;
+        if (item_next < n_items) vt_stage_async(job.planes, (uint32_t)((nxt.sd.beg + (uint64_t)kVStep * nxt.d.t) >> 5), ws.stage[buf ^ 1], lane);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+
+        const VTile d = cur.d;
+        const SliceDesc sd = cur.sd;
+        const bool valid = cur.valid;
+        const uint64_t rel0 = (uint64_t)kVStep * d.t, a0 = sd.beg + rel0, m = sd.len;
+        const bool first = d.t == 0, last = (uint64_t)d.t + 1 == vt_count(m);
+        const uint32_t wa = (uint32_t)(a0 >> 5), sft = (uint32_t)a0 & 31u; // (the host checks that word indices fit 32 bits)
+        // every word of the tile that holds a base of the slice must be plain
+        bool plain;
+        {
+            const uint64_t end = a0 + kVTile < sd.beg + m ? a0 + kVTile : sd.beg + m; // exclusive, > a0 for a valid tile
+            const uint32_t nw = valid ? (uint32_t)((end - 1) >> 5) - wa + 1u : 0u;    // 1 .. 33
+            const uint32_t *pb = job.plainbits + (wa >> 5);
+            const uint32_t p0 = __ldg(pb), p1 = __ldg(pb + 1), p2 = __ldg(pb + 2);
+            const uint32_t x = __funnelshift_r(p0, p1, wa & 31u), y = __funnelshift_r(p1, p2, wa & 31u);
+            const uint32_t need = nw >= 32u ? 0xFFFFFFFFu : (1u << nw) - 1u;
+            plain = (x & need) == need && (nw < 33u || (y & 1u));
+        }
+        // this item's words have arrived (all but the group just committed are complete); each lane takes its own
+        // 33 + 33, shifted to the tile's first base
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
+        uint32_t lo[32], hi[32];
+        {
+            const uint32_t *sl = stage + lane * 33, *sh2 = stage + 32 * 33 + lane * 33;
+            uint32_t pl = sl[0], ph = sh2[0];
+#pragma unroll
+            for (int b = 0; b < 32; b++) {
+                const uint32_t nl = sl[b + 1], nh = sh2[b + 1];
+                lo[b] = __funnelshift_r(pl, nl, sft);
+                hi[b] = __funnelshift_r(ph, nh, sft);
+                pl = nl; ph = nh;
+            }
+        }
+        __syncwarp(); // the staging buffer becomes the stash
+        const uint32_t h0 = lo[0] | hi[0];
+        vt_transpose32(lo);
+        vt_transpose32(hi);
+        // the item after next: its ticket has had time to arrive; fetch its descriptors now, use them at the end
+        const uint64_t item_after = 2 * n_warps + __shfl_sync(0xFFFFFFFFu, ticket, 0);
+        const VDesc aft = vt_desc(job, item_after < n_items ? item_after : n_items, lane);
+
+        const bool scan = valid && plain;
+        if (valid && !plain) { // left to the general kernel, as an ordinary item that owns the same chunk ends
+            const unsigned long long idx = atomicAdd(job.n_slow, 1ull);
+            job.slow_items[idx] = make_ex_item(sd, d.slice, first ? 0ull : rel0 + kVHalo, last ? m + k1 : rel0 + kVTile);
+        }
+        // tile-relative bounds: the tile owns the chunk ends in [own_lo, own_hi); the closing parity counts [par_lo, m_t)
+        const uint32_t m_t = m - rel0 < (uint64_t)kVTile ? (uint32_t)(m - rel0) : kVTile;
+        const uint32_t own_hi = last ? m_t : kVTile;
+        uint32_t evcount = 0; // events of this item so far (warp-uniform)
+        for (uint32_t k = k0; k <= k1; k++) {
+            uint32_t any = 0;
+            switch (k) {
+#define TIDK_VK(K)                                                                                          \
+    case K:                                                                                                 \
+        if constexpr (KMIN == 0 || (K >= KMIN && K <= KMAX)) any = vt_run_k<K>(lo, hi, sh.mask, d.t, stash_lane); \
+        break;
+                TIDK_VK(1) TIDK_VK(2) TIDK_VK(3) TIDK_VK(4) TIDK_VK(5) TIDK_VK(6) TIDK_VK(7) TIDK_VK(8)
+                TIDK_VK(9) TIDK_VK(10) TIDK_VK(11) TIDK_VK(12) TIDK_VK(13) TIDK_VK(14) TIDK_VK(15) TIDK_VK(16)
+#undef TIDK_VK
+            default: break;
+            }
+            // Run boundaries of this k (vt_emit, explore_vertical_core.hpp).  Few lanes have any, and those that do
+            // have one or two: the lanes step through "my next non-zero E word" / "its next bit" TOGETHER (ballots
+            // decide when to stop), so the warp pays for the busiest lane instead of for the sum over all lanes, and
+            // event slots come from a ballot, not from an atomic per event.
+            const uint32_t iflip = 2u * k - 1u; // (< 32: k <= 16)
+            const bool flip = first && vt_head_flip(h0, k);
+            const bool mine = scan && (any != 0u || flip);
+            if (!__any_sync(0xFFFFFFFFu, mine)) continue;
+            const uint32_t fg = iflip >> 2, fc = iflip & 3u;
+            uint32_t gm = 0; // groups of four E words with a bit in them
+            if (mine) {
+#pragma unroll
+                for (uint32_t g = 0; g < 8; g++) {
+                    const uint4 e4 = stash_lane[g * 32];
+                    if ((e4.x | e4.y | e4.z | e4.w) != 0u) gm |= 1u << g;
+                }
+                if (flip) gm |= 1u << fg;
+            }
+            const uint32_t par_lo = first ? iflip : 0u, own_lo = first ? iflip : kVHalo;
+            uint32_t parity = 0, pend = 0, pi = 0, cw = 0, cg = 0;
+            uint4 e4 = make_uint4(0u, 0u, 0u, 0u);
+            for (;;) {
+                while (pend == 0u && (cw | gm) != 0u) { // next non-zero word of this lane (a group can turn out empty: the head flip)
+                    if (cw == 0u) {
+                        cg = (uint32_t)__ffs((int)gm) - 1u;
+                        gm &= gm - 1u;
+                        e4 = stash_lane[cg * 32];
+                        if (flip && cg == fg) {
+                            if (fc == 0u) e4.x ^= 1u; else if (fc == 1u) e4.y ^= 1u; else if (fc == 2u) e4.z ^= 1u; else e4.w ^= 1u;
+                        }
+                        cw = (e4.x != 0u ? 1u : 0u) | (e4.y != 0u ? 2u : 0u) | (e4.z != 0u ? 4u : 0u) | (e4.w != 0u ? 8u : 0u);
+                    }
+                    if (cw != 0u) {
+                        const uint32_t c = (uint32_t)__ffs((int)cw) - 1u;
+                        cw &= cw - 1u;
+                        pend = c == 0u ? e4.x : c == 1u ? e4.y : c == 2u ? e4.z : e4.w;
+                        pi = 4u * cg + c;
+                    }
+                }
+                if (!__any_sync(0xFFFFFFFFu, pend != 0u)) break;
+                bool has_ev = false;
+                uint64_t key = 0;
+                if (pend != 0u) {
+                    const uint32_t b = (uint32_t)__ffs((int)pend) - 1u;
+                    pend &= pend - 1u;
+                    const uint32_t q = 32u * b + pi; // tile position
+                    if (q >= par_lo && q < m_t) parity ^= 1u;
+                    if (q >= own_lo && q < own_hi) {
+                        const uint64_t q1 = rel0 + q + 1; // slice position + 1: a multiple of k
+                        const uint64_t j = (q1 >> 32 ? q1 / k : (uint64_t)div_exact((uint32_t)q1, k)) - 2;
+                        key = pack_event(job.fmt, d.slice, k, j, 0u, 0u);
+                        has_ev = true;
+                    }
+                }
+                const uint32_t em = __ballot_sync(0xFFFFFFFFu, has_ev);
+                if (has_ev) vt_put(job, evbuf, evcount + (uint32_t)__popc(em & ((1u << lane) - 1u)), key);
+                evcount += (uint32_t)__popc(em);
+            }
+            { // the run that touches the end of the slice
+                const bool closer = mine && last && parity != 0u;
+                const uint32_t em = __ballot_sync(0xFFFFFFFFu, closer);
+                if (closer) vt_put(job, evbuf, evcount + (uint32_t)__popc(em & ((1u << lane) - 1u)), pack_event(job.fmt, d.slice, k, m / k - 1, 0u, 0u));
+                evcount += (uint32_t)__popc(em);
+            }
+            __syncwarp();
+        }
+        // the warp's events of these 32 tiles: one range of global slots
+        __syncwarp();
+        {
+            const uint32_t n = min(evcount, kVEvBuf);
+            if (n) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(job.n_events, (unsigned long long)n);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                for (uint32_t e = (uint32_t)lane; e < n; e += 32)
+                    if (base + e < job.cap_events) job.events[base + e] = evbuf[e];
+            }
+        }
+        __syncwarp();
+        item = item_next;
+        item_next = item_after;
+        cur = nxt;
+        nxt = aft;
+        buf ^= 1;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+} // namespace tidk

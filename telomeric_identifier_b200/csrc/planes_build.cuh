@@ -26,7 +26,8 @@ struct PlaneBuildJob {
     uint32_t *plainbits;  // [n_blocks + 1]
     uint32_t *validbits;  // [n_blocks + 1]
     uint64_t n_blocks;    // 1 KiB blocks to convert (covers the data and the padded tail)
-    uint32_t *err_flags;  // device word: bit 0 set when a byte >= 0x80 is seen
+    uint64_t total;       // bases in the batch: the word that holds the last base counts as plain when its bases are
+    uint32_t *err_flags;  // device word: bit 0 set when a byte >= 0x80 is seen, bit 1 when a word that holds a base is not plain
 };
 
 __device__ __forceinline__ uint32_t *plane_word_ptr(uint32_t *planes, uint64_t word) {
@@ -44,6 +45,8 @@ __global__ void __launch_bounds__(256, 4) planes_build_kernel(const PlaneBuildJo
         return;
     }
     uint32_t nonascii = 0;
+    bool other = false; // a word of the data (not of the padding) that is not plain
+    const uint64_t n_words = (job.total + 31) >> 5;
     uint32_t w[8];
     ld256_stream(job.seq + (blk << 10) + (uint32_t)lane * 32u, w);
     for (;;) {
@@ -58,7 +61,13 @@ __global__ void __launch_bounds__(256, 4) planes_build_kernel(const PlaneBuildJo
         const uint32_t va = (P.b0 ^ (P.hi & ~P.lo)) & P.ok;
         const uint32_t any_l = nib.Y[0] | nib.Y[1] | nib.Y[2] | nib.Y[3]; // ASCII bit 5 = bit 1 of the high nibbles
         const bool valid = va == 0xFFFFFFFFu;
-        const bool plain = valid && (any_l & 0x22222222u) == 0u;
+        bool plain = valid && (any_l & 0x22222222u) == 0u;
+        if (blk == (job.total >> 10) && (job.total & 31u) != 0u && (uint32_t)lane == ((uint32_t)(job.total >> 5) & 31u)) {
+            // the last, partial word of the batch: only its bases count (what follows is padding, never inside a slice)
+            const uint32_t tail = (1u << (job.total & 31u)) - 1u;
+            plain = (va & tail) == tail && (nibble_plane<1>(nib.Y) & tail) == 0u;
+        }
+        other |= !plain && (blk << 5) + (uint32_t)lane < n_words;
         uint32_t *p = plane_word_ptr(job.planes, (blk << 5) + (uint32_t)lane);
         p[0] = P.lo;
         p[kPackWords] = P.hi;
@@ -71,7 +80,8 @@ __global__ void __launch_bounds__(256, 4) planes_build_kernel(const PlaneBuildJo
         if (nxt >= job.n_blocks) break;
         blk = nxt;
     }
-    if (__any_sync(0xFFFFFFFFu, nonascii != 0) && lane == 0) atomicOr(job.err_flags, 1u);
+    const uint32_t flags = (__any_sync(0xFFFFFFFFu, nonascii != 0) ? 1u : 0u) | (__any_sync(0xFFFFFFFFu, other) ? 2u : 0u);
+    if (flags && lane == 0) atomicOr(job.err_flags, flags);
 }
 
 } // namespace tidk

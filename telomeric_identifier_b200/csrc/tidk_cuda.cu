@@ -50,7 +50,11 @@ struct tidk_seqbuf {
     size_t planes_cap = 0, bits_cap = 0;
     bool planes_ready = false;
     bool planes_nonascii = false; // the conversion saw a byte >= 0x80
+    bool planes_all_plain = false; // every word that holds a base is 32 (or, the last one, fewer) upper-case A C G T
     float planes_ms = 0.f;        // device time of the conversion
+    // a batch of a multi-device context (multi_device.cuh): one part per device, records [cut[g], cut[g + 1]) in part g
+    std::vector<tidk_seqbuf *> parts;
+    std::vector<uint32_t> cut;
 };
 
 // Packer threads of the host-packed upload, kept parked between calls: creating and joining 15 threads per call
@@ -349,7 +353,7 @@ int seqbuf_build_planes(tidk_ctx *ctx, tidk_seqbuf *b) {
     // (the plain / valid words behind the last converted block are read by the scans' look-ahead: zero)
     CU(ctx, cudaMemsetAsync(b->d_plainbits + n_blocks, 0, 8, ctx->stream));
     CU(ctx, cudaMemsetAsync(b->d_validbits + n_blocks, 0, 8, ctx->stream));
-    PlaneBuildJob job{b->d_seq, b->d_planes, b->d_plainbits, b->d_validbits, n_blocks, ctx->d_flags + 1};
+    PlaneBuildJob job{b->d_seq, b->d_planes, b->d_plainbits, b->d_validbits, n_blocks, b->total, ctx->d_flags + 1};
     const uint64_t want = (n_blocks + 7) / 8, cap = (uint64_t)ctx->sm_count * 8;
     CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     planes_build_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, ctx->stream>>>(job);
@@ -358,6 +362,7 @@ int seqbuf_build_planes(tidk_ctx *ctx, tidk_seqbuf *b) {
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     CU(ctx, cudaEventElapsedTime(&b->planes_ms, ctx->ev0, ctx->ev1));
     b->planes_nonascii = (ctx->h_flags[1] & 1u) != 0;
+    b->planes_all_plain = (ctx->h_flags[1] & 2u) == 0;
     ctx->h_flags[1] = 0;
     b->planes_ready = true;
     return TIDK_OK;
@@ -513,6 +518,8 @@ void revcomp_host(const uint8_t *f, uint32_t L, uint8_t *out) {
 
 } // namespace
 
+#include "multi_device.cuh"
+
 extern "C" {
 
 uint32_t tidk_cuda_abi_version(void) { return 1; }
@@ -520,8 +527,27 @@ uint32_t tidk_cuda_abi_version(void) { return 1; }
 int tidk_cuda_create(const int *device_ids, int n_devices, tidk_ctx **out) {
     if (!out) return fail(nullptr, TIDK_EARG, "out is NULL");
     *out = nullptr;
-    if (n_devices < 0 || n_devices > 1)
-        return fail(nullptr, TIDK_EARG, "one device per ctx (got %d); run one process per GPU", n_devices);
+    if (n_devices < 0 || n_devices > 64) return fail(nullptr, TIDK_EARG, "0 .. 64 devices per ctx (got %d)", n_devices);
+    if (n_devices > 1) { // one single-device context per listed device (multi_device.cuh)
+        if (!device_ids) return fail(nullptr, TIDK_EARG, "device_ids is NULL with %d devices", n_devices);
+        tidk_ctx *top = new (std::nothrow) tidk_ctx();
+        if (!top) return fail(nullptr, TIDK_ENOMEM, "out of host memory");
+        top->device = device_ids[0];
+        for (int g = 0; g < n_devices; g++) {
+            tidk_ctx *sub = nullptr;
+            const int rc = tidk_cuda_create(device_ids + g, 1, &sub);
+            if (rc) {
+                for (tidk_ctx *s2 : top->subs) tidk_cuda_destroy(s2);
+                delete top;
+                return rc;
+            }
+            top->subs.push_back(sub);
+        }
+        // the devices of one context share the host's cores (packer threads per single-device context)
+        setenv("LOCAL_WORLD_SIZE", std::to_string(n_devices).c_str(), 0);
+        *out = top;
+        return TIDK_OK;
+    }
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0)
@@ -545,6 +571,11 @@ int tidk_cuda_create(const int *device_ids, int n_devices, tidk_ctx **out) {
 
 void tidk_cuda_destroy(tidk_ctx *ctx) {
     if (!ctx) return;
+    if (!ctx->subs.empty()) {
+        for (tidk_ctx *sub : ctx->subs) tidk_cuda_destroy(sub);
+        delete ctx;
+        return;
+    }
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     seqbuf_release(&ctx->scratch);
@@ -581,7 +612,7 @@ void *tidk_cuda_host_alloc(tidk_ctx *ctx, size_t bytes) {
     if (!ctx) return nullptr;
     cudaSetDevice(ctx->device);
     void *p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { // (portable: every device of a multi-device context copies from it)
         fail(ctx, TIDK_ENOMEM, "cudaHostAlloc(%zu) failed", bytes);
         return nullptr;
     }
@@ -597,6 +628,7 @@ void tidk_cuda_host_free(tidk_ctx *ctx, void *p) {
 int tidk_cuda_seqbuf_upload(tidk_ctx *ctx, const uint8_t *seq, const uint64_t *offsets,
                             uint32_t n_records, tidk_seqbuf **out) {
     if (!ctx) return TIDK_EARG;
+    if (!ctx->subs.empty()) return multi::seqbuf_upload(ctx, seq, offsets, n_records, out);
     if (!out) return fail(ctx, TIDK_EARG, "out is NULL");
     *out = nullptr;
     CU(ctx, cudaSetDevice(ctx->device));
@@ -608,7 +640,7 @@ int tidk_cuda_seqbuf_upload(tidk_ctx *ctx, const uint8_t *seq, const uint64_t *o
         if (e != cudaSuccess) rc = fail(ctx, TIDK_ECUDA, "upload failed: %s", cudaGetErrorString(e));
     }
     // a batch that stays resident is transposed once (K1): every later pass reads the planes
-    static const bool planes_on = !(getenv("TIDK_PLANES") && atoi(getenv("TIDK_PLANES")) == 0);
+    const bool planes_on = !(getenv("TIDK_PLANES") && atoi(getenv("TIDK_PLANES")) == 0); // (read per call: measurements switch)
     if (rc == TIDK_OK && planes_on && b->total > 0) rc = seqbuf_build_planes(ctx, b);
     if (rc != TIDK_OK) { seqbuf_release(b); delete b; return rc; }
     *out = b;
@@ -617,6 +649,10 @@ int tidk_cuda_seqbuf_upload(tidk_ctx *ctx, const uint8_t *seq, const uint64_t *o
 
 void tidk_cuda_seqbuf_free(tidk_ctx *ctx, tidk_seqbuf *buf) {
     if (!buf) return;
+    if (!buf->parts.empty()) {
+        if (ctx) multi::seqbuf_free(ctx, buf);
+        return;
+    }
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
     seqbuf_release(buf);
     delete buf;
@@ -943,7 +979,7 @@ static bool queries_packable(const char *const *queries, const uint32_t *qlens, 
 static const uint32_t *resident_planes(tidk_ctx *ctx, const tidk_seqbuf *buf, const char *const *queries, const uint32_t *qlens,
                                        uint32_t nq, int *rc) {
     *rc = TIDK_OK;
-    static const bool on = !(getenv("TIDK_PLANES_COUNT") && atoi(getenv("TIDK_PLANES_COUNT")) == 0);
+    const bool on = !(getenv("TIDK_PLANES_COUNT") && atoi(getenv("TIDK_PLANES_COUNT")) == 0); // (read per call: measurements switch)
     if (!on || !buf || !buf->planes_ready || !queries_packable(queries, qlens, nq)) return nullptr;
     if (buf->planes_nonascii)
         *rc = fail(ctx, TIDK_ENONASCII, "sequence contains a byte >= 0x80 (the reference fails in str::from_utf8, search.rs:107)");
@@ -955,6 +991,7 @@ int tidk_cuda_window_counts_resident(tidk_ctx *ctx, const tidk_seqbuf *buf, uint
                                      uint32_t nq, uint64_t *out_fwd, uint64_t *out_rev,
                                      float *kernel_ms, uint32_t *kernel_launches) {
     if (!ctx) return TIDK_EARG;
+    if (!ctx->subs.empty()) return multi::window_counts_resident(ctx, buf, window, queries, qlens, nq, out_fwd, out_rev, kernel_ms, kernel_launches, false);
     int rc;
     const uint32_t *planes = resident_planes(ctx, buf, queries, qlens, nq, &rc);
     if (rc) return rc;
@@ -966,6 +1003,7 @@ int tidk_cuda_window_counts_resident_async(tidk_ctx *ctx, const tidk_seqbuf *buf
                                            const char *const *queries, const uint32_t *qlens,
                                            uint32_t nq, uint64_t *out_fwd, uint64_t *out_rev) {
     if (!ctx) return TIDK_EARG;
+    if (!ctx->subs.empty()) return multi::window_counts_resident(ctx, buf, window, queries, qlens, nq, out_fwd, out_rev, nullptr, nullptr, true);
     int rc;
     const uint32_t *planes = resident_planes(ctx, buf, queries, qlens, nq, &rc);
     if (rc) return rc;
@@ -974,6 +1012,7 @@ int tidk_cuda_window_counts_resident_async(tidk_ctx *ctx, const tidk_seqbuf *buf
 
 int tidk_cuda_wait(tidk_ctx *ctx, float *kernel_ms, uint32_t *kernel_launches) {
     if (!ctx) return TIDK_EARG;
+    if (!ctx->subs.empty()) return multi::wait(ctx, kernel_ms, kernel_launches);
     if (kernel_ms) *kernel_ms = 0.f;
     if (kernel_launches) *kernel_launches = 0;
     CU(ctx, cudaSetDevice(ctx->device));
@@ -1262,6 +1301,7 @@ int tidk_cuda_window_counts(tidk_ctx *ctx, const uint8_t *seq, const uint64_t *o
                             const uint32_t *qlens, uint32_t nq, uint64_t *out_fwd,
                             uint64_t *out_rev) {
     if (!ctx) return TIDK_EARG;
+    if (!ctx->subs.empty()) return multi::window_counts(ctx, seq, offsets, n_records, window, queries, qlens, nq, out_fwd, out_rev);
     if (window == 0) return fail(ctx, TIDK_EARG, "window must be > 0 (slice::chunks(0) panics, search.rs:98)");
     CU(ctx, cudaSetDevice(ctx->device));
     // host-packed path: worth it when there are enough cores to pack faster than PCIe moves ASCII,
@@ -1274,7 +1314,15 @@ int tidk_cuda_window_counts(tidk_ctx *ctx, const uint8_t *seq, const uint64_t *o
     // not by the bus (8 ranks: 184 GB/s of plain DMA in aggregate), and packing -- which reads the sequence
     // and writes + re-reads the planes -- only adds to that: measured 180 vs 184 Gbases/s on 8 GPUs.
     const char *eh = getenv("TIDK_HYBRID_UPLOAD");
-    const bool hybrid = window <= kSegBytes && (eh ? atoi(eh) != 0 : true); // windows of one 32 KiB item can be split between the sources
+    // the DMA front of the two-ended upload reads the caller's buffer directly: it has to be pinned (from pageable
+    // memory each 4 MiB copy would be staged synchronously on the packer thread that issues it)
+    bool pageable = true;
+    {
+        cudaPointerAttributes a{};
+        if (seq && cudaPointerGetAttributes(&a, seq) == cudaSuccess) pageable = a.type == cudaMemoryTypeUnregistered;
+        (void)cudaGetLastError();
+    }
+    const bool hybrid = !pageable && window <= kSegBytes && (eh ? atoi(eh) != 0 : true); // windows of one 32 KiB item can be split between the sources
     const bool packable = total >= (32u << 20) && seq && (env ? atoi(env) != 0 : T >= 12) && T >= 1 && queries_packable(queries, qlens, nq);
     uint64_t n_out = 0;
     for (uint32_t r = 0; r < n_records && offsets; r++) {
@@ -1303,6 +1351,7 @@ int tidk_cuda_explore_runs_resident(tidk_ctx *ctx, const tidk_seqbuf *buf, doubl
                                     tidk_run **out_runs, uint64_t *n_runs, float *kernel_ms,
                                     uint32_t *kernel_launches) {
     if (!ctx) return TIDK_EARG;
+    if (!ctx->subs.empty()) return multi::explore_runs_resident(ctx, buf, distance, kmin, kmax, threshold, out_runs, n_runs, kernel_ms, kernel_launches);
     if (kernel_ms) *kernel_ms = 0.f;
     if (kernel_launches) *kernel_launches = 0;
     if (!buf || !out_runs || !n_runs) return fail(ctx, TIDK_EARG, "NULL argument");
@@ -1316,7 +1365,8 @@ int tidk_cuda_explore_runs_resident(tidk_ctx *ctx, const tidk_seqbuf *buf, doubl
                                  buf->d_off, buf->h_off.data(), buf->n_records, distance, kmin, kmax,
                                  threshold, out_runs, n_runs, kernel_ms, kernel_launches, err,
                                  &ctx->explore_scan_ms, &ctx->explore_post_ms, ctx->explore_host_ms, nullptr,
-                                 buf->planes_ready ? buf->d_planes : nullptr, buf->planes_ready ? buf->d_plainbits : nullptr);
+                                 buf->planes_ready ? buf->d_planes : nullptr, buf->planes_ready ? buf->d_plainbits : nullptr,
+                                 buf->planes_ready && buf->planes_all_plain);
     if (rc) return fail(ctx, rc, "%s", err.c_str());
     return TIDK_OK;
 }
@@ -1325,6 +1375,7 @@ int tidk_cuda_explore_runs(tidk_ctx *ctx, const uint8_t *seq, const uint64_t *of
                            uint32_t n_records, double distance, uint32_t kmin, uint32_t kmax,
                            uint64_t threshold, tidk_run **out_runs, uint64_t *n_runs) {
     if (!ctx) return TIDK_EARG;
+    if (!ctx->subs.empty()) return multi::explore_runs(ctx, seq, offsets, n_records, distance, kmin, kmax, threshold, out_runs, n_runs);
     CU(ctx, cudaSetDevice(ctx->device));
     // Compacted upload: with --distance 0.01 only 2 % of a genome is ever looked at, so only the slices
     // cross the bus (C3: 10 MB instead of 500 MB), laid out back to back with room for the block
@@ -1412,6 +1463,21 @@ void tidk_cuda_free_runs(tidk_run *runs) {
 
 int tidk_cuda_seqbuf_planes_info(const tidk_seqbuf *buf, int *ready, float *build_ms, uint64_t *bytes) {
     if (!buf) return TIDK_EARG;
+    if (!buf->parts.empty()) { // multi-device batch: ready on every part, the slowest conversion, the sum of the bytes
+        int all = 1;
+        float mx = 0.f;
+        uint64_t sum = 0;
+        for (size_t g = 0; g < buf->parts.size(); g++) {
+            if (buf->cut[g + 1] <= buf->cut[g] || !buf->parts[g]) continue;
+            int r = 0; float ms = 0.f; uint64_t by = 0;
+            tidk_cuda_seqbuf_planes_info(buf->parts[g], &r, &ms, &by);
+            all &= r; mx = ms > mx ? ms : mx; sum += by;
+        }
+        if (ready) *ready = all;
+        if (build_ms) *build_ms = mx;
+        if (bytes) *bytes = sum;
+        return TIDK_OK;
+    }
     if (ready) *ready = buf->planes_ready ? 1 : 0;
     if (build_ms) *build_ms = buf->planes_ready ? buf->planes_ms : 0.f;
     if (bytes) *bytes = buf->planes_ready ? (uint64_t)buf->planes_cap + 2 * (uint64_t)buf->bits_cap : 0;
@@ -1420,6 +1486,15 @@ int tidk_cuda_seqbuf_planes_info(const tidk_seqbuf *buf, int *ready, float *buil
 
 int tidk_cuda_last_transfer(const tidk_ctx *ctx, uint64_t *h2d_bytes, uint64_t *d2h_bytes, int *host_packed) {
     if (!ctx) return TIDK_EARG;
+    if (!ctx->subs.empty()) { // the sum over the devices
+        uint64_t h = 0, d = 0;
+        int pk = 0;
+        for (const tidk_ctx *sub : ctx->subs) { h += sub->last_h2d; d += sub->last_d2h; pk |= sub->last_packed; }
+        if (h2d_bytes) *h2d_bytes = h;
+        if (d2h_bytes) *d2h_bytes = d;
+        if (host_packed) *host_packed = pk;
+        return TIDK_OK;
+    }
     if (h2d_bytes) *h2d_bytes = ctx->last_h2d;
     if (d2h_bytes) *d2h_bytes = ctx->last_d2h;
     if (host_packed) *host_packed = ctx->last_packed;

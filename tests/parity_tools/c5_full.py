@@ -23,6 +23,7 @@ from oracle import oracle as O
 N_READS = int(os.environ.get("TIDK_C5_READS", "2000000"))
 BATCH = int(os.environ.get("TIDK_C5_BATCH", "100000"))
 N_CHECK = int(os.environ.get("TIDK_C5_CHECK", "1500"))  # random reads per batch checked against the oracle
+CHECK_ALL = os.environ.get("TIDK_C5_CHECK_ALL", "0") == "1"  # every read of every batch against the oracle (all host threads)
 D, KMIN, KMAX, THR = 0.5, 5, 12, 100
 THREADS = os.cpu_count() or 1
 
@@ -71,6 +72,8 @@ def main():
     res = {"config": "C5: explore -m 5 -x 12 -t 100 --distance 0.5", "reads": N_READS, "batch_reads": BATCH,
            "batches": nb, "host_threads": THREADS}
     lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device="cuda")
+    import hashlib
+    sha_gpu, sha_ora = hashlib.sha256(), hashlib.sha256()
     per_k_labels = {k: [] for k in range(KMIN, KMAX + 1)}
     per_k_counts = {k: [] for k in range(KMIN, KMAX + 1)}
     tot = dict(bases=0, scanned=0, runs=0, e2e_s=0.0, scan_ms=0.0, post_ms=0.0, res_wall_s=0.0, checked_reads=0,
@@ -105,7 +108,7 @@ def main():
             assert (cnt > THR).all()
             # oracle on a subsample of reads (runs of a read do not depend on the other reads)
             t0 = time.perf_counter()
-            if b == 0 and os.environ.get("TIDK_C5_FULL_BATCH0", "1") == "1":
+            if CHECK_ALL or (b == 0 and os.environ.get("TIDK_C5_FULL_BATCH0", "1") == "1"):
                 pick = np.arange(n)
             else:
                 rng = synth._rng(5, 5000 + b)
@@ -123,6 +126,9 @@ def main():
             got["record"] = remap[got["record"]].astype(np.uint32)
             assert same_runs(got, want, ORACLE_FIELDS), f"batch {b}: runs of the checked reads differ from the oracle ({got.size} vs {want.size})"
             assert labels_of(sub_seq, sub_off, got) == labels_of(sub_seq, sub_off, want), f"batch {b}: run labels differ from the oracle"
+            for h, arr in ((sha_gpu, got), (sha_ora, want)):  # the run lists themselves, field by field, batch after batch
+                for f in ORACLE_FIELDS:
+                    h.update(np.ascontiguousarray(arr[f]).tobytes())
             tot["oracle_s"] += time.perf_counter() - t0
             tot["checked_reads"] += int(pick.size)
             tot["checked_runs"] += int(want.size)
@@ -157,13 +163,15 @@ def main():
         "scan_plus_post_gbases_per_s": tot["scanned"] / ((tot["scan_ms"] + tot["post_ms"]) * 1e-3) / 1e9,
         "resident_call_gbases_per_s": tot["scanned"] / tot["res_wall_s"] / 1e9,
         "parity": "host-pointer == resident run lists on every batch; oracle run lists identical on the checked reads",
+        "run_lists_sha256": {"gpu": sha_gpu.hexdigest(), "oracle": sha_ora.hexdigest(), "equal": sha_gpu.hexdigest() == sha_ora.hexdigest(),
+                             "of": "record, slice, k, first, start, end of every run of the checked reads, batch after batch"},
     })
     print(f"canonical_repeat_unit\tcount_repeat_runs_gt_{THR}")
     for k, c in table[:8]:
         print(f"{k.decode()}\t{c}")
     print(json.dumps(res))
     os.makedirs("gpurun_out", exist_ok=True)
-    with open("gpurun_out/c5_full.json", "w") as f:
+    with open(os.environ.get("TIDK_C5_OUT", "gpurun_out/c5_full.json"), "w") as f:
         json.dump(res, f, indent=1)
 
 

@@ -26,6 +26,20 @@ def _runs_equal(ctx, seq, off, d, kmin, kmax, thr):
     for f in ("record", "slice", "k", "first", "start", "end"):
         assert (got[f] == want[f]).all(), f
     assert run_labels(seq, off, d, got) == wlabels
+    # the same batch resident: bit-planes built at upload; once on the plane kernel (small batches stay there), once with
+    # the vertical scan forced (explore_vertical.cuh: plain tiles in vertical form, the rest handed to the plane kernel)
+    import os
+    batch = ctx.upload(np.ascontiguousarray(seq, dtype=np.uint8), np.ascontiguousarray(off, dtype=np.uint64))
+    try:
+        for min_tiles in ("1000000000", "0"):
+            os.environ["TIDK_VERTICAL_MIN_TILES"] = min_tiles
+            res = ctx.explore_runs_resident(batch, d, kmin, kmax, thr)
+            assert res.size == want.size, (min_tiles, res.size, want.size)
+            for f in ("record", "slice", "k", "first", "start", "end", "label_pos"):
+                assert (res[f] == got[f]).all(), (min_tiles, f)
+    finally:
+        os.environ.pop("TIDK_VERTICAL_MIN_TILES", None)
+        batch.free()
 
 
 def test_reference_golden_index_left(ctx):  # explore.rs:592-612
@@ -196,11 +210,16 @@ def test_host_and_device_run_building_agree(ctx):
         "ids, seq, off = synth.random_records(55, 5, 80000, b'ACGTacgtN', plant=b'TTAGGG')\n"
         "with T.Context(0) as ctx:\n"
         "    got = ctx.explore_runs(seq, off, 0.5, 2, 9, 1)\n"
+        "    b = ctx.upload(seq, off)\n"
+        "    res = ctx.explore_runs_resident(b, 0.5, 2, 9, 1)\n"
         "want, _ = O.explore_runs(seq, off, 0.5, 2, 9, 1, period_filter=False)\n"
-        "assert got.size == want.size and all((got[f] == want[f]).all() for f in ('record','slice','k','first','start','end'))\n"
+        "for g in (got, res):\n"
+        "    assert g.size == want.size and all((g[f] == want[f]).all() for f in ('record','slice','k','first','start','end'))\n"
         "print('ok', got.size)\n")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for env_extra in ({}, {"TIDK_EXPLORE_HOST_POST": "1"}):
+    # ... and (TIDK_EXPLORE_POST_MAX) the path of batches with more events than CUB's 32-bit counts take: packed keys,
+    # stitched on the host -- with the vertical scan forced, whose events carry no type bits
+    for env_extra in ({}, {"TIDK_EXPLORE_HOST_POST": "1"}, {"TIDK_EXPLORE_POST_MAX": "10", "TIDK_VERTICAL_MIN_TILES": "0"}):
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root,
                            env={**os.environ, **env_extra})
         assert r.returncode == 0 and r.stdout.startswith("ok"), r.stderr[-2000:]
@@ -350,3 +369,65 @@ def test_packed_upload_small_and_nonascii(ctx, monkeypatch):
     with pytest.raises(T.TidkCudaError) as e:
         ctx.explore_runs(bad, off, 0.5, 5, 6, 0)
     assert e.value.code == -4  # TIDK_ENONASCII
+
+
+# ---- vertical scan (explore_vertical.cuh): resident batches of upper-case A C G T ---------------------------------
+@pytest.mark.parametrize("seed", range(4))
+def test_vertical_heads_tails_and_tile_edges(ctx, seed):
+    """Records whose slices start with 0..40 A's (the head flip), end inside a repeat (the closing parity), and whose
+    lengths sit around the tile boundaries of the vertical scan (1024, 1024 + 960 j), for every k the scan supports."""
+    rng = np.random.default_rng(900 + seed)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    lens = [1, 7, 31, 47, 64, 65, 959, 960, 1023, 1024, 1025, 1087, 1088, 1983, 1984, 1985, 2944, 2945, 3904, 4000, 7777]
+    recs = []
+    for i in range(160):
+        n = 2 * lens[(i + seed) % len(lens)] + int(rng.integers(0, 2))
+        r = rng.choice(acgt, size=n)
+        na = (i * 7 + seed) % 41
+        r[:na] = ord("A")
+        r[n - (n // 2): n - (n // 2) + (na // 2)] = ord("A")      # the right slice starts with A's too
+        if i % 3 == 0:  # a repeat that runs into the end of the record (and of the left slice)
+            k = int(rng.integers(1, 17))
+            unit = rng.choice(acgt, size=k)
+            ln = min(n, int(rng.integers(k, 40 * k)))
+            r[n - ln:] = np.tile(unit, ln // k + 1)[:ln]
+            h = (n + 1) // 2
+            l2 = min(h, int(rng.integers(k, 40 * k)))
+            r[h - l2: h] = np.tile(unit, l2 // k + 1)[:l2]
+        recs.append(r)
+    seq = np.concatenate(recs)
+    off = np.zeros(len(recs) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([r.size for r in recs])
+    kmin = [1, 5, 9, 13][seed]
+    _runs_equal(ctx, seq, off, 0.5, kmin, kmin + 3, [0, 1, 2, 0][seed])
+    _runs_equal(ctx, seq, off, 0.5, 5, 12, 3)
+
+
+def test_vertical_mixed_plain_and_other_tiles(ctx):
+    """Soft-masked stretches, N gaps and IUPAC codes inside otherwise plain records: the tiles that hold them go to the
+    plane kernel, their neighbours stay on the vertical scan, and the seams do not show."""
+    rng = np.random.default_rng(77)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    recs = []
+    for i in range(40):
+        n = int(rng.integers(3000, 30000))
+        r = rng.choice(acgt, size=n)
+        unit = rng.choice(acgt, size=int(rng.integers(2, 13)))
+        p = int(rng.integers(0, n - 2000))
+        r[p:p + 1500] = np.tile(unit, 1500 // unit.size + 1)[:1500]
+        for _ in range(3):
+            q = int(rng.integers(0, n - 300))
+            ln = int(rng.integers(1, 300))
+            what = int(rng.integers(0, 3))
+            if what == 0:
+                r[q:q + ln] |= 0x20  # lower case
+            elif what == 1:
+                r[q:q + ln] = ord("N")
+            else:
+                r[q] = ord("R")
+        recs.append(r)
+    seq = np.concatenate(recs)
+    off = np.zeros(len(recs) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([r.size for r in recs])
+    _runs_equal(ctx, seq, off, 0.5, 5, 12, 10)
+    _runs_equal(ctx, seq, off, 0.37, 2, 7, 0)

@@ -8,13 +8,14 @@ from telomeric_identifier_b200 import synth
 n_reads = int(os.environ.get("TIDK_PROF_READS", "100000"))
 steps = int(os.environ.get("TIDK_PROF_STEPS", "3"))
 which = os.environ.get("TIDK_PROF_CFG", "c5,c3").split(",")
+KMIN, KMAX = int(os.environ.get("TIDK_PROF_KMIN", "5")), int(os.environ.get("TIDK_PROF_KMAX", "12"))
 with T.Context(0) as ctx:
     if "c5" in which:
         ids, seq, off = synth.config5(n_reads=n_reads)
         b = ctx.upload(seq, off)
         for _ in range(steps):
             t0 = time.perf_counter()
-            runs = ctx.explore_runs_resident(b, 0.5, 5, 12, 100)
+            runs = ctx.explore_runs_resident(b, 0.5, KMIN, KMAX, 100)
             dt = time.perf_counter() - t0
             scanned = sum(2 * int(np.ceil(float(l) * 0.5)) for l in (off[1:] - off[:-1]).tolist())
             sm, pm = ctx.explore_timings()
@@ -27,7 +28,7 @@ with T.Context(0) as ctx:
         b = ctx.upload(seq, off)
         for _ in range(steps):
             t0 = time.perf_counter()
-            runs = ctx.explore_runs_resident(b, 0.01, 5, 12, 100)
+            runs = ctx.explore_runs_resident(b, 0.01, KMIN, KMAX, 100)
             dt = time.perf_counter() - t0
             scanned = sum(2 * int(np.ceil(float(l) * 0.01)) for l in (off[1:] - off[:-1]).tolist())
             sm, pm = ctx.explore_timings()
