@@ -93,7 +93,9 @@ struct ExploreJob {
     KeyFmt fmt;
 };
 
+struct RunBlockPool; // pinned host blocks for run lists (explore_post.cuh); owned by the context, closed by tidk_cuda_destroy
 struct ExploreScratch {
+    RunBlockPool *run_pool = nullptr;
     void *slices = nullptr, *tile_base = nullptr, *tiles = nullptr, *events = nullptr, *misc = nullptr, *items = nullptr;
     void *keys2 = nullptr, *temp = nullptr, *runs = nullptr, *flags = nullptr, *runs_out = nullptr;
     void *vtiles = nullptr; // tile list of the vertical scan (explore_vertical.cuh)

@@ -334,7 +334,7 @@ inline int explore_runs_device(ExploreScratch &sc, cudaStream_t st, cudaEvent_t 
     }
     *n_runs = runs.size();
     if (!runs.empty()) {
-        *out_runs = (tidk_run *)malloc(runs.size() * sizeof(tidk_run));
+        *out_runs = run_list_alloc_plain(runs.size() * sizeof(tidk_run));
         if (!*out_runs) { err = "out of host memory"; *n_runs = 0; return TIDK_ENOMEM; }
         memcpy(*out_runs, runs.data(), runs.size() * sizeof(tidk_run));
     }

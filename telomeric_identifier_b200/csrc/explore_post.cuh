@@ -19,43 +19,97 @@
 namespace tidk {
 
 // Run lists leave the device into pinned host blocks (a 6 MB list: 0.15 ms by DMA against 0.5 ms through the
-// driver's staging of a pageable destination).  Pinning costs more than the copy, so the blocks are pooled:
-// tidk_cuda_free_runs hands a block back, the next call takes the smallest one that fits.  A handful of blocks
-// stay pinned for the life of the process; anything beyond that is released.
+// driver's staging of a pageable destination).  Pinning costs more than the copy, so the blocks are pooled: tidk_cuda_free_runs
+// hands a block back, the next call takes the smallest one that fits.  The pool belongs to its CONTEXT (no process-wide
+// state): every run list, pinned or plain, sits behind a 64-byte header that names its pool, so tidk_cuda_free_runs --
+// which takes only the pointer -- finds its way home.  tidk_cuda_destroy unpins the idle blocks; a list still held by the
+// caller at that point keeps the (then closed) pool alive until it is freed.
+struct RunBlockPool;
+struct RunListHeader {
+    uint64_t magic;
+    RunBlockPool *pool; // nullptr: plain malloc
+    uint64_t pad[6];
+};
+static_assert(sizeof(RunListHeader) == 64, "run lists stay 64-byte aligned behind their header");
+constexpr uint64_t kRunListMagic = 0x7469646b52756e73ull; // "tidkRuns"
+
 struct RunBlockPool {
     struct Block { void *p; size_t cap; bool in_use; };
     std::mutex mu;
     std::vector<Block> blocks;
-    static RunBlockPool &get() { static RunBlockPool *pool = new RunBlockPool; return *pool; } // never destroyed: no CUDA calls at exit
-    void *take(size_t bytes) {
+    bool closed = false; // the context is gone: returned blocks are unpinned, the last one deletes the pool
+    tidk_run *take(size_t bytes) {
         std::lock_guard<std::mutex> g(mu);
+        const size_t need = bytes + sizeof(RunListHeader);
         Block *best = nullptr;
         for (Block &b : blocks)
-            if (!b.in_use && b.cap >= bytes && (!best || b.cap < best->cap)) best = &b;
-        if (best) { best->in_use = true; return best->p; }
-        void *p = nullptr;
-        const size_t cap = bytes + bytes / 4 + 4096;
-        if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
-        blocks.push_back({p, cap, true});
-        return p;
-    }
-    bool give_back(void *p) { // false: not one of ours
-        std::lock_guard<std::mutex> g(mu);
-        size_t idle = 0;
-        for (Block &b : blocks) idle += !b.in_use;
-        for (size_t i = 0; i < blocks.size(); i++) {
-            if (blocks[i].p != p) continue;
-            if (idle >= 4) { // enough idle blocks already: unpin this one
-                cudaFreeHost(p);
-                blocks.erase(blocks.begin() + (long)i);
-            } else {
-                blocks[i].in_use = false;
-            }
-            return true;
+            if (!b.in_use && b.cap >= need && (!best || b.cap < best->cap)) best = &b;
+        if (!best) {
+            void *p = nullptr;
+            const size_t cap = need + need / 4 + 4096;
+            if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+            blocks.push_back({p, cap, false});
+            best = &blocks.back();
         }
-        return false;
+        best->in_use = true;
+        RunListHeader *h = (RunListHeader *)best->p;
+        h->magic = kRunListMagic;
+        h->pool = this;
+        return (tidk_run *)(h + 1);
+    }
+    void give_back(RunListHeader *h) {
+        bool last = false;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            size_t idle = 0, busy = 0;
+            for (Block &b : blocks) { idle += !b.in_use; busy += b.in_use; }
+            for (size_t i = 0; i < blocks.size(); i++) {
+                if (blocks[i].p != (void *)h) continue;
+                if (closed || idle >= 4) { // enough idle blocks already (or nobody left to reuse it): unpin this one
+                    cudaFreeHost(blocks[i].p);
+                    blocks.erase(blocks.begin() + (long)i);
+                } else {
+                    blocks[i].in_use = false;
+                }
+                busy--;
+                break;
+            }
+            last = closed && busy == 0;
+        }
+        if (last) delete this;
+    }
+    // tidk_cuda_destroy: unpin what is idle; lists the caller still holds stay valid
+    static void close(RunBlockPool *pool) {
+        if (!pool) return;
+        bool last = false;
+        {
+            std::lock_guard<std::mutex> g(pool->mu);
+            pool->closed = true;
+            for (size_t i = pool->blocks.size(); i-- > 0;)
+                if (!pool->blocks[i].in_use) {
+                    cudaFreeHost(pool->blocks[i].p);
+                    pool->blocks.erase(pool->blocks.begin() + (long)i);
+                }
+            last = pool->blocks.empty();
+        }
+        if (last) delete pool;
     }
 };
+
+// a run list outside any pool (small lists, host-built lists)
+inline tidk_run *run_list_alloc_plain(size_t bytes) {
+    RunListHeader *h = (RunListHeader *)malloc(bytes + sizeof(RunListHeader));
+    if (!h) return nullptr;
+    h->magic = kRunListMagic;
+    h->pool = nullptr;
+    return (tidk_run *)(h + 1);
+}
+inline void run_list_free(tidk_run *runs) {
+    if (!runs) return;
+    RunListHeader *h = (RunListHeader *)runs - 1;
+    if (h->magic != kRunListMagic) return; // not one of ours: leave it alone rather than corrupt the heap
+    if (h->pool) h->pool->give_back(h); else { h->magic = 0; free(h); }
+}
 
 __global__ void __launch_bounds__(256) runs_from_keys_kernel(const uint64_t *keys, KeyFmt fmt, uint64_t n_pairs, uint64_t threshold,
                                                             tidk_run *runs, uint8_t *flags, uint32_t *err_flags) {
@@ -98,7 +152,7 @@ __global__ void __launch_bounds__(256) runs_from_keys_kernel(const uint64_t *key
     }
 }
 
-// keys: n_events packed keys in sc.events.  On success *out_runs (malloc) / *n_runs hold the result.
+// keys: n_events packed keys in sc.events.  On success *out_runs (a block of sc.run_pool, or a plain allocation) / *n_runs hold the result.
 // n_sorted >= n_events keys sit in sc.events; the surplus are all-ones fillers, which the sort sends behind every event
 inline int explore_post_device(ExploreScratch &sc, cudaStream_t st, uint64_t n_events, uint64_t n_sorted, KeyFmt fmt, int key_bits, uint64_t threshold,
                                tidk_run **out_runs, uint64_t *n_runs, uint32_t *launches, std::string &err) {
@@ -150,13 +204,13 @@ inline int explore_post_device(ExploreScratch &sc, cudaStream_t st, uint64_t n_e
     if (h_nsel) {
         const size_t bytes = h_nsel * sizeof(tidk_run);
         const bool pooled = bytes >= (256u << 10); // small lists: a plain allocation and a staged copy are as fast
-        *out_runs = (tidk_run *)(pooled ? RunBlockPool::get().take(bytes) : nullptr);
-        const bool pinned = *out_runs != nullptr;
-        if (!pinned) *out_runs = (tidk_run *)malloc(bytes);
+        if (pooled && !sc.run_pool) sc.run_pool = new RunBlockPool;
+        *out_runs = pooled ? sc.run_pool->take(bytes) : nullptr;
+        if (!*out_runs) *out_runs = run_list_alloc_plain(bytes);
         if (!*out_runs) { err = "out of host memory"; return TIDK_ENOMEM; }
         if ((e = cudaMemcpyAsync(*out_runs, sc.runs_out, bytes, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
             (e = cudaStreamSynchronize(st)) != cudaSuccess) {
-            if (pinned) RunBlockPool::get().give_back(*out_runs); else free(*out_runs);
+            run_list_free(*out_runs);
             *out_runs = nullptr;
             return cuerr(e, "D2H runs");
         }

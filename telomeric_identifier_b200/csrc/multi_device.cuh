@@ -130,7 +130,7 @@ inline int merge_runs(tidk_ctx *ctx, std::vector<std::vector<tidk_run>> &part, t
     *n_runs = total;
     *out_runs = nullptr;
     if (total == 0) return TIDK_OK;
-    tidk_run *all = (tidk_run *)malloc(total * sizeof(tidk_run));
+    tidk_run *all = tidk::run_list_alloc_plain(total * sizeof(tidk_run));
     if (!all) { *n_runs = 0; return fail(ctx, TIDK_ENOMEM, "out of host memory"); }
     uint64_t at = 0;
     for (auto &p : part) {

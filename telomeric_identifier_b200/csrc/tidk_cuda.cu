@@ -581,6 +581,7 @@ void tidk_cuda_destroy(tidk_ctx *ctx) {
     seqbuf_release(&ctx->scratch);
     for (DevBuf *b : {&ctx->win_base, &ctx->out_fwd, &ctx->out_rev, &ctx->misc, &ctx->qbytes, &ctx->runs, &ctx->items, &ctx->exc, &ctx->chunk_state})
         if (b->p) cudaFree(b->p);
+    tidk::RunBlockPool::close(ctx->ex.run_pool); // lists the caller still holds stay valid (explore_post.cuh)
     explore_scratch_release(ctx->ex);
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
     if (ctx->packed.p) cudaFree(ctx->packed.p);
@@ -1458,7 +1459,7 @@ int tidk_cuda_explore_runs(tidk_ctx *ctx, const uint8_t *seq, const uint64_t *of
 
 void tidk_cuda_free_runs(tidk_run *runs) {
     if (!runs) return;
-    if (!tidk::RunBlockPool::get().give_back(runs)) free(runs); // large lists live in pooled pinned blocks (explore_post.cuh)
+    tidk::run_list_free(runs); // the header in front of the list names its context's pool of pinned blocks, or none (explore_post.cuh)
 }
 
 int tidk_cuda_seqbuf_planes_info(const tidk_seqbuf *buf, int *ready, float *build_ms, uint64_t *bytes) {
