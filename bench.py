@@ -539,17 +539,22 @@ def main():
         k_ms = kernel_ms / (steps * PASSES)  # max over ranks of the mean device time per pass
         per_gpu = total_bases / world
         achieved = per_gpu / (k_ms * 1e-3) / 1e9  # GB/s per GPU at 1 B per scanned base
-        src_name = "PackedSource" if planes_ready else "AsciiSource"
+        flat = planes_ready and os.environ.get("TIDK_FLAT", "1") != "0"
+        kname = ("window_counts_flat_kernel<StaticMatcher<6,TTAGGG>,3>" if flat else
+                 "window_counts_kernel<StaticMatcher<6,TTAGGG>,4,%s>" % ("PackedSource" if planes_ready else "AsciiSource"))
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": f"window_counts_kernel<StaticMatcher<6,TTAGGG>,4,{src_name}>", "kernel_ms": k_ms,
+                "traffic": None, "kernel": kname, "kernel_ms": k_ms,
                 "algorithmic_bytes_per_launch": per_gpu, "peak_source": peak_src,
                 "note": "per GPU: bases of one rank's range / slowest rank's mean kernel time per pass; `achieved` counts the "
                         "ALGORITHMIC 1 B per scanned base (SURVEY.md 8d)"}
         if planes_ready:
-            # the resident batch is read as bit-planes (lo / hi / validity, 0.375 B per base) that K1 built once behind the
-            # upload: frac above 1 means less than one byte per base crosses HBM, not that the peak was beaten
+            # the resident batch is read as bit-planes (lo / hi: 0.25 B per base; the validity plane, 0.125 B per base, only in
+            # the 4 096-base steps that hold anything but A C G T) that K1 built once behind the upload: frac above 1 means
+            # less than one byte per base crosses HBM, not that the peak was beaten.  The estimate is the upper bound (all
+            # three planes); `traffic` is what ncu measured.
             dram = 0.375 * per_gpu
-            roof["source"] = {"what": "resident bit-planes, built once per upload by planes_build_kernel (K1)",
+            roof["source"] = {"what": "resident bit-planes, built once per upload by planes_build_kernel (K1); flat form (window_counts_flat.cuh): "
+                                      "a warp walks 32 Ki consecutive bases in 4 096-base steps, windows are an accounting matter",
                               "dram_bytes_per_launch_estimate": dram, "dram_gbs_estimate": dram / (k_ms * 1e-3) / 1e9,
                               "frac_of_peak_on_dram_bytes": dram / (k_ms * 1e-3) / 1e9 / peak,
                               "k1_planes_build_ms": planes_ms, "k1_bytes": "1 B read + 0.375 B written per base",

@@ -19,6 +19,11 @@
 #include "explore_planes.cuh"
 #include "explore_vertical_core.hpp"
 
+// A/B switch (kernel-tuning builds): the warps of a CTA enter every item behind a barrier
+#ifndef TIDK_V_SYNC
+#define TIDK_V_SYNC 0
+#endif
+
 namespace tidk {
 
 constexpr int kVWarps = 4;          // warps per CTA
@@ -155,21 +160,41 @@ __device__ __forceinline__ VDesc vt_desc(const VJob &job, uint64_t item, int lan
 }
 
 // the 32 x 33 words of each plane that the warp's tiles start in, row by row (a tile's words are consecutive in the
-// plane: coalesced), straight into shared memory; wa = this lane's first word
+// plane: coalesced), straight into shared memory; wa = this lane's first word.  Every lane forms the address of ITS
+// tile's first word once; the loop over the 32 tiles then broadcasts it (two SHFL) together with the number of words
+// left in the tile's 4 MiB chunk of the plane layout (a row that runs over the end of its chunk continues 2 * kPackWords
+// further on, behind the chunk's hi and va parts): 8 instructions per row where forming the address per row took 17.
 __device__ __forceinline__ void vt_stage_async(const uint32_t *planes, uint32_t wa, uint32_t *stage, int lane) {
-    const uint32_t s_lo = (uint32_t)__cvta_generic_to_shared(stage), s_hi = s_lo + 32 * 33 * 4;
+    const uint32_t s_lo = (uint32_t)__cvta_generic_to_shared(stage) + (uint32_t)lane * 4u, s_hi = s_lo + 32 * 33 * 4;
+    const unsigned long long row = (unsigned long long)(uintptr_t)plane_word_ptr(planes, (uint64_t)wa);
+    const uint32_t left = kPackWords - (wa & (kPackWords - 1u)); // words of this chunk from wa on (>= 1)
+    constexpr unsigned long long kSkip = 2ull * kPackWords * 4ull;
+    if (!__any_sync(0xFFFFFFFFu, left < 33u)) { // (nearly always) no row of this item reaches the end of its chunk
 #pragma unroll 8
-    for (int L = 0; L < 32; L++) {
-        const uint32_t wl = __shfl_sync(0xFFFFFFFFu, wa, L);
-        const uint32_t *p = plane_word_ptr(planes, (uint64_t)wl + (uint32_t)lane);
-        const uint32_t off = (uint32_t)(L * 33 + lane) * 4u;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_lo + off), "l"(p) : "memory");
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_hi + off), "l"(p + kPackWords) : "memory");
+        for (int L = 0; L < 32; L++) {
+            const unsigned long long pp = __shfl_sync(0xFFFFFFFFu, row, L) + (uint32_t)lane * 4u;
+            const uint32_t off = (uint32_t)(L * 33) * 4u;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_lo + off), "l"(pp) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_hi + off), "l"(pp + (unsigned long long)kPackWords * 4ull) : "memory");
+        }
+        const uint32_t off = (uint32_t)(lane * 32 + 32) * 4u;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_lo + off), "l"(row + 128ull) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_hi + off), "l"(row + 128ull + (unsigned long long)kPackWords * 4ull) : "memory");
+        return;
     }
-    const uint32_t *p = plane_word_ptr(planes, (uint64_t)wa + 32u);
-    const uint32_t off = (uint32_t)(lane * 33 + 32) * 4u;
+#pragma unroll 1
+    for (int L = 0; L < 32; L++) {
+        const unsigned long long rl = __shfl_sync(0xFFFFFFFFu, row, L);
+        const uint32_t ll = __shfl_sync(0xFFFFFFFFu, left, L);
+        const unsigned long long p = rl + (uint32_t)lane * 4u + ((uint32_t)lane >= ll ? kSkip : 0ull);
+        const uint32_t off = (uint32_t)(L * 33) * 4u;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_lo + off), "l"(p) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1+%2], 4;" ::"r"(s_hi + off), "l"(p), "n"(kPackWords * 4u) : "memory"); // the hi part of the chunk
+    }
+    const unsigned long long p = row + 32ull * 4ull + (32u >= left ? kSkip : 0ull);
+    const uint32_t off = (uint32_t)(lane * 32 + 32) * 4u; // (+ lane * 4 from s_lo: word lane * 33 + 32)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_lo + off), "l"(p) : "memory");
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_hi + off), "l"(p + kPackWords) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1+%2], 4;" ::"r"(s_hi + off), "l"(p), "n"(kPackWords * 4u) : "memory");
 }
 
 // KMIN > 0: the k range is a compile-time constant; KMIN == 0: run-time range (job.kmin .. job.kmax, <= kVMaxK).
@@ -199,7 +224,14 @@ __global__ void __launch_bounds__(kVWarps * 32, TIDK_V_MINB) explore_vertical_ke
     asm volatile("cp.async.commit_group;" ::: "memory");
     VDesc nxt = vt_desc(job, item_next < n_items ? item_next : n_items, lane);
     uint32_t buf = 0;
+#if TIDK_V_SYNC
+    for (;;) { // the warps of a CTA enter every item together: they run the same stretch of code at about the same time
+        const bool active_ = item < n_items;
+        if (!__syncthreads_or(active_)) break;
+        if (!active_) continue;
+#else
     while (item < n_items) {
+#endif
         uint32_t ticket = 0;
         if (lane == 0) asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(ticket) : "l"(job.work_counter) : "memory");
         uint32_t *const stage = ws.stage[buf];

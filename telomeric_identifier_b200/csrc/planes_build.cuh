@@ -27,7 +27,7 @@ struct PlaneBuildJob {
     uint32_t *validbits;  // [n_blocks + 1]
     uint64_t n_blocks;    // 1 KiB blocks to convert (covers the data and the padded tail)
     uint64_t total;       // bases in the batch: the word that holds the last base counts as plain when its bases are
-    uint32_t *err_flags;  // device word: bit 0 set when a byte >= 0x80 is seen, bit 1 when a word that holds a base is not plain
+    uint32_t *err_flags;  // two words of mapped host memory: [0] = 1 when a byte >= 0x80 is seen, [1] = 1 when a word that holds a base is not plain
 };
 
 __device__ __forceinline__ uint32_t *plane_word_ptr(uint32_t *planes, uint64_t word) {
@@ -80,8 +80,14 @@ __global__ void __launch_bounds__(256, 4) planes_build_kernel(const PlaneBuildJo
         if (nxt >= job.n_blocks) break;
         blk = nxt;
     }
-    const uint32_t flags = (__any_sync(0xFFFFFFFFu, nonascii != 0) ? 1u : 0u) | (__any_sync(0xFFFFFFFFu, other) ? 2u : 0u);
-    if (flags && lane == 0) atomicOr(job.err_flags, flags);
+    // Plain posted stores, one word per flag: an atomicOr on mapped host memory is a PCIe atomic per warp, and on a genome
+    // with N gaps or soft-masked stretches every warp has something to report -- 4 736 of them in a row took the kernel
+    // from 0.8 to 24.7 ms on the C4 genome (3.1 Gb).
+    const bool f0 = __any_sync(0xFFFFFFFFu, nonascii != 0), f1 = __any_sync(0xFFFFFFFFu, other);
+    if (lane == 0) {
+        if (f0) *(volatile uint32_t *)&job.err_flags[0] = 1u;
+        if (f1) *(volatile uint32_t *)&job.err_flags[1] = 1u;
+    }
 }
 
 } // namespace tidk

@@ -22,6 +22,7 @@
 #include "explore_host.cuh"
 #include "host_pack.hpp"
 #include "planes_build.cuh"
+#include "window_counts_flat.cuh"
 #include "window_counts.cuh"
 
 using namespace tidk;
@@ -160,6 +161,9 @@ struct tidk_ctx {
     // work items cached for (sequence batch, window, query count): several clades or output
     // formats over one uploaded genome reuse them
     uint64_t items_buf_id = 0, items_window = 0, items_n = 0, items_nwin = 0;
+    bool items_built = false;     // the item table of (items_buf_id, items_window, items_nq) exists (calls served by the flat kernels never build it)
+    DevBuf spans;                 // span descriptors of the flat window counter (window_counts_flat.cuh), cached like the items
+    uint64_t spans_buf_id = 0, spans_window = 0, spans_nq = 0;
     uint32_t items_nq = 0;
 };
 
@@ -361,9 +365,9 @@ int seqbuf_build_planes(tidk_ctx *ctx, tidk_seqbuf *b) {
     CU(ctx, cudaGetLastError());
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     CU(ctx, cudaEventElapsedTime(&b->planes_ms, ctx->ev0, ctx->ev1));
-    b->planes_nonascii = (ctx->h_flags[1] & 1u) != 0;
-    b->planes_all_plain = (ctx->h_flags[1] & 2u) == 0;
-    ctx->h_flags[1] = 0;
+    b->planes_nonascii = ((volatile uint32_t *)ctx->h_flags)[1] != 0;
+    b->planes_all_plain = ((volatile uint32_t *)ctx->h_flags)[2] == 0;
+    ctx->h_flags[1] = ctx->h_flags[2] = 0;
     b->planes_ready = true;
     return TIDK_OK;
 }
@@ -442,8 +446,36 @@ void launch_static(const WindowJob &job, const LaunchEnv &env) {
     const int grid = resident_grid(window_counts_kernel<M, 4, Src>, env, job.n_items);
     window_counts_kernel<M, 4, Src><<<grid, kWarpsPerBlock * 32, 0, env.st>>>(job, mp);
 }
-struct StaticEntry { int L; uint64_t F; LaunchFn fn, fn_packed; };
-#define X_(s) {cx_len(s), cx_enc(s), &launch_static<cx_len(s), cx_enc(s), AsciiSource>, &launch_static<cx_len(s), cx_enc(s), PackedSource>},
+// flat form on resident planes (window_counts_flat.cuh)
+#ifndef TIDK_FLAT_MINB
+#define TIDK_FLAT_MINB 3
+#endif
+using FlatLaunchFn = void (*)(const FlatJob &, const LaunchEnv &);
+template <int L, uint64_t F>
+void launch_static_flat(const FlatJob &job, const LaunchEnv &env) {
+    using M = StaticMatcher<L, F>;
+    const int grid = resident_grid(window_counts_flat_kernel<M, TIDK_FLAT_MINB>, env, job.n_spans);
+    window_counts_flat_kernel<M, TIDK_FLAT_MINB><<<grid, kWarpsPerBlock * 32, 0, env.st>>>(job, 0u);
+}
+template <int L>
+void launch_runtime_flat(const FlatJob &job, const typename FlatRuntime<L>::Params &rp, const LaunchEnv &env) {
+    using M = FlatRuntime<L>;
+    const int grid = resident_grid(window_counts_flat_kernel<M, TIDK_FLAT_MINB>, env, job.n_spans);
+    window_counts_flat_kernel<M, TIDK_FLAT_MINB><<<grid, kWarpsPerBlock * 32, 0, env.st>>>(job, rp);
+}
+void launch_flat_runtime(int L, const FlatJob &job, const FlatRuntime<1>::Params &rp0, const LaunchEnv &env) {
+    switch (L) {
+#define C_(n) case n: { FlatRuntime<n>::Params rp; memcpy(&rp, &rp0, sizeof(rp)); launch_runtime_flat<n>(job, rp, env); break; }
+        C_(1) C_(2) C_(3) C_(4) C_(5) C_(6) C_(7) C_(8) C_(9) C_(10) C_(11) C_(12) C_(13) C_(14)
+        C_(15) C_(16) C_(17) C_(18) C_(19) C_(20) C_(21) C_(22) C_(23) C_(24) C_(25) C_(26) C_(27)
+        C_(28) C_(29) C_(30) C_(31) C_(32)
+#undef C_
+    default: break;
+    }
+}
+
+struct StaticEntry { int L; uint64_t F; LaunchFn fn, fn_packed; FlatLaunchFn fn_flat; };
+#define X_(s) {cx_len(s), cx_enc(s), &launch_static<cx_len(s), cx_enc(s), AsciiSource>, &launch_static<cx_len(s), cx_enc(s), PackedSource>, &launch_static_flat<cx_len(s), cx_enc(s)>},
 const StaticEntry kStatic[] = {TIDK_STATIC_MOTIFS(X_)};
 #undef X_
 
@@ -483,6 +515,15 @@ const CladeSet kCladeSets[] = {
       "AAAATTGTCCGTCC", "AAACCC", "AACCC", "AACCCAGACCC", "AACCCAGACGC", "AACCCTGACGC"},
      &launch_multi<Hymenoptera, 2, AsciiSource>, &launch_multi<Hymenoptera, 2, PackedSource>},
 };
+
+FlatLaunchFn find_static_flat(const uint8_t *pat, uint32_t L) {
+    if (L > 32) return nullptr;
+    uint64_t f = 0;
+    for (uint32_t j = 0; j < L; j++) f |= cx_code((char)pat[j]) << (2 * j);
+    for (const StaticEntry &e : kStatic)
+        if (e.L == (int)L && e.F == f) return e.fn_flat;
+    return nullptr;
+}
 
 LaunchFn find_clade_set(const char *const *queries, const uint32_t *qlens, uint32_t nq, bool packed = false) {
     for (const CladeSet &c : kCladeSets) {
@@ -579,7 +620,7 @@ void tidk_cuda_destroy(tidk_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     seqbuf_release(&ctx->scratch);
-    for (DevBuf *b : {&ctx->win_base, &ctx->out_fwd, &ctx->out_rev, &ctx->misc, &ctx->qbytes, &ctx->runs, &ctx->items, &ctx->exc, &ctx->chunk_state})
+    for (DevBuf *b : {&ctx->win_base, &ctx->out_fwd, &ctx->out_rev, &ctx->misc, &ctx->qbytes, &ctx->runs, &ctx->items, &ctx->spans, &ctx->exc, &ctx->chunk_state})
         if (b->p) cudaFree(b->p);
     tidk::RunBlockPool::close(ctx->ex.run_pool); // lists the caller still holds stay valid (explore_post.cuh)
     explore_scratch_release(ctx->ex);
@@ -764,7 +805,11 @@ static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint3
     }
     ctx->counters_dirty = true; // cleared when this call has completed all its launches
     uint64_t *d_fwd = (uint64_t *)ctx->out_dev[slot].p, *d_rev = d_fwd + n_out;
-    if (spw > 1) {
+    // Flat form (window_counts_flat.cuh) for single queries whenever the source is the batch's own resident planes: it
+    // adds into pre-zeroed counters.
+    const bool flat_ok = packed && packed == buf->d_planes && buf->planes_ready && split == 0 && buf->d_validbits &&
+                         !(getenv("TIDK_FLAT") && atoi(getenv("TIDK_FLAT")) == 0);
+    if (spw > 1 || flat_ok) {
         CU(ctx, cudaMemsetAsync(d_fwd, 0, 2 * n_out * 8, ctx->stream));
     }
 
@@ -773,19 +818,47 @@ static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint3
     if (!cached) {
         ctx->items_buf_id = 0;
         if ((rc = ensure(ctx, ctx->win_base, wb.size() * 8))) return rc;
-        if ((rc = ensure(ctx, ctx->items, n_items * sizeof(ItemDesc)))) return rc;
         CU(ctx, cudaMemcpyAsync(ctx->win_base.p, wb.data(), wb.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->items_buf_id = buf->id; ctx->items_window = window; ctx->items_nq = nq;
+        ctx->items_n = n_items; ctx->items_nwin = n_windows;
+        ctx->items_built = false;
+    }
+    // the per-window item table: built by the first launch of the per-window kernels that needs it
+    auto need_items = [&]() -> int {
+        if (ctx->items_built) return TIDK_OK;
+        int rc2;
+        if ((rc2 = ensure(ctx, ctx->items, n_items * sizeof(ItemDesc)))) return rc2;
         PrepJob pj{buf->d_off, (const uint64_t *)ctx->win_base.p, (ItemDesc *)ctx->items.p, window, n_items, nrec, spw, nq};
         window_items_kernel<<<(unsigned)((n_items + 255) / 256), 256, 0, ctx->stream>>>(pj);
         launches++;
-        ctx->items_buf_id = buf->id; ctx->items_window = window; ctx->items_nq = nq;
-        ctx->items_n = n_items; ctx->items_nwin = n_windows;
+        ctx->items_built = true;
+        return TIDK_OK;
+    };
+
+    const uint64_t n_spans = (buf->total + kFlatSpanBases - 1) / kFlatSpanBases;
+    if (flat_ok && !(ctx->spans_buf_id == buf->id && ctx->spans_window == window && ctx->spans_nq == nq)) {
+        ctx->spans_buf_id = 0;
+        if ((rc = ensure(ctx, ctx->spans, n_spans * sizeof(SpanDesc)))) return rc;
+        FlatPrepJob fp{buf->d_off, (const uint64_t *)ctx->win_base.p, (SpanDesc *)ctx->spans.p, window, n_spans, 0, nrec, nq};
+        flat_spans_kernel<<<(unsigned)((n_spans + 255) / 256), 256, 0, ctx->stream>>>(fp);
+        launches++;
+        ctx->spans_buf_id = buf->id; ctx->spans_window = window; ctx->spans_nq = nq;
+    }
+    FlatJob fjob{};
+    if (flat_ok) {
+        fjob.planes = buf->d_planes; fjob.validbits = buf->d_validbits;
+        fjob.rec_off = buf->d_off; fjob.win_base = (const uint64_t *)ctx->win_base.p;
+        fjob.spans = (const SpanDesc *)ctx->spans.p;
+        fjob.out_fwd = (unsigned long long *)d_fwd; fjob.out_rev = (unsigned long long *)d_rev;
+        fjob.window = window; fjob.total = buf->total; fjob.n_spans = n_spans; fjob.span0 = 0;
+        fjob.n_vblocks = (buf->total + 1023) / 1024 + kSeqPad / 1024;
+        fjob.n_records = nrec; fjob.nq_total = nq;
     }
 
     WindowJob job{};
     job.seq = buf->d_seq;
     job.packed = packed; // non-null: the host-packed planes are the source (every query has a static kernel)
-    job.items = (const ItemDesc *)ctx->items.p;
+    job.items = nullptr; // set by run_static / the run-time launches once the item table exists (need_items)
     job.out_fwd = d_fwd;
     job.out_rev = d_rev;
     job.err_flags = ctx->d_flags; // written only when a byte >= 0x80 is seen: no flag copy per call
@@ -842,7 +915,11 @@ static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint3
             n_ascii_items += below < nw ? below : nw;
         }
     }
-    auto run_static = [&](LaunchFn f_ascii, LaunchFn f_packed, const WindowJob &j) {
+    int lazy_rc = TIDK_OK;
+    auto run_static = [&](LaunchFn f_ascii, LaunchFn f_packed, const WindowJob &j0) {
+        if ((lazy_rc = need_items())) return;
+        WindowJob j = j0;
+        j.items = (const ItemDesc *)ctx->items.p;
         if (n_ascii_items > 0) {
             WindowJob ja = j;
             ja.packed = nullptr;
@@ -864,11 +941,33 @@ static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint3
         WindowJob j2 = job; // the whole query list is a known clade: one fused pass
         j2.q0 = 0; j2.nq = nq;
         run_static(clade, packed ? find_clade_set(queries, qlens, nq, true) : nullptr, j2);
+        if (lazy_rc) return lazy_rc;
         fast.clear();
     }
     for (uint32_t q : fast) {
         const uint8_t *f = (const uint8_t *)queries[q];
         revcomp_host(f, qlens[q], rcbuf);
+        if (flat_ok) {
+            FlatJob fj = fjob;
+            fj.q = q;
+            fj.work_counter = next_counter(); fj.next_counter = next_zeroed;
+            if (FlatLaunchFn ff = find_static_flat(f, qlens[q])) {
+                ff(fj, env);
+            } else if ((ff = find_static_flat(rcbuf, qlens[q]))) { // the listed motif is this query's reverse complement: swap the outputs
+                std::swap(fj.out_fwd, fj.out_rev);
+                ff(fj, env);
+            } else {
+                FlatRuntime<1>::Params rp{};
+                const StrandPattern pf = encode_strand(f, qlens[q]), pr = encode_strand(rcbuf, qlens[q]);
+                for (uint32_t s2 = 0; s2 < qlens[q]; s2++) {
+                    rp.flo[s2] = 0u - ((pf.plo >> s2) & 1u); rp.fhi[s2] = 0u - ((pf.phi >> s2) & 1u);
+                    rp.rlo[s2] = 0u - ((pr.plo >> s2) & 1u); rp.rhi[s2] = 0u - ((pr.phi >> s2) & 1u);
+                }
+                launch_flat_runtime((int)qlens[q], fj, rp, env);
+            }
+            launches++;
+            continue;
+        }
         LaunchFn fn = find_static(f, qlens[q], false), fnp = packed ? find_static(f, qlens[q], true) : nullptr;
         bool swap = false;
         if (!fn && (fn = find_static(rcbuf, qlens[q], false))) {
@@ -881,6 +980,7 @@ static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint3
         j2.q0 = q; j2.nq = 1;
         if (swap) { j2.out_fwd = d_rev; j2.out_rev = d_fwd; }
         run_static(fn, fnp, j2);
+        if (lazy_rc) return lazy_rc;
     }
     // Run-time patterns: one unrolled single-query launch each (about 100 us + 6.5 us per base on C2),
     // unless there are many -- the fused run-time kernel is not unrolled and costs about 130 us per
@@ -899,7 +999,9 @@ static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint3
             rq.len[i - g0] = (uint8_t)qlens[q];
         }
         rq.nq = (uint32_t)(g1 - g0);
+        if ((rc = need_items())) return rc;
         WindowJob j2 = job;
+        j2.items = (const ItemDesc *)ctx->items.p;
         j2.q0 = fused[g0]; j2.nq = rq.nq;
         j2.work_counter = next_counter(); j2.next_counter = next_zeroed;
         launch_planes(rq.nq == 1 ? (int)rq.len[0] : 0, j2, rq, env);
@@ -981,7 +1083,14 @@ static const uint32_t *resident_planes(tidk_ctx *ctx, const tidk_seqbuf *buf, co
                                        uint32_t nq, int *rc) {
     *rc = TIDK_OK;
     const bool on = !(getenv("TIDK_PLANES_COUNT") && atoi(getenv("TIDK_PLANES_COUNT")) == 0); // (read per call: measurements switch)
-    if (!on || !buf || !buf->planes_ready || !queries_packable(queries, qlens, nq)) return nullptr;
+    if (!on || !buf || !buf->planes_ready) return nullptr;
+    const bool flat_on = !(getenv("TIDK_FLAT") && atoi(getenv("TIDK_FLAT")) == 0);
+    bool all_fast = flat_on && queries && qlens && nq > 0; // the flat kernels take any A/C/G/T query up to 32 bases from the planes
+    for (uint32_t q = 0; all_fast && q < nq; q++) {
+        all_fast = queries[q] && qlens[q] >= 1 && qlens[q] <= (uint32_t)kMaxFastLen;
+        for (uint32_t j = 0; all_fast && j < qlens[q]; j++) all_fast = is_acgt((uint8_t)queries[q][j]);
+    }
+    if (!all_fast && !queries_packable(queries, qlens, nq)) return nullptr;
     if (buf->planes_nonascii)
         *rc = fail(ctx, TIDK_ENONASCII, "sequence contains a byte >= 0x80 (the reference fails in str::from_utf8, search.rs:107)");
     return buf->d_planes;

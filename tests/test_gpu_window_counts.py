@@ -300,16 +300,23 @@ def test_host_packed_upload_path(ctx, monkeypatch):
     monkeypatch.setenv("TIDK_HOST_PACK", "1")
     # hybrid (two-ended) upload: ASCII chunks by DMA from the front, packed chunks from the back, the
     # windows split between the two sources wherever the two meet; "0" = everything packed
+    # The DMA front reads the caller's buffer directly, so it is taken for PINNED sources only (a pageable source --
+    # a plain numpy array, a malloc'ed FASTA buffer -- travels all-packed whatever the knob says): both are run.
+    pinned = ctx.pinned_empty(seq.size)
+    pinned[:] = seq
     splits = set()
-    for hybrid, threads in (("1", "2"), ("1", "16"), ("0", "16")):   # 2 packers: the DMA thread takes a real share
+    for hybrid, threads, src in (("1", "2", pinned), ("1", "16", pinned), ("0", "16", pinned), ("1", "16", seq)):   # 2 packers: the DMA front takes a real share
         monkeypatch.setenv("TIDK_HYBRID_UPLOAD", hybrid)
         monkeypatch.setenv("TIDK_PACK_THREADS", threads)
         for qs, W in (([b"TTAGGG"], 10000), ([b"CCCTAA", b"AACCT"], 4321), (hym, 10000), ([b"TTAGGG"], 50000),
                       ([b"TTAGGG"], 32768)):
-            f, r = ctx.window_counts(seq, off, W, qs)
+            f, r = ctx.window_counts(src, off, W, qs)
             h2d, d2h, was_packed = ctx.last_transfer()
             assert was_packed
-            splits.add((hybrid, threads, h2d))
+            if src is pinned:
+                splits.add((hybrid, threads, h2d))
+            else:
+                assert h2d < seq.size // 2, "a pageable source must not take the DMA front"
             of, orr = O.window_counts(seq, off, W, qs, False, threads=4)
             assert (f == of).all() and (r == orr).all(), (qs, W, hybrid, threads)
     monkeypatch.delenv("TIDK_HYBRID_UPLOAD")
