@@ -359,6 +359,10 @@ int seqbuf_build_planes(tidk_ctx *ctx, tidk_seqbuf *b) {
     CU(ctx, cudaMemsetAsync(b->d_validbits + n_blocks, 0, 8, ctx->stream));
     PlaneBuildJob job{b->d_seq, b->d_planes, b->d_plainbits, b->d_validbits, n_blocks, b->total, ctx->d_flags + 1};
     const uint64_t want = (n_blocks + 7) / 8, cap = (uint64_t)ctx->sm_count * 8;
+    {   // the module is loaded lazily at a kernel's first launch (about 20 ms for this library): not between the two events
+        cudaFuncAttributes fa;
+        (void)cudaFuncGetAttributes(&fa, planes_build_kernel);
+    }
     CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     planes_build_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, ctx->stream>>>(job);
     CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
@@ -836,19 +840,22 @@ static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint3
     };
 
     const uint64_t n_spans = (buf->total + kFlatSpanBases - 1) / kFlatSpanBases;
-    if (flat_ok && !(ctx->spans_buf_id == buf->id && ctx->spans_window == window && ctx->spans_nq == nq)) {
+    auto need_spans = [&]() -> int { // the span table of the flat kernels: built by the first flat launch on (batch, window, query count)
+        if (ctx->spans_buf_id == buf->id && ctx->spans_window == window && ctx->spans_nq == nq) return TIDK_OK;
         ctx->spans_buf_id = 0;
-        if ((rc = ensure(ctx, ctx->spans, n_spans * sizeof(SpanDesc)))) return rc;
+        int rc2;
+        if ((rc2 = ensure(ctx, ctx->spans, n_spans * sizeof(SpanDesc)))) return rc2;
         FlatPrepJob fp{buf->d_off, (const uint64_t *)ctx->win_base.p, (SpanDesc *)ctx->spans.p, window, n_spans, 0, nrec, nq};
         flat_spans_kernel<<<(unsigned)((n_spans + 255) / 256), 256, 0, ctx->stream>>>(fp);
         launches++;
         ctx->spans_buf_id = buf->id; ctx->spans_window = window; ctx->spans_nq = nq;
-    }
+        return TIDK_OK;
+    };
     FlatJob fjob{};
     if (flat_ok) {
         fjob.planes = buf->d_planes; fjob.validbits = buf->d_validbits;
         fjob.rec_off = buf->d_off; fjob.win_base = (const uint64_t *)ctx->win_base.p;
-        fjob.spans = (const SpanDesc *)ctx->spans.p;
+        fjob.spans = nullptr; // set by the launch (need_spans)
         fjob.out_fwd = (unsigned long long *)d_fwd; fjob.out_rev = (unsigned long long *)d_rev;
         fjob.window = window; fjob.total = buf->total; fjob.n_spans = n_spans; fjob.span0 = 0;
         fjob.n_vblocks = (buf->total + 1023) / 1024 + kSeqPad / 1024;
@@ -948,7 +955,9 @@ static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint3
         const uint8_t *f = (const uint8_t *)queries[q];
         revcomp_host(f, qlens[q], rcbuf);
         if (flat_ok) {
+            if ((rc = need_spans())) return rc;
             FlatJob fj = fjob;
+            fj.spans = (const SpanDesc *)ctx->spans.p;
             fj.q = q;
             fj.work_counter = next_counter(); fj.next_counter = next_zeroed;
             if (FlatLaunchFn ff = find_static_flat(f, qlens[q])) {

@@ -31,6 +31,17 @@
 #include "planes_build.cuh"
 #include "window_counts.cuh"
 
+// kernel-tuning switches: unroll factor of the step loop (the software pipeline's register rotation disappears at 2),
+// L2 prefetch of the step after next
+#ifndef TIDK_FLAT_UNROLL
+#define TIDK_FLAT_UNROLL 1
+#endif
+#ifndef TIDK_FLAT_PF
+#define TIDK_FLAT_PF 0
+#endif
+#define TIDK_PRAGMA_(x) _Pragma(#x)
+#define TIDK_UNROLL_(n) TIDK_PRAGMA_(unroll n)
+
 namespace tidk {
 
 constexpr uint32_t kFlatStepBases = 4096;  // 128 words: four per lane
@@ -135,6 +146,15 @@ window_counts_flat_kernel(const FlatJob job, const typename std::conditional<fla
     };
     uint32_t vb = valid_word(word0);
     uint4 da = __ldg(sp + 2 * span), db = __ldg(sp + 2 * span + 1);
+    uint32_t n_c_lo = 0, n_c_hi = 0, n_c_va = 0;
+    auto load_front = [&](uint64_t w0) { // lane 31: the word in front of the span that starts at word w0
+        n_c_lo = n_c_hi = n_c_va = 0u;
+        if (lane == 31 && w0 > 0) {
+            const uint32_t *q = plane_word_ptr(job.planes, w0 - 1);
+            n_c_lo = __ldg(q); n_c_hi = __ldg(q + kPackWords); n_c_va = __ldg(q + 2 * kPackWords);
+        }
+    };
+    load_front(word0);
 
     for (;;) {
         // ticket for the span after this one: used at the end of the span
@@ -151,19 +171,15 @@ window_counts_flat_kernel(const FlatJob job, const typename std::conditional<fla
 
         const uint64_t span_pos = (job.span0 + span) * (uint64_t)kFlatSpanBases;
         const uint32_t valid_blocks = __ballot_sync(0xFFFFFFFFu, vb == 0xFFFFFFFFu); // bit b: block b of the span is all valid
-        // look-behind across the span start: lane 31 holds the word in front of the span
-        uint32_t c_lo = 0, c_hi = 0, c_va = 0;
-        if (lane == 31 && word0 > 0) {
-            const uint32_t *q = plane_word_ptr(job.planes, word0 - 1);
-            c_lo = __ldg(q); c_hi = __ldg(q + kPackWords); c_va = __ldg(q + 2 * kPackWords);
-        }
+        // look-behind across the span start: lane 31 holds the word in front of the span (loaded with the span's first step)
+        uint32_t c_lo = n_c_lo, c_hi = n_c_hi, c_va = n_c_va;
         uint32_t cf = 0, cr = 0;
         const uint64_t left = job.total - span_pos; // > 0
         const uint32_t n_steps = left >= kFlatSpanBases ? kFlatSpanSteps : (uint32_t)((left + kFlatStepBases - 1) / kFlatStepBases);
         unsigned long long span_next = 0;
         bool have_next = false;
 
-#pragma unroll 1
+        TIDK_UNROLL_(TIDK_FLAT_UNROLL)
         for (uint32_t st = 0; st < n_steps; st++) {
             const uint4 lo4 = nlo, hi4 = nhi;
             uint4 va4 = nva;
@@ -173,6 +189,12 @@ window_counts_flat_kernel(const FlatJob job, const typename std::conditional<fla
                 pp += kFlatStepBases / 32;
                 nlo = ldg128_stream(pp); nhi = ldg128_stream(pp + kPackWords);
                 if (((valid_blocks >> (4u * (st + 1))) & 0xFu) != 0xFu) nva = ldg128_stream(pp + 2 * kPackWords); // (all valid: va is not read, 0.25 B per base)
+#if TIDK_FLAT_PF
+                if (st + 2 < n_steps && (lane & 7) == 0) { // the step after next: its four lines per plane into L2
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + kFlatStepBases / 32));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + kFlatStepBases / 32 + kPackWords));
+                }
+#endif
             } else {
                 span_next = ticket0 + (unsigned long long)__shfl_sync(0xFFFFFFFFu, t2, 0) * kQueues;
                 have_next = span_next < job.n_spans;
@@ -182,6 +204,7 @@ window_counts_flat_kernel(const FlatJob job, const typename std::conditional<fla
                     nlo = ldg128_stream(pp); nhi = ldg128_stream(pp + kPackWords); nva = ldg128_stream(pp + 2 * kPackWords);
                     vb = valid_word(word0);
                     da = __ldg(sp + 2 * span_next); db = __ldg(sp + 2 * span_next + 1);
+                    load_front(word0);
                 }
             }
             if (step_valid) va4 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);

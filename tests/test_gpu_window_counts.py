@@ -410,3 +410,55 @@ def test_async_reports_non_ascii_at_wait(ctx):
     assert ei.value.code == T.api.TIDK_ENONASCII
     ctx.wait()  # the error is reported once
     batch.free()
+
+
+# ---------------------------------------------------------------- flat form on resident planes (window_counts_flat.cuh)
+@pytest.mark.parametrize("seed", range(8))
+def test_flat_resident_random(ctx, seed, monkeypatch):
+    """Resident batches are counted by the flat kernels (spans of 32 Ki bases, windows by accounting): ragged and empty
+    records, N / IUPAC / lower case, windows from 1 base to several spans, compile-time motifs, their reverse
+    complements and run-time patterns of every length class -- against the oracle and against the per-window kernels."""
+    from telomeric_identifier_b200 import synth
+    rng = np.random.default_rng(9000 + seed)
+    alpha = [b"ACGT", b"ACGTN", b"ACGTacgtNRY", b"AC"][seed % 4]
+    plant = [b"TTAGGG", b"AACCT", b"CCCTAA", b"GATTACA"][seed % 4]
+    ids, seq, off = synth.random_records(700 + seed, 1 + 5 * (seed % 3), [90_000, 300_000, 40_000][seed % 3], alpha, plant=plant, p_empty=0.15)
+    if seq.size == 0:
+        pytest.skip("empty batch")
+    b = ctx.upload(seq, off)
+    try:
+        assert b.planes_info()[0]
+        windows = [1, 7, 31, 32, 33, 100, 1000, 4095, 4096, 4097, 10000, 32768, 32769, 70001, 10 ** 9]
+        queries = [plant, b"TTAGGG", b"CCCTAA", b"A", b"AC", b"GATTACAGATTA", b"ACGTACGTACGTACGTACGTACGTACGTACGT",
+                   bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=int(rng.integers(2, 32))))]
+        for W in [windows[i] for i in rng.choice(len(windows), size=6, replace=False)]:
+            qs = [queries[i] for i in rng.choice(len(queries), size=3, replace=False)]
+            f, r = ctx.window_counts_resident(b, W, qs)
+            f, r = f.copy(), r.copy()
+            of, orr = O.window_counts(seq, off, W, qs, False)
+            assert np.array_equal(f, of) and np.array_equal(r, orr), (seed, W, qs)
+            monkeypatch.setenv("TIDK_FLAT", "0")
+            f0, r0 = ctx.window_counts_resident(b, W, qs)
+            monkeypatch.delenv("TIDK_FLAT")
+            assert np.array_equal(f0, of) and np.array_equal(r0, orr), (seed, W, qs, "per-window kernels")
+    finally:
+        b.free()
+
+
+def test_flat_window_straddles_and_span_edges(ctx):
+    """Occurrences that straddle a window boundary are lost (search.rs:98 cuts the windows first), also when the
+    boundary coincides with a 4 096-base step or a 32 Ki-base span edge of the flat kernel, or with a record edge."""
+    unit = b"TTAGGG"
+    n = 3 * 32768 + 500
+    seq = np.frombuffer((unit * (n // 6 + 1))[:n], dtype=np.uint8).copy()
+    for cut in (4096, 32768, 65536):           # a second record that starts exactly on a step / span edge
+        off = np.array([0, cut, n], dtype=np.uint64)
+        b = ctx.upload(seq, off)
+        try:
+            for W in (4096, 4098, 8192, 32768, 32770, 6, 5, 11):
+                for q in (unit, b"GGGTTA", b"TTAGGGTTAGGG"):
+                    f, r = ctx.window_counts_resident(b, W, [q])
+                    of, orr = O.window_counts(seq, off, W, [q], False)
+                    assert np.array_equal(f, of) and np.array_equal(r, orr), (cut, W, q)
+        finally:
+            b.free()
