@@ -31,17 +31,6 @@
 #include "planes_build.cuh"
 #include "window_counts.cuh"
 
-// kernel-tuning switches: unroll factor of the step loop (the software pipeline's register rotation disappears at 2),
-// L2 prefetch of the step after next
-#ifndef TIDK_FLAT_UNROLL
-#define TIDK_FLAT_UNROLL 1
-#endif
-#ifndef TIDK_FLAT_PF
-#define TIDK_FLAT_PF 0
-#endif
-#define TIDK_PRAGMA_(x) _Pragma(#x)
-#define TIDK_UNROLL_(n) TIDK_PRAGMA_(unroll n)
-
 namespace tidk {
 
 constexpr uint32_t kFlatStepBases = 4096;  // 128 words: four per lane
@@ -179,7 +168,7 @@ window_counts_flat_kernel(const FlatJob job, const typename std::conditional<fla
         unsigned long long span_next = 0;
         bool have_next = false;
 
-        TIDK_UNROLL_(TIDK_FLAT_UNROLL)
+#pragma unroll 1 // (unrolled by two -- no register rotation -- and with an L2 prefetch two steps ahead: no gain, the alu pipe is the limiter)
         for (uint32_t st = 0; st < n_steps; st++) {
             const uint4 lo4 = nlo, hi4 = nhi;
             uint4 va4 = nva;
@@ -189,12 +178,6 @@ window_counts_flat_kernel(const FlatJob job, const typename std::conditional<fla
                 pp += kFlatStepBases / 32;
                 nlo = ldg128_stream(pp); nhi = ldg128_stream(pp + kPackWords);
                 if (((valid_blocks >> (4u * (st + 1))) & 0xFu) != 0xFu) nva = ldg128_stream(pp + 2 * kPackWords); // (all valid: va is not read, 0.25 B per base)
-#if TIDK_FLAT_PF
-                if (st + 2 < n_steps && (lane & 7) == 0) { // the step after next: its four lines per plane into L2
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + kFlatStepBases / 32));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + kFlatStepBases / 32 + kPackWords));
-                }
-#endif
             } else {
                 span_next = ticket0 + (unsigned long long)__shfl_sync(0xFFFFFFFFu, t2, 0) * kQueues;
                 have_next = span_next < job.n_spans;

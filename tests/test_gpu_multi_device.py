@@ -11,8 +11,11 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(scope="module", params=[2, 3])
 def mctx(request):
+    import os
     import telomeric_identifier_b200 as T
-    c = T.Context([0] * request.param)
+    # TIDK_TEST_DEVICES="0,1,2": distinct devices on a multi-GPU box (cycled to the requested count); default: device 0 listed n times
+    pool = [int(x) for x in os.environ.get("TIDK_TEST_DEVICES", "0").split(",")]
+    c = T.Context([pool[i % len(pool)] for i in range(request.param)])
     yield c
     c.close()
 

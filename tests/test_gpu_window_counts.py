@@ -397,18 +397,31 @@ def test_async_equals_blocking(ctx):
     batch.free()
 
 
-def test_async_reports_non_ascii_at_wait(ctx):
+def test_async_reports_non_ascii_at_wait(ctx, monkeypatch):
+    """A byte >= 0x80 (the reference fails in str::from_utf8, search.rs:107).  Counting from the ASCII copy, the kernel finds
+    it and the asynchronous call can only report it when it is collected; counting from the resident planes, K1 has seen it
+    at upload and the call itself refuses."""
     import telomeric_identifier_b200 as T
     seq = np.frombuffer(b"ACGT" * 5000, dtype=np.uint8).copy()
     seq[12345] = 0xC3
     off = np.array([0, seq.size], dtype=np.uint64)
     batch = ctx.upload(seq, off)
     po = ctx.pinned_empty(2 * 2 * 8).view(np.uint64)
+    monkeypatch.setenv("TIDK_PLANES_COUNT", "0")
     ctx.window_counts_resident_async(batch, 10000, [b"ACGT"], (po[:2], po[2:]))
     with pytest.raises(T.TidkCudaError) as ei:
         ctx.wait()
     assert ei.value.code == T.api.TIDK_ENONASCII
     ctx.wait()  # the error is reported once
+    monkeypatch.delenv("TIDK_PLANES_COUNT")
+    for q in (b"ACGT", b"TTAGGG"):  # run-time and compile-time flat kernels
+        with pytest.raises(T.TidkCudaError) as ei:
+            ctx.window_counts_resident_async(batch, 10000, [q], (po[:2], po[2:]))
+        assert ei.value.code == T.api.TIDK_ENONASCII
+        with pytest.raises(T.TidkCudaError) as ei:
+            ctx.window_counts_resident(batch, 10000, [q])
+        assert ei.value.code == T.api.TIDK_ENONASCII
+    ctx.wait()
     batch.free()
 
 
