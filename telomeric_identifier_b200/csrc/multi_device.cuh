@@ -17,6 +17,7 @@
 //                                  one contiguous block of the [record][query][window] arrays)
 // included by tidk_cuda.cu (host code only).
 #pragma once
+#include <array>
 #include <thread>
 
 namespace multi {
@@ -123,21 +124,56 @@ inline int window_counts(tidk_ctx *ctx, const uint8_t *seq, const uint64_t *offs
     });
 }
 
-// the groups' run lists, in record order within each k
-inline int merge_runs(tidk_ctx *ctx, std::vector<std::vector<tidk_run>> &part, tidk_run **out_runs, uint64_t *n_runs) {
+// The groups' run lists, in record order within each k.  Every group's list is sorted by (k, record, slice, start) already
+// (explore_post.cuh), so the merged list is, for k = kmin .. kmax, the groups' k-segments one behind the other: segment
+// boundaries by binary search, then every group copies its segments to their places on its own thread and shifts the record
+// numbers on the way (a stable sort of the concatenation took 13 ms on 400 000 runs: longer than the scan it followed).
+// The lists are handed back to their contexts' pools here.
+struct PartRuns { tidk_run *runs = nullptr; uint64_t n = 0; uint32_t r0 = 0; };
+inline int merge_runs(tidk_ctx *ctx, std::vector<PartRuns> &part, tidk_run **out_runs, uint64_t *n_runs) {
+    auto release = [&]() {
+        for (PartRuns &p : part) { if (p.runs) tidk_cuda_free_runs(p.runs); p.runs = nullptr; }
+    };
     uint64_t total = 0;
-    for (auto &p : part) total += p.size();
+    for (auto &p : part) total += p.n;
     *n_runs = total;
     *out_runs = nullptr;
-    if (total == 0) return TIDK_OK;
-    tidk_run *all = tidk::run_list_alloc_plain(total * sizeof(tidk_run));
-    if (!all) { *n_runs = 0; return fail(ctx, TIDK_ENOMEM, "out of host memory"); }
-    uint64_t at = 0;
-    for (auto &p : part) {
-        if (!p.empty()) memcpy(all + at, p.data(), p.size() * sizeof(tidk_run));
-        at += p.size();
+    if (total == 0) { release(); return TIDK_OK; }
+    const size_t bytes = total * sizeof(tidk_run);
+    tidk_run *all = nullptr;
+    if (bytes >= (256u << 10)) { // a pinned block of the first device's pool: reused from call to call, no fresh pages to fault in
+        tidk::ExploreScratch &sc0 = ctx->subs[0]->ex;
+        if (!sc0.run_pool) sc0.run_pool = new tidk::RunBlockPool;
+        cudaSetDevice(ctx->subs[0]->device);
+        all = sc0.run_pool->take(bytes);
     }
-    std::stable_sort(all, all + total, [](const tidk_run &x, const tidk_run &y) { return x.k < y.k; });
+    if (!all) all = tidk::run_list_alloc_plain(bytes);
+    if (!all) { *n_runs = 0; release(); return fail(ctx, TIDK_ENOMEM, "out of host memory"); }
+    const size_t P = part.size();
+    // seg[g][k] = first run of group g with key k (k = 0 .. 256)
+    std::vector<std::array<uint64_t, 257>> seg(P);
+    for (size_t g = 0; g < P; g++) {
+        const tidk_run *r = part[g].runs;
+        for (uint32_t k = 0; k <= 256; k++)
+            seg[g][k] = (uint64_t)(std::lower_bound(r, r + part[g].n, k, [](const tidk_run &x, uint32_t kk) { return (uint32_t)x.k < kk; }) - r);
+    }
+    std::vector<std::array<uint64_t, 256>> dst(P); // where group g's k-segment goes
+    uint64_t at = 0;
+    for (uint32_t k = 0; k < 256; k++)
+        for (size_t g = 0; g < P; g++) { dst[g][k] = at; at += seg[g][k + 1] - seg[g][k]; }
+    auto copy_group = [&](size_t g) {
+        const tidk_run *r = part[g].runs;
+        const uint32_t r0 = part[g].r0;
+        for (uint32_t k = 0; k < 256; k++) {
+            tidk_run *o = all + dst[g][k];
+            for (uint64_t i = seg[g][k]; i < seg[g][k + 1]; i++) { tidk_run t = r[i]; t.record += r0; *o++ = t; }
+        }
+    };
+    std::vector<std::thread> th;
+    for (size_t g = 1; g < P; g++) th.emplace_back(copy_group, g);
+    copy_group(0);
+    for (auto &t : th) t.join();
+    release();
     *out_runs = all;
     return TIDK_OK;
 }
@@ -155,7 +191,7 @@ inline int explore_runs(tidk_ctx *ctx, const uint8_t *seq, const uint64_t *offse
         const double v = std::ceil((double)(offsets[r + 1] - offsets[r]) * distance);
         return 2 * (v > 0 ? (uint64_t)v : 0);
     });
-    std::vector<std::vector<tidk_run>> part((size_t)world);
+    std::vector<PartRuns> part((size_t)world);
     const int rc = on_all(ctx, [&](int g, tidk_ctx *sub) -> int {
         const uint32_t r0 = cut[(size_t)g], r1 = cut[(size_t)g + 1];
         if (r1 <= r0) return TIDK_OK;
@@ -165,12 +201,13 @@ inline int explore_runs(tidk_ctx *ctx, const uint8_t *seq, const uint64_t *offse
         uint64_t n = 0;
         const int rc2 = tidk_cuda_explore_runs(sub, seq + offsets[r0], loc_off.data(), r1 - r0, distance, kmin, kmax, threshold, &runs, &n);
         if (rc2) return rc2;
-        part[(size_t)g].assign(runs, runs + n);
-        for (tidk_run &r : part[(size_t)g]) r.record += r0;
-        tidk_cuda_free_runs(runs);
+        part[(size_t)g].runs = runs; part[(size_t)g].n = n; part[(size_t)g].r0 = r0;
         return TIDK_OK;
     });
-    if (rc) return rc;
+    if (rc) {
+        for (PartRuns &p : part) if (p.runs) tidk_cuda_free_runs(p.runs);
+        return rc;
+    }
     return merge_runs(ctx, part, out_runs, n_runs);
 }
 
@@ -278,7 +315,7 @@ inline int explore_runs_resident(tidk_ctx *ctx, const tidk_seqbuf *b, double dis
     *out_runs = nullptr; *n_runs = 0;
     if (!is_multi_buf(ctx, b)) return fail(ctx, TIDK_EARG, "the batch was not uploaded through this multi-device context");
     const size_t world = ctx->subs.size();
-    std::vector<std::vector<tidk_run>> part(world);
+    std::vector<PartRuns> part(world);
     std::vector<float> ms(world, 0.f);
     std::vector<uint32_t> nl(world, 0);
     const int rc = on_all(ctx, [&](int g, tidk_ctx *sub) -> int {
@@ -288,12 +325,13 @@ inline int explore_runs_resident(tidk_ctx *ctx, const tidk_seqbuf *b, double dis
         uint64_t n = 0;
         const int rc2 = tidk_cuda_explore_runs_resident(sub, b->parts[(size_t)g], distance, kmin, kmax, threshold, &runs, &n, &ms[(size_t)g], &nl[(size_t)g]);
         if (rc2) return rc2;
-        part[(size_t)g].assign(runs, runs + n);
-        for (tidk_run &r : part[(size_t)g]) r.record += r0;
-        tidk_cuda_free_runs(runs);
+        part[(size_t)g].runs = runs; part[(size_t)g].n = n; part[(size_t)g].r0 = r0;
         return TIDK_OK;
     });
-    if (rc) return rc;
+    if (rc) {
+        for (PartRuns &p : part) if (p.runs) tidk_cuda_free_runs(p.runs);
+        return rc;
+    }
     float mx = 0.f, scan = 0.f, post = 0.f;
     uint32_t sum = 0;
     for (size_t g = 0; g < world; g++) {

@@ -202,6 +202,10 @@ int ensure(tidk_ctx *ctx, DevBuf &b, size_t bytes) {
 }
 
 constexpr size_t kSeqPad = 8192; // zeroed bytes behind the data: block loads never leave the buffer
+// 1 KiB blocks that K1 converts: the data and as many whole blocks of the zero padding as lie INSIDE it (the last block
+// starts below total + 1024 - 1 + 6 KiB and ends inside the 8 KiB that were zeroed; one block more would read up to
+// 1 023 bytes of whatever the allocation held before -- a stale byte >= 0x80 there made the batch "non-ASCII")
+inline uint64_t planes_blocks(uint64_t total) { return (total + 1023) / 1024 + kSeqPad / 1024 - 1; }
 
 static int pack_threads() {
     if (const char *e = getenv("TIDK_PACK_THREADS")) return atoi(e);
@@ -332,7 +336,7 @@ void seqbuf_release(tidk_seqbuf *b) {
 // of an upload waits for the copy anyway) and records the device time.
 int seqbuf_build_planes(tidk_ctx *ctx, tidk_seqbuf *b) {
     b->planes_ready = false;
-    const uint64_t n_blocks = (b->total + 1023) / 1024 + kSeqPad / 1024; // the data and the zero padding behind it
+    const uint64_t n_blocks = planes_blocks(b->total); // the data and the zero padding behind it
     const uint64_t n_chunks = (n_blocks * 32 + kPackWords - 1) / kPackWords;
     const size_t plane_bytes = (size_t)n_chunks * 3 * kPackWords * 4, bits_bytes = ((size_t)n_blocks + 2) * 4;
     auto grow = [&](uint32_t *&p, size_t &cap, size_t need) -> int {
@@ -858,7 +862,7 @@ static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint3
         fjob.spans = nullptr; // set by the launch (need_spans)
         fjob.out_fwd = (unsigned long long *)d_fwd; fjob.out_rev = (unsigned long long *)d_rev;
         fjob.window = window; fjob.total = buf->total; fjob.n_spans = n_spans; fjob.span0 = 0;
-        fjob.n_vblocks = (buf->total + 1023) / 1024 + kSeqPad / 1024;
+        fjob.n_vblocks = planes_blocks(buf->total);
         fjob.n_records = nrec; fjob.nq_total = nq;
     }
 

@@ -34,7 +34,10 @@
 namespace tidk {
 
 constexpr uint32_t kFlatStepBases = 4096;  // 128 words: four per lane
-constexpr uint32_t kFlatSpanSteps = 8;
+#ifndef TIDK_FLAT_SPAN_STEPS
+#define TIDK_FLAT_SPAN_STEPS 8
+#endif
+constexpr uint32_t kFlatSpanSteps = TIDK_FLAT_SPAN_STEPS; // (1, 2, 4 or 8: a span's blocks are one validbits word per lane)
 constexpr uint32_t kFlatSpanBases = kFlatStepBases * kFlatSpanSteps; // 32 Ki bases = 32 plane blocks = one validbits line
 
 struct __align__(32) SpanDesc { // the window that holds the first base of a span
