@@ -18,9 +18,72 @@
 // included by tidk_cuda.cu (host code only).
 #pragma once
 #include <array>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 
 namespace multi {
+
+// One parked host thread per device but the first (which the caller's thread serves).  A call is fanned out by bumping a
+// generation counter; the workers spin on it for a short while after each job -- a loop of asynchronous passes then finds
+// them awake and a dispatch costs about a microsecond -- and sleep on a condition variable otherwise.  (Spawning the
+// threads per call cost 100-150 us on an 8-device context: three times the kernel of an eighth of the C4 genome.)
+struct Workers {
+    std::vector<std::thread> th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::atomic<uint64_t> gen{0};
+    std::atomic<int> pending{0};
+    std::atomic<bool> quit{false};
+    std::function<void(int)> job;
+    explicit Workers(int n) {
+        for (int g = 1; g < n; g++) th.emplace_back([this, g] { loop(g); });
+    }
+    ~Workers() {
+        quit.store(true);
+        { std::lock_guard<std::mutex> l(mu); gen.fetch_add(1); }
+        cv.notify_all();
+        for (auto &t : th) t.join();
+    }
+    void loop(int g) {
+        uint64_t seen = 0;
+        for (;;) {
+            uint64_t cur = gen.load(std::memory_order_acquire);
+            if (cur == seen) { // spin briefly, then sleep
+                const auto t0 = std::chrono::steady_clock::now();
+                while ((cur = gen.load(std::memory_order_acquire)) == seen) {
+                    if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(200)) {
+                        std::unique_lock<std::mutex> l(mu);
+                        cv.wait(l, [&] { return gen.load(std::memory_order_acquire) != seen; });
+                        cur = gen.load(std::memory_order_acquire);
+                        break;
+                    }
+                }
+            }
+            seen = cur;
+            if (quit.load()) return;
+            job(g);
+            pending.fetch_sub(1, std::memory_order_acq_rel);
+        }
+    }
+    // f(g) for g = 0 .. n - 1, g = 0 on the calling thread; returns when all are done.  Not re-entrant (a tidk_ctx is single-caller).
+    void run(const std::function<void(int)> &f) {
+        if (th.empty()) { f(0); return; }
+        job = f;
+        pending.store((int)th.size(), std::memory_order_release);
+        { std::lock_guard<std::mutex> l(mu); gen.fetch_add(1, std::memory_order_release); }
+        cv.notify_all();
+        f(0);
+        while (pending.load(std::memory_order_acquire) != 0) { /* the others finish within microseconds of the caller's share */
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+    }
+};
 
 struct Piece { uint32_t rec; uint64_t first, n; };
 
@@ -68,10 +131,8 @@ template <class F>
 inline int on_all(tidk_ctx *ctx, F f) {
     const size_t n = ctx->subs.size();
     std::vector<int> rc(n, TIDK_OK);
-    std::vector<std::thread> th;
-    for (size_t g = 1; g < n; g++) th.emplace_back([&, g] { rc[g] = f((int)g, ctx->subs[g]); });
-    rc[0] = f(0, ctx->subs[0]);
-    for (auto &t : th) t.join();
+    if (!ctx->workers) ctx->workers = new Workers((int)n);
+    ctx->workers->run([&](int g) { rc[(size_t)g] = f(g, ctx->subs[(size_t)g]); });
     for (size_t g = 0; g < n; g++)
         if (rc[g] != TIDK_OK) {
             ctx->err = "device " + std::to_string(ctx->subs[g]->device) + ": " + ctx->subs[g]->err;
@@ -246,10 +307,15 @@ inline void seqbuf_free(tidk_ctx *ctx, tidk_seqbuf *b) {
 }
 
 // first element of record r in the [record][query][window] arrays
-inline std::vector<uint64_t> out_base(const tidk_seqbuf *b, uint64_t window, uint32_t nq) {
-    std::vector<uint64_t> ob((size_t)b->n_records + 1, 0);
-    for (uint32_t r = 0; r < b->n_records; r++) ob[r + 1] = ob[r] + n_windows(b->h_off[r + 1] - b->h_off[r], window) * nq;
-    return ob;
+// first output element of every record (cached per batch for the last (window, query count): a loop of passes asks again and again)
+inline const std::vector<uint64_t> &out_base(const tidk_seqbuf *b, uint64_t window, uint32_t nq) {
+    if (b->ob_window != window || b->ob_nq != nq || b->ob_cache.size() != (size_t)b->n_records + 1) {
+        std::vector<uint64_t> &ob = b->ob_cache;
+        ob.assign((size_t)b->n_records + 1, 0);
+        for (uint32_t r = 0; r < b->n_records; r++) ob[r + 1] = ob[r] + n_windows(b->h_off[r + 1] - b->h_off[r], window) * nq;
+        b->ob_window = window; b->ob_nq = nq;
+    }
+    return b->ob_cache;
 }
 
 inline bool is_multi_buf(tidk_ctx *ctx, const tidk_seqbuf *b) { return b && b->parts.size() == ctx->subs.size(); }
@@ -260,7 +326,7 @@ inline int window_counts_resident(tidk_ctx *ctx, const tidk_seqbuf *b, uint64_t 
     if (kernel_launches) *kernel_launches = 0;
     if (!is_multi_buf(ctx, b)) return fail(ctx, TIDK_EARG, "the batch was not uploaded through this multi-device context");
     if (window == 0 || nq == 0 || !out_fwd || !out_rev) return fail(ctx, TIDK_EARG, "window must be > 0, at least one query, outputs not NULL");
-    const std::vector<uint64_t> ob = out_base(b, window, nq);
+    const std::vector<uint64_t> &ob = out_base(b, window, nq);
     std::vector<float> ms(ctx->subs.size(), 0.f);
     std::vector<uint32_t> nl(ctx->subs.size(), 0);
     auto one = [&](int g, tidk_ctx *sub) -> int {
@@ -270,14 +336,10 @@ inline int window_counts_resident(tidk_ctx *ctx, const tidk_seqbuf *b, uint64_t 
         return tidk_cuda_window_counts_resident(sub, b->parts[(size_t)g], window, queries, qlens, nq, out_fwd + ob[r0], out_rev + ob[r0], &ms[(size_t)g], &nl[(size_t)g]);
     };
     int rc = TIDK_OK;
-    if (async) { // the calls only enqueue: issued from this thread, one after the other
-        for (size_t g = 0; g < ctx->subs.size() && rc == TIDK_OK; g++) {
-            rc = one((int)g, ctx->subs[g]);
-            if (rc) ctx->err = ctx->subs[g]->err;
-        }
-        return rc;
-    }
+    // (asynchronous calls only enqueue, but an enqueue is 10-20 us of driver calls per device: on the parked threads too --
+    // issued one after the other from the caller's thread, eight devices cost 165 us per pass against a 49 us kernel)
     rc = on_all(ctx, one);
+    if (async) return rc;
     float mx = 0.f;
     uint32_t sum = 0;
     for (size_t g = 0; g < ms.size(); g++) { mx = std::max(mx, ms[g]); sum += nl[g]; }

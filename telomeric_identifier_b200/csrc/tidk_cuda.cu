@@ -56,6 +56,9 @@ struct tidk_seqbuf {
     // a batch of a multi-device context (multi_device.cuh): one part per device, records [cut[g], cut[g + 1]) in part g
     std::vector<tidk_seqbuf *> parts;
     std::vector<uint32_t> cut;
+    mutable std::vector<uint64_t> ob_cache; // first output element of every record for (ob_window, ob_nq): multi_device.cuh out_base
+    mutable uint64_t ob_window = 0;
+    mutable uint32_t ob_nq = 0;
 };
 
 // Packer threads of the host-packed upload, kept parked between calls: creating and joining 15 threads per call
@@ -117,6 +120,8 @@ class PackPool {
     bool stop_ = false;
 };
 
+namespace multi { struct Workers; }
+
 struct tidk_ctx {
     int device = 0;
     int sm_count = 148;
@@ -144,11 +149,13 @@ struct tidk_ctx {
     uint32_t *h_flags = nullptr;    // pinned + mapped: the window kernels store the (rare) error flag straight into host memory
     uint32_t *d_flags = nullptr;    // device view of h_flags
     ExploreScratch ex;
-    // window counts, asynchronous form: two device output buffers used alternately; the counts of call i leave on
-    // the copy stream while the kernel of call i + 1 runs
+    // window counts, asynchronous form: three device output buffers used in turn; the counts of call i leave on
+    // the copy stream while the kernel of call i + 1 runs -- and zeroes the buffer of call i + 2 on the side (flat kernels)
     struct WinSlot { cudaEvent_t k0 = nullptr, k1 = nullptr, done = nullptr; bool busy = false; uint32_t launches = 0; };
-    WinSlot wslot[2];
-    DevBuf out_dev[2];
+    static constexpr int kWinSlots = 3;
+    WinSlot wslot[kWinSlots];
+    DevBuf out_dev[kWinSlots];
+    size_t out_zero_bytes[kWinSlots] = {0, 0, 0}; // leading bytes of out_dev[s] known to be zero (written by the previous flat launch)
     cudaStream_t copy_st = nullptr;
     uint32_t wslot_next = 0;
     float pending_kernel_ms = 0.f;     // device time / launches of the calls retired since the last tidk_cuda_wait
@@ -158,6 +165,7 @@ struct tidk_ctx {
     uint64_t next_buf_id = 1;
     // multi-device context: one single-device context per device, this one holds no device state of its own
     std::vector<tidk_ctx *> subs;
+    multi::Workers *workers = nullptr; // parked host threads, one per device but the first (multi_device.cuh)
     // work items cached for (sequence batch, window, query count): several clades or output
     // formats over one uploaded genome reuse them
     uint64_t items_buf_id = 0, items_window = 0, items_n = 0, items_nwin = 0;
@@ -621,6 +629,7 @@ int tidk_cuda_create(const int *device_ids, int n_devices, tidk_ctx **out) {
 void tidk_cuda_destroy(tidk_ctx *ctx) {
     if (!ctx) return;
     if (!ctx->subs.empty()) {
+        delete ctx->workers; // joins the parked threads
         for (tidk_ctx *sub : ctx->subs) tidk_cuda_destroy(sub);
         delete ctx;
         return;
@@ -640,7 +649,7 @@ void tidk_cuda_destroy(tidk_ctx *ctx) {
         if (L.ev[1]) cudaEventDestroy(L.ev[1]);
         if (L.st) cudaStreamDestroy(L.st);
     }
-    for (int s = 0; s < 2; s++) {
+    for (int s = 0; s < tidk_ctx::kWinSlots; s++) {
         if (ctx->wslot[s].busy) cudaEventSynchronize(ctx->wslot[s].done);
         for (cudaEvent_t e : {ctx->wslot[s].k0, ctx->wslot[s].k1, ctx->wslot[s].done})
             if (e) cudaEventDestroy(e);
@@ -729,7 +738,7 @@ static int retire_slot(tidk_ctx *ctx, int s) {
 
 static int drain_slots(tidk_ctx *ctx) {
     int rc = TIDK_OK;
-    for (int s = 0; s < 2; s++) {
+    for (int s = 0; s < tidk_ctx::kWinSlots; s++) {
         const int r = retire_slot(ctx, s);
         if (r && !rc) rc = r;
     }
@@ -784,7 +793,7 @@ static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint3
     // allocation each, forward counts then reverse counts, so that a caller whose two output arrays are adjacent
     // in memory gets both with a single copy.
     if (!async && (rc = drain_slots(ctx))) return rc; // a blocking call behind asynchronous ones: collect those first
-    const int slot = (int)(ctx->wslot_next & 1u);
+    const int slot = (int)(ctx->wslot_next % (uint32_t)tidk_ctx::kWinSlots);
     tidk_ctx::WinSlot &S = ctx->wslot[slot];
     if ((rc = retire_slot(ctx, slot))) return rc;
     if (!S.k0) {
@@ -794,6 +803,7 @@ static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint3
     }
     if (async && !ctx->copy_st) CU(ctx, cudaStreamCreateWithFlags(&ctx->copy_st, cudaStreamNonBlocking));
     if (2 * n_out * 8 > ctx->out_dev[slot].cap) { // (re)allocation: nothing of this slot is in flight (retired above)
+        ctx->out_zero_bytes[slot] = 0;
         if ((rc = ensure(ctx, ctx->out_dev[slot], 2 * n_out * 8))) return rc;
     }
     constexpr size_t kCounterBytes = 2 * (size_t)kQueues * kQueueStride * 8; // two sets of queue counters (each launch zeroes the other set)
@@ -817,9 +827,12 @@ static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint3
     // adds into pre-zeroed counters.
     const bool flat_ok = packed && packed == buf->d_planes && buf->planes_ready && split == 0 && buf->d_validbits &&
                          !(getenv("TIDK_FLAT") && atoi(getenv("TIDK_FLAT")) == 0);
-    if (spw > 1 || flat_ok) {
+    if ((spw > 1 || flat_ok) && ctx->out_zero_bytes[slot] < 2 * n_out * 8) { // (a flat launch of the previous call may have zeroed it already)
         CU(ctx, cudaMemsetAsync(d_fwd, 0, 2 * n_out * 8, ctx->stream));
     }
+    ctx->out_zero_bytes[slot] = 0; // this call writes into it
+    bool next_zeroed_out = false;  // this call's first flat launch zeroes the NEXT slot's buffer on the side
+    int zeroing_slot = -1;
 
     uint32_t launches = 0;
     CU(ctx, cudaEventRecord(S.k0, ctx->stream));
@@ -963,6 +976,18 @@ static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint3
             FlatJob fj = fjob;
             fj.spans = (const SpanDesc *)ctx->spans.p;
             fj.q = q;
+            if (!next_zeroed_out) { // one memset node less per pass: 2-4 us of a 40 us pass on an eighth of the C4 genome
+                const int nslot = (slot + 1) % tidk_ctx::kWinSlots;
+                if ((rc = retire_slot(ctx, nslot))) return rc; // its counts have left the device
+                if (2 * n_out * 8 > ctx->out_dev[nslot].cap) {
+                    ctx->out_zero_bytes[nslot] = 0;
+                    if ((rc = ensure(ctx, ctx->out_dev[nslot], 2 * n_out * 8))) return rc;
+                }
+                fj.zero_ptr = (uint4 *)ctx->out_dev[nslot].p;
+                fj.zero_n16 = n_out; // 2 * n_out * 8 bytes
+                zeroing_slot = nslot;
+                next_zeroed_out = true;
+            }
             fj.work_counter = next_counter(); fj.next_counter = next_zeroed;
             if (FlatLaunchFn ff = find_static_flat(f, qlens[q])) {
                 ff(fj, env);
@@ -979,6 +1004,7 @@ static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint3
                 launch_flat_runtime((int)qlens[q], fj, rp, env);
             }
             launches++;
+            if (zeroing_slot >= 0) { ctx->out_zero_bytes[zeroing_slot] = 2 * n_out * 8; zeroing_slot = -1; } // (enqueued: true from here on in stream order)
             continue;
         }
         LaunchFn fn = find_static(f, qlens[q], false), fnp = packed ? find_static(f, qlens[q], true) : nullptr;
@@ -1055,7 +1081,7 @@ static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint3
     CU(ctx, cudaEventRecord(S.done, cst));
     S.busy = true;
     S.launches = launches;
-    ctx->wslot_next ^= 1u;
+    ctx->wslot_next = (ctx->wslot_next + 1u) % (uint32_t)tidk_ctx::kWinSlots;
     ctx->counters_dirty = false; // every launch of this call is enqueued; the counters are handed on in stream order
     if (async) return TIDK_OK;
     const float ms0 = ctx->pending_kernel_ms;

@@ -87,6 +87,8 @@ struct FlatJob {
     unsigned long long *work_counter, *next_counter; // as in window_counts.cuh: kQueues ticket counters per set
     uint64_t window, total, n_spans, span0;
     uint64_t n_vblocks;        // validbits entries that exist (blocks behind them count as not valid)
+    uint4 *zero_ptr;           // zero_n16 16-byte words to zero on the side (the output buffer of the NEXT call), or nullptr
+    uint64_t zero_n16;
     uint32_t n_records, nq_total, q; // this launch's query index
 };
 
@@ -120,6 +122,10 @@ window_counts_flat_kernel(const FlatJob job, const typename std::conditional<fla
     const unsigned long long n_warps = (unsigned long long)gridDim.x * kWarpsPerBlock;
     const unsigned long long gw = (unsigned long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (blockIdx.x == 0 && threadIdx.x < kQueues) job.next_counter[threadIdx.x * kQueueStride] = 0ull; // for the launch after this one
+    if (job.zero_ptr) { // the counters the next call will add into: no memset node between two passes
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < job.zero_n16; i += (uint64_t)gridDim.x * blockDim.x) job.zero_ptr[i] = z;
+    }
     unsigned long long span = gw;
     if (span >= job.n_spans) return;
     uint32_t *const queue = reinterpret_cast<uint32_t *>(job.work_counter + (gw & (kQueues - 1)) * kQueueStride);
