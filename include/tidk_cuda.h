@@ -123,8 +123,9 @@ int tidk_cuda_window_counts_resident(tidk_ctx *ctx, const tidk_seqbuf *buf, uint
                                      float *kernel_ms, uint32_t *kernel_launches);
 
 /* Asynchronous form of tidk_cuda_window_counts_resident: the kernels are enqueued and the call returns; the counts
- * leave the device on a second stream while the next call's kernels run (two output buffers are used alternately, so
- * up to two calls are in flight and a third first waits for the oldest).  out_fwd / out_rev must stay valid -- and
+ * leave the device on a second stream while the next call's kernels run (three device output buffers are used in turn:
+ * a call first waits for the counts of the call two before it to have left the device; its kernel also zeroes the
+ * counters of the call after it).  The caller needs two sets of output arrays, used alternately.  out_fwd / out_rev must stay valid -- and
  * should be tidk_cuda_host_alloc memory, or the copy is staged -- until tidk_cuda_wait returns.  A single-threaded
  * host (search.rs:57 is one sequential loop) keeps the device busy this way: the per-call cost of a blocking call
  * (copy of the counts + wake-up of the waiting thread, 40-80 us) is as long as a whole launch on a sharded genome. */

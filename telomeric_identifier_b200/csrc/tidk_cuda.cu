@@ -833,6 +833,16 @@ static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint3
     ctx->out_zero_bytes[slot] = 0; // this call writes into it
     bool next_zeroed_out = false;  // this call's first flat launch zeroes the NEXT slot's buffer on the side
     int zeroing_slot = -1;
+    const int nslot = (slot + 1) % tidk_ctx::kWinSlots;
+    bool nslot_ready = false;
+    if (flat_ok) { // (before the first timed event: an allocation here must not sit between the events)
+        if ((rc = retire_slot(ctx, nslot))) return rc; // its counts have left the device
+        if (2 * n_out * 8 > ctx->out_dev[nslot].cap) {
+            ctx->out_zero_bytes[nslot] = 0;
+            if ((rc = ensure(ctx, ctx->out_dev[nslot], 2 * n_out * 8))) return rc;
+        }
+        nslot_ready = true;
+    }
 
     uint32_t launches = 0;
     CU(ctx, cudaEventRecord(S.k0, ctx->stream));
@@ -976,19 +986,12 @@ static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint3
             FlatJob fj = fjob;
             fj.spans = (const SpanDesc *)ctx->spans.p;
             fj.q = q;
-            if (!next_zeroed_out) { // one memset node less per pass: 2-4 us of a 40 us pass on an eighth of the C4 genome
-                const int nslot = (slot + 1) % tidk_ctx::kWinSlots;
-                if ((rc = retire_slot(ctx, nslot))) return rc; // its counts have left the device
-                if (2 * n_out * 8 > ctx->out_dev[nslot].cap) {
-                    ctx->out_zero_bytes[nslot] = 0;
-                    if ((rc = ensure(ctx, ctx->out_dev[nslot], 2 * n_out * 8))) return rc;
-                }
+            if (!next_zeroed_out && nslot_ready) { // one memset node less per pass: 2-4 us of a 40 us pass on an eighth of the C4 genome
                 fj.zero_ptr = (uint4 *)ctx->out_dev[nslot].p;
                 fj.zero_n16 = n_out; // 2 * n_out * 8 bytes
                 zeroing_slot = nslot;
                 next_zeroed_out = true;
             }
-            fj.work_counter = next_counter(); fj.next_counter = next_zeroed;
             if (FlatLaunchFn ff = find_static_flat(f, qlens[q])) {
                 ff(fj, env);
             } else if ((ff = find_static_flat(rcbuf, qlens[q]))) { // the listed motif is this query's reverse complement: swap the outputs

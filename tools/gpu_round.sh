@@ -10,6 +10,6 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --
 echo "launch list rc=$?"
 unset TIDK_BENCH_PASSES
 timeout 300 python tools/prof_r02.py > gpurun_out/r02_prof_plain.log 2>&1 &&
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'explore_vertical_kernel|window_counts_kernel|window_counts_flat_kernel|explore_planes_kernel|planes_build' -c 30 -o gpurun_out/r02_prof python tools/prof_r02.py > gpurun_out/r02_ncu_full.log 2>&1
+timeout 1200 ncu --set full --clock-control none -k regex:"explore_vertical_kernel|window_counts_kernel|window_counts_flat_kernel|explore_planes_kernel|planes_build" -c 26 -o gpurun_out/r02_prof python tools/prof_r02.py > gpurun_out/r02_ncu_full.log 2>&1
 echo "full capture rc=$?"
 cat gpurun_out/r02_prof_plain.log

@@ -31,4 +31,11 @@ with T.Context(0) as ctx:
         f, r = ctx.window_counts_resident(b, 10000, [b"GATTACAGATTA"])
         print(f"C4 {src} runtime 12-mer kernel_ms={ctx.last_kernel_ms:.4f}", flush=True)
     os.environ.pop("TIDK_PLANES_COUNT", None)
+    # the fused clade kernel (find --clade Hymenoptera: 15 repeats in one pass, per-window form on the resident planes)
+    from telomeric_identifier_b200 import clades
+    db = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "clades_min.csv")
+    hym = [r.encode() for r in clades.return_telomere_sequence("Hymenoptera", db)]
+    for _ in range(2):
+        f, r = ctx.window_counts_resident(b, 10000, hym)
+        print(f"C4 find --clade Hymenoptera ({len(hym)} repeats) kernel_ms={ctx.last_kernel_ms:.4f} launches={ctx.last_kernel_launches}", flush=True)
     b.free()
