@@ -992,6 +992,7 @@ static int window_counts_impl(tidk_ctx *ctx, const tidk_seqbuf *buf, const uint3
                 zeroing_slot = nslot;
                 next_zeroed_out = true;
             }
+            fj.work_counter = next_counter(); fj.next_counter = next_zeroed;
             if (FlatLaunchFn ff = find_static_flat(f, qlens[q])) {
                 ff(fj, env);
             } else if ((ff = find_static_flat(rcbuf, qlens[q]))) { // the listed motif is this query's reverse complement: swap the outputs

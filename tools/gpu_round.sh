@@ -1,6 +1,6 @@
 #!/bin/bash
 # full GPU pass of the current build: tests, bench line, reference arm, launch list, full ncu capture of the hot kernels
-mkdir -p gpurun_out
+mkdir -p gpurun_out; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 (timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/r02_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02_pytest.log); tail -4 gpurun_out/r02_pytest.log | cut -c1-200
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/r02_bench_n1.json 2> gpurun_out/r02_bench_n1.err; echo "bench rc=$?"
 timeout 200 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r02_bench_ref.json 2> gpurun_out/r02_bench_ref.err
