@@ -308,9 +308,10 @@ def fasta_e2e(pieces_all, world, local):
             best = (dt, json.loads(stats[-1]) if stats else {})
     tsv = os.path.join(d, "c4_telomeric_repeat_windows.tsv")
     out = {"value": int(seq.size) / best[0] / 1e9, "unit": UNIT, "wall_s": best[0], "fasta_bytes": os.path.getsize(fa),
-           "tsv_bytes": os.path.getsize(tsv), "devices": world,
-           "what": "fresh `tidk search` process: FASTA parse (mmap, multi-threaded) + CUDA context creation + upload + count + format + "
-                   "write; page cache warm; best of 2", "breakdown": best[1], "fasta_write_s_untimed": wrote_s}
+           "tsv_bytes": os.path.getsize(tsv), "devices_offered": world, "devices_used": best[1].get("devices_used", world),
+           "what": "fresh `tidk search --gpus N` process: FASTA parse (mmap, multi-threaded) + CUDA context creation + upload + count + format + "
+                   "write; page cache warm; best of 2.  --gpus N means up to N devices: the driver takes one device per 4 Gb of work (a "
+                   "context costs ~0.25 s to create and as much to tear down; TIDK_GPUS_EXACT=1 forces N)", "breakdown": best[1], "fasta_write_s_untimed": wrote_s}
     for f in (fa, tsv):
         try:
             os.unlink(f)

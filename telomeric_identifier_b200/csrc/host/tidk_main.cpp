@@ -232,6 +232,20 @@ std::vector<std::vector<Piece>> plan_shards(const std::vector<uint64_t> &offsets
     return plans;
 }
 
+// --gpus N means "up to N devices": a CUDA context costs about a quarter of a second to create and as much to tear down, per
+// device and one after the other, while a device counts 3 Gb in 0.1 s end to end -- on the 3.1 Gb genome eight devices took
+// 4.1 s where one takes 0.7.  One device per 4 Gb of work, at most N (TIDK_GPUS_EXACT=1, or the one-GPU test switch
+// TIDK_GPUS_SAME_DEVICE=1, keep exactly N).
+int devices_for(const Args &a, uint64_t work_bases) {
+    if (a.gpus <= 1) return 1;
+    const bool exact = (getenv("TIDK_GPUS_EXACT") && atoi(getenv("TIDK_GPUS_EXACT")) != 0) ||
+                       (getenv("TIDK_GPUS_SAME_DEVICE") && atoi(getenv("TIDK_GPUS_SAME_DEVICE")) != 0);
+    if (exact) return a.gpus;
+    const uint64_t per_device = 4000000000ull;
+    const uint64_t want = (work_bases + per_device - 1) / per_device;
+    return (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)a.gpus, want));
+}
+
 void sharded_counts(const Args &a, const Fasta &fa, const std::vector<const char *> &qp, const std::vector<uint32_t> &ql,
                     std::vector<uint64_t> &f, std::vector<uint64_t> &r, float *kernel_ms_max) {
     const int world = a.gpus;
@@ -369,9 +383,11 @@ int run_counts(const Args &a, const std::vector<std::string> &queries, const std
     for (auto &q : queries) { qp.push_back(q.c_str()); ql.push_back((uint32_t)q.size()); }
     float ms = 0;
     uint32_t nl = 0;
-    if (a.gpus > 1) {
-        sharded_counts(a, fa, qp, ql, f, r, &ms);
-        nl = (uint32_t)a.gpus;
+    Args a_eff = a;
+    a_eff.gpus = devices_for(a, (uint64_t)fa.seq.size() * queries.size());
+    if (a_eff.gpus > 1) {
+        sharded_counts(a_eff, fa, qp, ql, f, r, &ms);
+        nl = (uint32_t)a_eff.gpus;
     } else {
         // host-pointer entry point: the two-ended upload (2-bit planes packed by the host cores from the back, ASCII
         // by DMA from the front) moves a parsed genome several times faster than one copy from pageable memory
@@ -388,10 +404,10 @@ int run_counts(const Args &a, const std::vector<std::string> &queries, const std
         auto s = [](auto x, auto y) { return std::chrono::duration<double>(y - x).count(); };
         fprintf(stderr, "{\"bases\": %zu, \"kernel_ms\": %.4f, \"kernel_launches\": %u, \"kernel_gbases_s\": %.1f, "
                         "\"parse_s\": %.3f, \"wait_for_context_s\": %.3f, \"upload_and_count_s\": %.3f, \"write_s\": %.3f, "
-                        "\"end_to_end_gbases_s\": %.3f}\n",
+                        "\"end_to_end_gbases_s\": %.3f, \"devices_used\": %d}\n",
                 fa.seq.size(), ms, nl, ms > 0 ? fa.seq.size() / (ms * 1e-3) / 1e9 : 0.0, s(t0, t1), s(t1, t_ready), s(t_ready, t2),
                 s(t2, t3),
-                fa.seq.size() / s(t0, t3) / 1e9);
+                fa.seq.size() / s(t0, t3) / 1e9, a_eff.gpus);
     }
     return 0;
 }
@@ -478,6 +494,7 @@ int cmd_explore(const Args &a) { // explore::explore, explore.rs:20-149
     float ms = 0;
     uint32_t nl = 0;
     uint64_t n = 0;
+    bool multi_dev = false;
     if (a.gpus < 1 || a.gpus > 64) die("--gpus must be between 1 and 64", 1);
     if (kmax >= kmin && kmin > 0) {
         ctx.ready();
@@ -486,11 +503,14 @@ int cmd_explore(const Args &a) { // explore::explore, explore.rs:20-149
         const uint64_t thr = a.threshold < 0 ? (uint64_t)(int64_t)a.threshold : (uint64_t)a.threshold;
         std::vector<tidk_run> sharded;
         tidk_run *runs = nullptr;
-        if (a.gpus > 1) {
-            sharded = sharded_explore(a, fa, kmin, kmax, thr);
+        Args a_eff = a; // (explore's work: the scanned slices, 2 * ceil(d * len) per record)
+        a_eff.gpus = devices_for(a, (uint64_t)(2.0 * a.distance * (double)fa.seq.size()) + 1);
+        multi_dev = a_eff.gpus > 1;
+        if (multi_dev) {
+            sharded = sharded_explore(a_eff, fa, kmin, kmax, thr);
             runs = sharded.data();
             n = sharded.size();
-            nl = (uint32_t)a.gpus;
+            nl = (uint32_t)a_eff.gpus;
         } else {
             // the host-pointer entry point uploads only the chromosome-end slices when --distance is small
             ctx.check(tidk_cuda_explore_runs(ctx.h, fa.seq.data(), fa.offsets.data(), (uint32_t)fa.ids.size(), a.distance, kmin, kmax,
@@ -515,7 +535,7 @@ int cmd_explore(const Args &a) { // explore::explore, explore.rs:20-149
             labels.push_back(lab);
             counts.push_back((long long)((r.end - r.start) / r.k));
         }
-        if (a.gpus <= 1) tidk_cuda_free_runs(runs);
+        if (!multi_dev) tidk_cuda_free_runs(runs);
         rows = estimates(labels, counts);
     }
     fprintf(stderr, "[+]\tFinished searching genome\n[+]\tGenerating output\n");
