@@ -48,6 +48,12 @@ with T.Context(0) as ctx:
             of, orr = O.window_counts(seq, off, W, qs, False)
             if not ((f == of).all() and (r == orr).all()):
                 bad += 1; print("WINDOW MISMATCH", seed, W, qs)
+            if seq.size:  # the resident path: K1 planes + the flat kernels (window_counts_flat.cuh)
+                bt = ctx.upload(seq, off)
+                f2, r2 = ctx.window_counts_resident(bt, W, qs)
+                if not (np.array_equal(f2, of) and np.array_equal(r2, orr)):
+                    bad += 1; print("RESIDENT WINDOW MISMATCH", seed, W, qs)
+                bt.free()
     # ---- the upload paths on one bigger batch (forced packing, few threads so the DMA takes a share)
     ids, seq, off = synth.config4(scale=0.015)
     of, orr = O.window_counts(seq, off, 10000, [b"TTAGGG"], False, threads=4)

@@ -159,3 +159,19 @@ def test_cli_sharded_over_several_contexts(genome, gpus):
                         "--gpus", str(gpus)], capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stderr
     assert r.stdout == O.explore_text(seqs, 0.05, 5, 12, 20, literal=True)
+
+
+@pytest.mark.gpu
+def test_cli_gpus_is_an_upper_bound(genome):
+    """`--gpus N` takes up to N devices, one per 4 Gb of work (creating a CUDA context costs more than counting a small
+    genome): a small FASTA with `--gpus 8` runs on ONE device -- also on a one-GPU box -- and writes the same file."""
+    import json
+    d, fa, ids, seq, off, seqs = genome
+    out = str(d / "g8_auto")
+    env = {k: v for k, v in os.environ.items() if k not in ("TIDK_GPUS_SAME_DEVICE", "TIDK_GPUS_EXACT")}
+    r = subprocess.run([TIDK, "search", fa, "-s", "TTAGG", "-w", "7777", "-o", "s", "-d", out, "--gpus", "8", "--gpu-stats"],
+                       capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stderr
+    stats = json.loads([l for l in r.stderr.splitlines() if l.startswith("{")][-1])
+    assert stats["devices_used"] == 1
+    assert open(os.path.join(out, "s_telomeric_repeat_windows.tsv")).read() == O.search_text(ids, seqs, b"TTAGG", 7777)
