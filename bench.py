@@ -9,7 +9,9 @@ human-scale 3.1 Gb / 24-chromosome genome with N gaps.
           W, so no halo and no data-path collective): "scaling": "strong".  Every rank generates
           only the chromosomes its range touches.
 
-A "step" is PASSES (32) passes of the window counter over the resident genome, issued through the
+A "step" is P passes of the window counter over the resident genome (P >= 32, chosen before the warm-up so that a step
+lasts about 15 ms on the slowest rank -- 32 at N = 1, a few hundred on an eighth of the genome -- and identical on all
+ranks; TIDK_BENCH_PASSES fixes it), issued through the
 asynchronous entry point (tidk_cuda_window_counts_resident_async: the counts of pass i leave the device
 while pass i + 1 counts) and collected with tidk_cuda_wait at the end of the step, so the counts of every
 pass are in host memory when its step ends.  Passes are what makes the timed region long enough (>= 0.3 s
@@ -48,7 +50,8 @@ import numpy as np  # noqa: E402
 
 WINDOW = 10000
 QUERY = [b"TTAGGG"]
-PASSES = int(os.environ.get("TIDK_BENCH_PASSES", "32"))
+PASSES = int(os.environ.get("TIDK_BENCH_PASSES", "0"))  # 0: calibrated (>= 32, a step of about 15 ms)
+STEP_MS_TARGET = 15.0
 METRIC = "search_window_count_throughput"
 UNIT = "Gbases/s"
 SCALE = float(os.environ.get("TIDK_BENCH_SCALE", "1.0"))
@@ -349,7 +352,8 @@ def main():
     ncpu = os.cpu_count() or 1
 
     config = {"workload": "C4: tidk search --string TTAGGG --window 10000, synthetic 3.1 Gb / 24 chromosomes with N gaps",
-              "window": WINDOW, "queries": [q.decode() for q in QUERY], "passes_per_step": PASSES,
+              "window": WINDOW, "queries": [q.decode() for q in QUERY],
+              "passes_per_step": "calibrated per run: >= 32, a step of about 15 ms on the slowest rank (the line's passes_per_step)",
               "l2": "inputs (3.1 GB at N = 1, 386 MB per GPU at N = 8) larger than the 126 MB L2; no flush needed",
               "sharding": "contiguous window ranges of the one genome across ranks (long chromosomes cut at multiples of W), no collective"}
     if SCALE != 1.0:
@@ -409,10 +413,28 @@ def main():
     for o in outs:
         assert np.array_equal(o[0], f) and np.array_equal(o[1], r), "asynchronous counts differ from the blocking call"
 
-    def step():
-        for p in range(PASSES):
+    def run_passes(n):
+        for p in range(n):
             ctx.window_counts_resident_async(batch, WINDOW, QUERY, outs[p & 1])
         return ctx.wait()
+
+    # passes per step: enough for a step of about STEP_MS_TARGET on the slowest rank (the timed region of the default
+    # run then lasts >= 0.3 s at every N), the same number on every rank
+    passes = PASSES
+    if passes <= 0:
+        run_passes(8)
+        barrier()
+        t_c = time.perf_counter()
+        run_passes(32)
+        per_pass_ms = (time.perf_counter() - t_c) / 32 * 1e3
+        if dist is not None:
+            tc = torch.tensor([per_pass_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+            per_pass_ms = float(tc.item())
+        passes = int(min(2048, max(32, -(-STEP_MS_TARGET // per_pass_ms))))
+
+    def step():
+        return run_passes(passes)
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -427,7 +449,7 @@ def main():
         kernel_ms += ms
         launches += nl
         if os.environ.get("TIDK_BENCH_VERBOSE"):
-            print(f"step kernel ms per pass {ms / PASSES:.4f}", file=sys.stderr)
+            print(f"step kernel ms per pass {ms / passes:.4f}", file=sys.stderr)
     barrier()
     dt = time.perf_counter() - t0
     # nvidia-smi samples every 100 ms: keep the same step running (untimed) until the sampler has
@@ -539,7 +561,7 @@ def main():
         barrier()
 
     if rank == 0:
-        k_ms = kernel_ms / (steps * PASSES)  # max over ranks of the mean device time per pass
+        k_ms = kernel_ms / (steps * passes)  # max over ranks of the mean device time per pass
         per_gpu = total_bases / world
         achieved = per_gpu / (k_ms * 1e-3) / 1e9  # GB/s per GPU at 1 B per scanned base
         flat = planes_ready and os.environ.get("TIDK_FLAT", "1") != "0"
@@ -585,11 +607,12 @@ def main():
                             "restates tidk 0.2.7 (the Rust reference cannot be built here; the reference itself is single-threaded, search.rs:57)",
                   "all_windows_equal_to_gpu": bool(np.array_equal(cf, f) and np.array_equal(cr, r))}
         e2e_val = total_bases * e2e_steps / dt_e2e / 1e9
-        line = {"metric": METRIC, "value": total_bases * PASSES * steps / dt / 1e9, "unit": UNIT, "n_gpus": world,
+        line = {"metric": METRIC, "value": total_bases * passes * steps / dt / 1e9, "unit": UNIT, "n_gpus": world,
                 "steps": steps, "warmup": warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
-                "kernel_ms_per_pass": k_ms, "wall_ms_per_pass": dt / steps / PASSES * 1e3,
-                "wall_over_kernel": dt / steps / PASSES * 1e3 / k_ms,
+                "passes_per_step": passes, "timed_region_s": dt,
+                "kernel_ms_per_pass": k_ms, "wall_ms_per_pass": dt / steps / passes * 1e3,
+                "wall_over_kernel": dt / steps / passes * 1e3 / k_ms,
                 "kernel_only_value": total_bases / (k_ms * 1e-3) / 1e9,
                 "counts": {"fwd_total": fwd_total, "rev_total": rev_total}, "blocking_call": blocking, "clocks": clocks,
                 "e2e": {"value": e2e_val, "unit": UNIT,
