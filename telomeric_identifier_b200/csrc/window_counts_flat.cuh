@@ -168,6 +168,13 @@ window_counts_flat_kernel(const FlatJob job, const typename std::conditional<fla
         bool open = true; // a window is open (false behind the last record)
 
         const uint64_t span_pos = (job.span0 + span) * (uint64_t)kFlatSpanBases;
+        // the two boundaries as span-relative 32-bit numbers (the per-step tests are then single compares): nb = next
+        // boundary, "far" (beyond any span) when it lies outside; lb = last boundary, clamped well below any straddle zone
+        constexpr uint32_t kFar = 0x40000000u;
+        auto rel_next = [&](uint64_t b) { return b - span_pos < (uint64_t)kFar ? (uint32_t)(b - span_pos) : kFar; };
+        auto rel_last = [&](uint64_t b) { return b >= span_pos ? (int)rel_next(b) : (span_pos - b < 64 ? -(int)(span_pos - b) : -64); };
+        uint32_t nb = rel_next(next_b);
+        int lb = rel_last(last_b);
         const uint32_t valid_blocks = __ballot_sync(0xFFFFFFFFu, vb == 0xFFFFFFFFu); // bit b: block b of the span is all valid
         // look-behind across the span start: lane 31 holds the word in front of the span (loaded with the span's first step)
         uint32_t c_lo = n_c_lo, c_hi = n_c_hi, c_va = n_c_va;
@@ -251,18 +258,18 @@ window_counts_flat_kernel(const FlatJob job, const typename std::conditional<fla
             }
 
             // windows: the boundaries inside this step, in order
-            const uint64_t sb = span_pos + (uint64_t)st * kFlatStepBases;
-            const int lane_rel = lane * 128;
-            if (last_b + (uint64_t)(L - 1) > sb) { // the straddle zone of the last boundary reaches into this step
-                const int r0 = (int)(int64_t)(last_b - sb) - lane_rel; // (last_b may lie below sb: negative)
+            const int sb = (int)(st * kFlatStepBases); // span-relative position of the step
+            const int lane_rel = sb + lane * 128;
+            if (lb + (L - 1) > sb) { // the straddle zone of the last boundary reaches into this step
+                const int r0 = lb - lane_rel; // (the boundary may lie below the step: negative)
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const uint32_t keep = ~range_mask32(r0 - 32 * j, r0 - 32 * j + (L - 1));
                     mf[j] &= keep; mr[j] &= keep;
                 }
             }
-            while (next_b < sb + kFlatStepBases) {
-                const int r0 = (int)(next_b - sb) - lane_rel;
+            while (nb < (uint32_t)sb + kFlatStepBases) {
+                const int r0 = (int)nb - lane_rel;
                 uint32_t bf = 0, br = 0;
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
@@ -280,12 +287,13 @@ window_counts_flat_kernel(const FlatJob job, const typename std::conditional<fla
                 }
                 // the window that starts at next_b
                 last_b = next_b;
+                lb = (int)nb;
                 wi++;
                 if (wi < nwin_r) {
                     out++;
                 } else { // first window of the next record that has one
                     do { rec++; } while (rec < job.n_records && __ldg(job.rec_off + rec + 1) == __ldg(job.rec_off + rec));
-                    if (rec >= job.n_records) { open = false; next_b = ~0ull; break; }
+                    if (rec >= job.n_records) { open = false; next_b = ~0ull; nb = kFar; break; }
                     rec_end = __ldg(job.rec_off + rec + 1);
                     const uint64_t wb0 = __ldg(job.win_base + rec);
                     nwin_r = (uint32_t)(__ldg(job.win_base + rec + 1) - wb0);
@@ -293,6 +301,7 @@ window_counts_flat_kernel(const FlatJob job, const typename std::conditional<fla
                     wi = 0;
                 }
                 next_b = job.window < rec_end - last_b ? last_b + job.window : rec_end;
+                nb = rel_next(next_b);
             }
 #pragma unroll
             for (int j = 0; j < 4; j++) { cf += __popc(mf[j]); cr += __popc(mr[j]); }
