@@ -70,14 +70,34 @@ __global__ void __launch_bounds__(256) vt_items_kernel(const uint64_t *base /* [
     }
 }
 
-// Shared memory of a CTA (dynamic): per warp two staging buffers (the horizontal words of 32 tiles: 33 words x 2 planes
-// each; the buffer of the tile in work becomes the E stash once its words are in registers, the other one receives
-// the next tiles' words by cp.async meanwhile) and the event buffer; one chunk-end mask table.
+// Shared memory of a CTA (dynamic), per warp: a staging buffer for the horizontal plane words of the item's 32 tiles, a stash
+// for the E words of the k in work, the event buffer (and, in the cp.async build, a second staging buffer: there the buffer
+// of the item in work doubles as the stash); one chunk-end mask table per CTA.
+#ifndef TIDK_V_TMA
+#define TIDK_V_TMA 1 // staging by bulk copies (TMA), one per run of tiles of a slice; 0: four-byte cp.async, row by row
+#endif
+#if TIDK_V_TMA
+// TMA variant: ONE staging buffer per warp, filled by bulk copies (cp.async.bulk), one per RUN of tiles of the same slice and
+// plane: consecutive tiles of a slice start 30 words apart, so the tiles of one slice in a warp's item are one contiguous
+// stretch of each plane.  The run that starts in lane h lands 40 h words into the plane's half of the buffer (a run of n
+// tiles needs at most 30 n + 8 words); completion is counted on the warp's mbarrier.  A separate 4 KB stash for the E words.
+constexpr uint32_t kVRunSlot = 40;                 // words per lane slot: 160 bytes, a multiple of 16
+constexpr uint32_t kVPlaneWords = 32 * kVRunSlot;  // one plane's half of the staging buffer
+constexpr uint32_t kVStageWords = 2 * kVPlaneWords;
+struct __align__(16) VWarpShared {
+    uint32_t stage[1][kVStageWords];
+    uint4 stash[8 * 32];
+    unsigned long long ev[kVEvBuf];
+    unsigned long long mbar;
+    unsigned long long pad;
+};
+#else
 constexpr uint32_t kVStageWords = 2 * 32 * 33;
 struct __align__(16) VWarpShared {
     uint32_t stage[2][kVStageWords];
     unsigned long long ev[kVEvBuf];
 };
+#endif
 struct __align__(16) VShared {
     VWarpShared w[kVWarps];
     uint32_t mask[kVMaskWords];
@@ -197,6 +217,61 @@ __device__ __forceinline__ void vt_stage_async(const uint32_t *planes, uint32_t 
     asm volatile("cp.async.ca.shared.global [%0], [%1+%2], 4;" ::"r"(s_hi + off), "l"(p), "n"(kPackWords * 4u) : "memory");
 }
 
+#if TIDK_V_TMA
+// One bulk copy (TMA) of `bytes` (a multiple of 16) from global to shared memory, completion counted on `mbar`.
+__device__ __forceinline__ void vt_bulk(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+// Stages the plane words of the warp's 32 tiles run by run.  slice / wa / valid: this lane's tile (valid lanes are a prefix of
+// the warp; the tiles of a slice sit in consecutive lanes, 30 words apart).  Returns the word offset of this lane's row in a
+// plane's half of the buffer (its 33 words start there).
+__device__ __forceinline__ uint32_t vt_stage_tma(const uint32_t *planes, uint32_t slice, uint32_t wa, bool valid, uint32_t *stage,
+                                                 uint32_t mbar, int lane) {
+    const uint32_t prev_slice = __shfl_up_sync(0xFFFFFFFFu, slice, 1);
+    const uint32_t vm = __ballot_sync(0xFFFFFFFFu, valid);
+    const uint32_t heads = __ballot_sync(0xFFFFFFFFu, valid && (lane == 0 || slice != prev_slice));
+    const uint32_t n_valid = (uint32_t)__popc(vm);
+    // my run: head lane h, and (for heads) its length
+    const uint32_t below = heads & (0xFFFFFFFFu >> (31 - lane));          // heads at or below this lane
+    const uint32_t h = below ? 31u - (uint32_t)__clz((int)below) : 0u;
+    const uint32_t above = lane < 31 ? heads & (0xFFFFFFFEu << lane) : 0u; // heads above this lane
+    const uint32_t run_end = above ? (uint32_t)__ffs((int)above) - 1u : n_valid;
+    const uint32_t wa_h = __shfl_sync(0xFFFFFFFFu, wa, (int)h);
+    const bool head = valid && h == (uint32_t)lane;
+    uint32_t words = 0;
+    if (head) words = ((wa & 3u) + 30u * (run_end - (uint32_t)lane - 1u) + 33u + 3u) & ~3u;
+    const uint32_t total = __reduce_add_sync(0xFFFFFFFFu, words);
+    if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(total * 8u) : "memory"); // two planes
+    __syncwarp();
+    if (head) {
+        const uint32_t a4 = wa & ~3u;
+        const uint32_t *src = plane_word_ptr(planes, (uint64_t)a4);
+        const uint32_t left = kPackWords - (a4 & (kPackWords - 1u)); // words of this chunk from a4 on: a multiple of 4, >= 4
+        const uint32_t n1 = left < words ? left : words, n2 = words - n1;
+        const uint32_t d_lo = (uint32_t)__cvta_generic_to_shared(stage) + (uint32_t)lane * kVRunSlot * 4u, d_hi = d_lo + kVPlaneWords * 4u;
+        vt_bulk(d_lo, src, n1 * 4u, mbar);
+        vt_bulk(d_hi, src + kPackWords, n1 * 4u, mbar);
+        if (n2) { // the run crosses the end of its 4 MiB chunk of the plane layout: the next chunk's lo part starts 2 * kPackWords on
+            const uint32_t *src2 = src + left + 2u * kPackWords;
+            vt_bulk(d_lo + n1 * 4u, src2, n2 * 4u, mbar);
+            vt_bulk(d_hi + n1 * 4u, src2 + kPackWords, n2 * 4u, mbar);
+        }
+    }
+    return kVRunSlot * h + (wa_h & 3u) + 30u * ((uint32_t)lane - h);
+}
+// wait for the phase with the given parity (bounded: a wrong byte count must not hang the device -- the results would be wrong
+// and the parity tests would say so)
+__device__ __forceinline__ void vt_mbar_wait(uint32_t mbar, uint32_t parity) {
+    for (uint32_t spin = 0; spin < (1u << 24); spin++) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+        if (ok) return;
+    }
+}
+#endif
+
 // KMIN > 0: the k range is a compile-time constant; KMIN == 0: run-time range (job.kmin .. job.kmax, <= kVMaxK).
 #ifndef TIDK_V_MINB
 #define TIDK_V_MINB 3
@@ -206,9 +281,21 @@ __global__ void __launch_bounds__(kVWarps * 32, TIDK_V_MINB) explore_vertical_ke
     extern __shared__ __align__(16) unsigned char vt_smem[];
     VShared &sh = *reinterpret_cast<VShared *>(vt_smem);
     for (uint32_t e = threadIdx.x; e < kVMaskWords; e += blockDim.x) sh.mask[e] = c_vt_mask.w[e];
+#if TIDK_V_TMA
+    if ((threadIdx.x & 31) == 0) {
+        const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&sh.w[threadIdx.x >> 5].mbar);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the barrier is used by the async proxy (bulk copies)
+    }
+#endif
     __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     VWarpShared &ws = sh.w[wid];
+#if TIDK_V_TMA
+    const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&ws.mbar);
+    uint32_t mb_parity = 0, row_off = 0, row_off_next = 0;
+#endif
     unsigned long long *const evbuf = ws.ev;
     const uint32_t k0 = KMIN > 0 ? KMIN : job.kmin, k1 = KMIN > 0 ? KMAX : job.kmax;
 
@@ -220,8 +307,13 @@ __global__ void __launch_bounds__(kVWarps * 32, TIDK_V_MINB) explore_vertical_ke
     const uint64_t n_warps = (uint64_t)gridDim.x * kVWarps;
     uint64_t item = (uint64_t)blockIdx.x * kVWarps + wid, item_next = item + n_warps;
     VDesc cur = vt_desc(job, item, lane);
+#if TIDK_V_TMA
+    if (item < n_items)
+        row_off = vt_stage_tma(job.planes, cur.d.slice, (uint32_t)((cur.sd.beg + (uint64_t)kVStep * cur.d.t) >> 5), cur.valid, ws.stage[0], mbar, lane);
+#else
     if (item < n_items) vt_stage_async(job.planes, (uint32_t)((cur.sd.beg + (uint64_t)kVStep * cur.d.t) >> 5), ws.stage[0], lane);
     asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
     VDesc nxt = vt_desc(job, item_next < n_items ? item_next : n_items, lane);
     uint32_t buf = 0;
 #if TIDK_V_SYNC
@@ -234,10 +326,15 @@ __global__ void __launch_bounds__(kVWarps * 32, TIDK_V_MINB) explore_vertical_ke
 #endif
         uint32_t ticket = 0;
         if (lane == 0) asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(ticket) : "l"(job.work_counter) : "memory");
+#if TIDK_V_TMA
+        uint32_t *const stage = ws.stage[0];
+        uint4 *const stash_lane = ws.stash + lane;
+#else
         uint32_t *const stage = ws.stage[buf];
         uint4 *const stash_lane = reinterpret_cast<uint4 *>(stage) + lane;
         if (item_next < n_items) vt_stage_async(job.planes, (uint32_t)((nxt.sd.beg + (uint64_t)kVStep * nxt.d.t) >> 5), ws.stage[buf ^ 1], lane);
         asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
 
         const VTile d = cur.d;
         const SliceDesc sd = cur.sd;
@@ -258,6 +355,25 @@ __global__ void __launch_bounds__(kVWarps * 32, TIDK_V_MINB) explore_vertical_ke
         }
         // this item's words have arrived (all but the group just committed are complete); each lane takes its own
         // 33 + 33, shifted to the tile's first base
+#if TIDK_V_TMA
+        vt_mbar_wait(mbar, mb_parity);
+        mb_parity ^= 1u;
+        uint32_t lo[32], hi[32];
+        {
+            const uint32_t *sl = stage + row_off, *sh2 = stage + kVPlaneWords + row_off; // (rows of a run are 30 words apart: two-way bank conflicts)
+            uint32_t pl = sl[0], ph = sh2[0];
+#pragma unroll
+            for (int b = 0; b < 32; b++) {
+                const uint32_t nl = sl[b + 1], nh = sh2[b + 1];
+                lo[b] = __funnelshift_r(pl, nl, sft);
+                hi[b] = __funnelshift_r(ph, nh, sft);
+                pl = nl; ph = nh;
+            }
+        }
+        __syncwarp(); // every lane has its rows in registers: the staging buffer takes the next item's
+        if (item_next < n_items)
+            row_off_next = vt_stage_tma(job.planes, nxt.d.slice, (uint32_t)((nxt.sd.beg + (uint64_t)kVStep * nxt.d.t) >> 5), nxt.valid, ws.stage[0], mbar, lane);
+#else
         asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncwarp();
         uint32_t lo[32], hi[32];
@@ -273,6 +389,7 @@ __global__ void __launch_bounds__(kVWarps * 32, TIDK_V_MINB) explore_vertical_ke
             }
         }
         __syncwarp(); // the staging buffer becomes the stash
+#endif
         const uint32_t h0 = lo[0] | hi[0];
         vt_transpose32(lo);
         vt_transpose32(hi);
@@ -380,13 +497,18 @@ __global__ void __launch_bounds__(kVWarps * 32, TIDK_V_MINB) explore_vertical_ke
             }
         }
         __syncwarp();
+#if TIDK_V_TMA
+        row_off = row_off_next;
+#endif
         item = item_next;
         item_next = item_after;
         cur = nxt;
         nxt = aft;
         buf ^= 1;
     }
+#if !TIDK_V_TMA
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
 }
 
 } // namespace tidk
