@@ -253,7 +253,7 @@ def explore_block(ctx, peak):
         out[name] = {"scan_kernel_ms": best[0], "post_ms": best[1], "resident_call_wall_ms": best[2] * 1e3, "runs": int(r.size),
                      "scan_gbases_per_s": ach,
                      "roofline": {"bound": "instruction fetch / alu pipe, not hbm (0.26 B per base cross HBM): see DESIGN.md 3.3",
-                                  "frac_of_alu_pipe_ncu": 0.49 if name == "k5_12" else 0.56, "issue_slots_busy_ncu": 0.39 if name == "k5_12" else 0.51,
+                                  "frac_of_alu_pipe_ncu": 0.51 if name == "k5_12" else 0.58, "issue_slots_busy_ncu": 0.39 if name == "k5_12" else 0.47,
                                   "ncu": "profiles/r02_ncu_full_prof_r02.json (top stall no_instruction 2.5 per issue for k = 5..12)",
                                   "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "algorithmic_bytes_per_launch": scanned},
                      "all_kernels": {"ms": all_ms, "achieved": scanned / (all_ms * 1e-3) / 1e9, "frac": scanned / (all_ms * 1e-3) / 1e9 / peak,
